@@ -1,0 +1,344 @@
+#!/usr/bin/env python3
+"""Benchmark of the NEM partitioning hot path (BASELINE.json metric: NEM EM iterations/sec vs the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--families F] [--genomes G]
+
+Workload (config.workload): BASELINE.json configs[4] -- synthetic 50 000 genomes x 200 000 families, one un-chunked
+NEM instance (K = 3, beta = 2.5, dispersion "sk_"), row-sharded over the N GPUs (strong scaling: the pangenome is
+fixed, every rank holds N_fam / N rows).  It is the configuration the metric is quoted on ("at 1/2/4/8 B200") and
+fits one GPU (1.25 GB of bits).  A *step* is one EM iteration: M-step (column statistics of the bit matrix -> centres,
+dispersions, proportions), E-step (log-densities of every family, then the level-scheduled Gauss-Seidel posterior
+sweep) and the convergence read-back.  The matrix is 10x larger than L2, so no L2 flush is needed between steps.
+
+`value`  : EM iterations / s with the matrix resident in HBM (max over ranks of the CUDA-event time of K steps).
+`e2e`    : the same metric through the host-buffer C-ABI call `nemb200_nem_host` (pinned host matrix -> H2D -> EM to
+           convergence -> posteriors D2H), i.e. what a caller of `run_partitioning` pays per instance.
+`roofline`: the dominant kernel of a step, algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the reference's own C (oracle/_ref/libnem_ref.so, unmodified NEM 1.08 sources)
+           on a bounded row sample of the same matrix, one process per host core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+K_CLASSES = 3
+BETA = 2.5
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--families", type=int, default=200_000)
+    ap.add_argument("--genomes", type=int, default=50_000)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--cpu-sample-rows", type=int, default=400)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.is_file():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+
+
+def b_iter_bytes(N, D, K, nnz):
+    """algorithmic bytes of one EM iteration (matrix counted once)."""
+    return N * ((D + 7) // 8) + 2 * N * K * 4 + (N + 1) * 4 + nnz * 8 + nnz * K * 4 + 3 * K * D * 4
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def _ref_worker(args):
+    """One host process: the unmodified reference C on a row sample, through its file interface."""
+    X, rowptr, col, w, K, beta, workdir = args
+    from oracle import refnem
+    import tempfile
+    d = Path(tempfile.mkdtemp(dir=workdir))
+    N, D = X.shape
+    w_text = [repr(round(float(v), 4)) for v in w]
+    refnem.write_nem_files(d, X, refnem.csr_to_nei_lists(N, rowptr, col, w_text))
+    refnem.write_init_file(d, K, D)
+    t = time.time()
+    rc = refnem.ref_nem_call(d, K, float(np.float32(beta)), False, 100)
+    dt = time.time() - t
+    out = refnem.parse_ref_outputs(d, K, D)
+    n_iter = out["n_iter"] if out and out["n_iter"] else 1
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+    return n_iter, dt, rc
+
+
+def _port_worker(args):
+    X, rowptr, col, w, K, beta, workdir = args
+    from oracle import refnem
+    t = time.time()
+    o = refnem.oracle_nem_run(X, rowptr, col, w, K, beta, False, 100, mode=refnem.FP64)
+    return max(o["n_iter"], 1), time.time() - t, o["status"]
+
+
+def cpu_reference_run(N_full, D, rows, seed, K, beta, cores, repeats=1):
+    """EM it/s of the CPU reference on `rows` sampled families x D genomes per core, scaled to the full family count."""
+    from oracle import refnem
+    from multiprocessing import get_context
+    from ppanggolin_b200.synthetic import _family_probs
+    kind = "reference" if refnem.have_ref() else "port"
+    if kind == "port":
+        refnem.build(ref=False)
+    rng = np.random.default_rng(seed + 1)
+    cls, p = _family_probs(rows * cores, rng)
+    jobs = []
+    workdir = os.environ.get("TMPDIR", "/tmp")
+    for c in range(cores):
+        pc = p[c * rows:(c + 1) * rows]
+        X = (rng.random((rows, D)) < pc[:, None]).astype(np.uint8)
+        X[X.sum(1) == 0, 0] = 1
+        # chain neighbourhood of the sample (each family linked to the next one), weights ~ joint presence
+        col = []; w = []; rowptr = [0]
+        for i in range(rows):
+            for j in (i - 1, i + 1):
+                if 0 <= j < rows:
+                    col.append(j); w.append(round(float(pc[i] * pc[j]), 4) or 0.0001)
+            rowptr.append(len(col))
+        ew = sum(w) / 2
+        jobs.append((X, np.array(rowptr, np.int32), np.array(col, np.int32), np.array(w, np.float32), K,
+                     beta * rows / ew, workdir))
+    fn = _ref_worker if kind == "reference" else _port_worker
+    t0 = time.time()
+    with get_context("fork").Pool(cores) as pool:
+        res = pool.map(fn, jobs)
+    wall = time.time() - t0
+    # aggregate: every core finished n_iter iterations over `rows` families in its own nem() time
+    its = sum(n / dt for n, dt, _ in res)                 # sample-size iterations / s over all cores
+    full_its = its * rows / N_full                         # the same work rate expressed in full-matrix iterations / s
+    return {"value": full_its, "unit": "EM iterations/s", "cores": cores, "kind": kind,
+            "sample": f"{cores} x ({rows} families x {D} genomes, K={K}), linear extrapolation to {N_full} families; "
+                      f"nem() time only (text export excluded); iterations={[r[0] for r in res]}",
+            "wall_s": wall}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    cores = min(cores, 32)
+    vals = []
+    t0 = time.time()
+    total = a.warmup + a.steps
+    budget_s = 240.0
+    rows = a.cpu_sample_rows
+    for s in range(total):
+        r = cpu_reference_run(a.families, a.genomes, rows, a.seed + s, K_CLASSES, BETA, cores)
+        if s >= a.warmup:
+            vals.append(r)
+        if time.time() - t0 > budget_s and vals:
+            break
+    v = float(np.mean([r["value"] for r in vals]))
+    line = {"metric": "NEM EM iterations/sec", "value": v, "unit": "EM iterations/s", "impl": "reference",
+            "n_gpus": a.gpus, "steps": len(vals), "warmup": a.warmup, "ms_per_step": 1000.0 / v if v > 0 else None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64 (reference C)",
+            "data": "synthetic", "config": workload_config(a),
+            "cpu_baseline": {"value": v, "unit": "EM iterations/s", "cores": vals[-1]["cores"], "kind": vals[-1]["kind"],
+                             "sample": vals[-1]["sample"]},
+            "e2e": {"value": v, "unit": "EM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a):
+    return {"workload": f"cfg5: synthetic {a.genomes} genomes x {a.families} families, one un-chunked NEM instance, "
+                        f"K={K_CLASSES}, beta={BETA}, dispersion sk_, Gauss-Seidel sweep, log-space epilogue, "
+                        f"row-sharded over the GPUs", "families": a.families, "genomes": a.genomes, "K": K_CLASSES,
+            "beta": BETA, "l2_policy": "matrix (families x genomes bits) is larger than L2; no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from ppanggolin_b200.nem import engine
+    from ppanggolin_b200.nem.sharded import CudaBackend, ShardedEM, shard_rows
+    from ppanggolin_b200.synthetic import synth_pangenome_large
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    N, D, K = a.families, a.genomes, K_CLASSES
+    lo, hi = shard_rows(N, world, rank)
+
+    # synthetic pangenome: every rank generates the same full graph (tiny) and its own rows of the matrix
+    sp = synth_pangenome_large(N, D, a.seed, device=dev, rows=(lo, hi))
+    beta = float(np.float32(sp.beta_eff(BETA)))
+    graph = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), D, sp.rowptr, sp.col, sp.w, device=dev)
+    nnz = int(len(sp.col))
+    be = CudaBackend(sp.bits, D, N, K, False, engine.EPI_LOGSPACE, graph)
+    em = ShardedEM(be, N, K, rank, world, group)
+    em.start(beta)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=group)
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        em.iterate(beta)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    be.launches = 0
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
+    st = torch.cuda.current_stream()
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record(st)
+    statuses = []
+    for s in range(a.steps):
+        e = ev[s]
+        e[0].record(st)
+        be.accumulate(be.T[em.cur][em.lo:em.hi]); e[1].record(st)
+        em._allreduce_stats(); be.finalize(); e[2].record(st)
+        be.density(be.logf_full[em.lo:em.hi]); e[3].record(st)
+        em._allgather_logf(); be.sweep(be.T[em.cur], be.T[1 - em.cur], beta); em.cur = 1 - em.cur; e[4].record(st)
+        statuses.append(be.read_flags())
+    t_end.record(st)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = t_start.elapsed_time(t_end)
+    stage = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in ev])  # accumulate, finalize, density, sweep
+    launches = be.launches
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        ms_total = float(t.item())
+    value = a.steps / (ms_total / 1000.0)
+
+    # correctness guard inside the bench: labels must recover the generator's classes
+    lab, _ = engine.labels_device(be.T[em.cur])
+    truth = torch.from_numpy(sp.true_class.astype(np.int32)).to(dev)
+    acc = float((lab == truth).float().mean().item())
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        st_mean = stage.mean(0)
+        names = ["mstep_accumulate (k_mstep_onehot + classify/scatter/fuzzy)", "mstep_finalize", "density (k_density_sk)",
+                 "sweep (k_sweep, level-scheduled)"]
+        n_loc = hi - lo
+        x_bytes = n_loc * ((D + 7) // 8)
+        alg = {0: x_bytes + n_loc * K * 4 + n_loc * 4 + K * D * 4,          # matrix + posteriors + row->class + counts out
+               2: x_bytes + n_loc * K * 8 + 2 * K * ((D + 7) // 8)}         # matrix + log-densities out + centre planes
+        dom = int(np.argmax(st_mean))
+        if dom not in alg:
+            dom = 2 if st_mean[2] >= st_mean[0] else 0
+        achieved = alg[dom] / (st_mean[dom] / 1000.0) / 1e9
+        biter = b_iter_bytes(N, D, K, nnz)
+        line = {"metric": "NEM EM iterations/sec", "value": value, "unit": "EM iterations/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit ops + f64 epilogue", "data": "synthetic",
+                "config": workload_config(a), "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": float(st_mean[dom]),
+                             "stage_ms": {n: float(v) for n, v in zip(names, st_mean)},
+                             "iteration": {"B_iter_bytes": biter, "achieved_GBs": biter / (ms_total / a.steps / 1000.0) / 1e9,
+                                           "frac": biter / (ms_total / a.steps / 1000.0) / 1e9 / (peak * world)}},
+                "check": {"label_accuracy_vs_generator": acc, "gs_levels": graph.n_levels, "nnz": nnz,
+                          "last_maxdiff": statuses[-1][0], "status": statuses[-1][1]}}
+    # ---- end to end through the host-buffer C ABI (rank 0's shard when N > 1: every rank would do the same)
+    if not a.no_e2e and world == 1:
+        host_bits = torch.empty(sp.bits.shape, dtype=torch.int32, pin_memory=True)
+        host_bits.copy_(sp.bits)
+        torch.cuda.synchronize()
+        hb = host_bits.numpy().view(np.uint32)
+        del be, em
+        sp.bits = None
+        torch.cuda.empty_cache()
+        t0 = time.perf_counter()
+        run = engine.nem_run_host(hb, D, sp.rowptr, sp.col, sp.w, K, beta, False, 100, 0.01, engine.EPI_LOGSPACE)
+        dt = time.perf_counter() - t0
+        its = max(run.n_iter, 1)
+        line["e2e"] = {"value": its / dt, "unit": "EM iterations/s", "h2d_bytes_per_step": int(hb.nbytes + sp.col.nbytes * 2 + sp.rowptr.nbytes) // its,
+                       "d2h_bytes_per_step": int(N * K * 4 + 2 * K * D * 4) // its, "iterations": its, "wall_s": dt,
+                       "em_device_ms": run.elapsed_ms, "converged": run.converged,
+                       "call": "nemb200_nem_host (pinned host matrix -> H2D -> EM to convergence -> posteriors D2H)"}
+    elif rank == 0:
+        line["e2e"] = None
+    if rank == 0 and not a.no_cpu:
+        cores = min(os.cpu_count() or 1, 32)
+        try:
+            cb = cpu_reference_run(N, D, a.cpu_sample_rows, a.seed, K, BETA, cores)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:  # the baseline must not take the GPU numbers down with it
+            line["cpu_baseline"] = {"value": None, "unit": "EM iterations/s", "cores": cores, "kind": "unavailable", "sample": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(group=group)
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)

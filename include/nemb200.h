@@ -1,0 +1,141 @@
+/*
+ * nemb200.h -- C ABI of the B200-native NEM partitioning path (libnemb200.so, sm_100a only).
+ *
+ * Drop-in boundary.  In the reference the only native entry point on this path is
+ *     int nem(const char* Fname, int nk, const char* algo, float beta, const char* convergence, float convergence_th,
+ *             const char* format, int it_max, int dolog, const char* model_family, const char* proportion,
+ *             const char* dispersion, int init_mode, const char* init_file, const char* out_file_prefix, int seed)
+ * (/root/reference/ppanggolin/nem/NEM/nem_exe.h:23-38, bound by NEM/nem_stats.pyx:1-17, called from
+ * ppanggolin/nem/partition.py:126-150) and every operand travels through text files (partition.py:344-436 writes
+ * .str/.dat/.nei/.index, :65-85 writes the init .m, :170-231 parses .uf/.mf).  The entry points below replace that
+ * call with the same operands passed in memory:
+ *     .dat  -> `bits`   bit-packed presence matrix (families x genomes)
+ *     .nei  -> `rowptr/col/w`  CSR neighbour lists with contiguity weights, as nem_exe.c:1347-1483 keeps them
+ *     .m    -> built on the device from K and D (partition.py:65-85 is a pure function of K, D)
+ *     .uf   -> `T`      posteriors (float32, N x K);  .mf -> `crit`, `mu`, `eps`, `pk`
+ * nem()'s constant arguments in PPanGGOLiN (algo "nem", convergence "clas", format "fuzzy", family "bern",
+ * proportion "pk", init_mode 2) are the only supported configuration and are therefore not parameters;
+ * dispersion "sk_"/"skd" is `free_disp`; `seed` has no effect on this path.
+ *
+ * Conventions: plain pointers and sizes, no torch types.  Matrix layout: row-major uint32 words, bit b of word w of a
+ * row is genome column 32*w+b; `row_stride_words` is a multiple of 4 (rows start 16-byte aligned) and padding bits
+ * are zero.  All functions return NEMB200_OK (0) or a negative error; nemb200_last_error() gives the message of the
+ * calling thread's last failure.  A run whose EM hits an empty class reports it in result->status (the reference
+ * then writes no .uf and partition.py:233-265 returns ({}, None, None)); that is not an API error.
+ * There is no CPU fallback: without a CUDA device every compute entry fails with NEMB200_ERR_CUDA.
+ */
+#ifndef NEMB200_H
+#define NEMB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEMB200_ABI_VERSION 1
+#define NEMB200_MAX_K 32
+
+enum { NEMB200_OK = 0, NEMB200_ERR_ARG = -1, NEMB200_ERR_CUDA = -2, NEMB200_ERR_NOMEM = -3 };
+
+/* result->status: what the reference's StatusET would have been (nem_exe.c:642-708) */
+enum { NEMB200_STS_OK = 0, NEMB200_STS_EMPTYCLASS = 1, NEMB200_STS_INFINITE = 2 };
+
+/* flags */
+enum {
+  NEMB200_EPI_REF      = 0,      /* E-step epilogue with the reference's arithmetic: float32 log-density, double
+                                    exp() that may underflow, S==0 -> 1/K (nem_alg.c:2660-2698)                  */
+  NEMB200_EPI_LOGSPACE = 1 << 0, /* log-sum-exp epilogue: valid for any number of genomes */
+  NEMB200_JACOBI       = 1 << 1  /* parallel posterior update instead of the reference's in-place Gauss-Seidel
+                                    sweep (nem_alg.c:2459-2464); off by default                                  */
+};
+
+typedef struct nemb200_result {
+  double  crit[5];    /* U, D, L, M, Z  (.mf line 3, nem_exe.c:1713-1717); partition.py:187 reads crit[3] */
+  int32_t n_iter;     /* EM iterations executed (".stderr": "NEM converged after n iterations") */
+  int32_t converged;
+  int32_t status;     /* NEMB200_STS_* */
+  int32_t n_levels;   /* depth of the Gauss-Seidel level schedule that was used */
+  float   elapsed_ms; /* device time of the EM loop (CUDA events), excluding copies */
+} nemb200_result;
+
+int         nemb200_abi_version(void);
+const char* nemb200_last_error(void);
+int         nemb200_device_count(void);
+
+/* ---- whole-run entry points (replace nem(), nem_exe.h:23-38) ------------------------------------------------- */
+
+/* Host buffers in, host buffers out; host<->device copies happen inside.  T_out: N*K, mu_out/eps_out: K*D,
+ * pk_out: K (any may be NULL). */
+int nemb200_nem_host(const uint32_t* bits, int64_t N, int64_t D, int64_t row_stride_words,
+                     const int32_t* rowptr, const int32_t* col, const float* w,
+                     int32_t K, float beta, int32_t free_disp, int32_t itermax, float cv_th, uint32_t flags,
+                     float* T_out, float* mu_out, float* eps_out, float* pk_out, nemb200_result* result);
+
+/* Same with the matrix, CSR and outputs resident in device memory (device pointers); runs on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream).  rowptr/col/w may be NULL when beta == 0.
+ * `sched_*`: Gauss-Seidel level schedule in device memory from nemb200_gs_schedule (may be NULL when beta == 0 or
+ * NEMB200_JACOBI is set). */
+int nemb200_nem_device(const uint32_t* bits, int64_t N, int64_t D, int64_t row_stride_words,
+                       const int32_t* rowptr, const int32_t* col, const float* w,
+                       const int32_t* sched_level_ptr, const int32_t* sched_rows, int32_t n_levels,
+                       int32_t K, float beta, int32_t free_disp, int32_t itermax, float cv_th, uint32_t flags,
+                       float* T_out, float* mu_out, float* eps_out, float* pk_out, nemb200_result* result,
+                       void* stream);
+
+/* Host helper: level schedule of the in-place sweep.  level(i) = 1 + max level(j) over neighbours j < i, so rows of one
+ * level can be updated concurrently and still read exactly the values the sequential sweep 0..N-1 would (neighbours
+ * j < i already updated, j >= i not yet; nem_alg.c:2441-2476).  level_ptr_out: N+1 ints (only n_levels+1 used),
+ * rows_out: N ints.  Returns n_levels (>= 1) or a negative error. */
+int nemb200_gs_schedule(int64_t N, const int32_t* rowptr, const int32_t* col, int32_t* level_ptr_out, int32_t* rows_out);
+
+/* ---- stepwise entry points (device pointers): used by the row-sharded multi-GPU driver and by the parity tests -- */
+
+typedef struct nemb200_plan nemb200_plan; /* opaque: device workspace for one (N rows on this rank, D, K) shape */
+
+int  nemb200_plan_create(nemb200_plan** plan, int64_t N_local, int64_t N_total, int64_t D, int64_t row_stride_words,
+                         int32_t K, int32_t free_disp, uint32_t flags);
+void nemb200_plan_destroy(nemb200_plan* plan);
+
+/* partition.py:65-85 + nem_exe.c:1023-1040: initial pk/mu/eps for (K, D), written into the plan's parameter block. */
+int nemb200_init_params(nemb200_plan* plan, void* stream);
+
+/* M-step, part 1 (nem_mod.c:1270-1312, :1641-1699 restated as column sums): accumulate this rank's sufficient
+ * statistics from posteriors T (N_local x K, device).  Outputs live in the plan; nemb200_stats_ptrs exposes them so a
+ * multi-GPU driver can all-reduce them in place: cnt = int32[K][Dpad] one-hot column counts,
+ * fsum = double[K][Dpad] fuzzy column sums, nk_cnt = int64-free int32[K], nk_fz = double[K]. */
+int nemb200_mstep_accumulate(nemb200_plan* plan, const uint32_t* bits, const float* T, void* stream);
+int nemb200_stats_ptrs(nemb200_plan* plan, int32_t** cnt, double** fsum, int32_t** nk_cnt, double** nk_fz, int64_t* Dpad);
+
+/* M-step, part 2 (nem_mod.c:1317-1474 median, :1020-1076 / :1131-1170 dispersion, :455-459 proportions): parameters
+ * from (all-reduced) statistics.  Sets the plan's status word to NEMB200_STS_EMPTYCLASS when a class is empty. */
+int nemb200_mstep_finalize(nemb200_plan* plan, void* stream);
+
+/* E-step, part 1 (nem_mod.c:618-689 + nem_alg.c:2319-2374): log f_k(x_i) for this rank's rows -> logf (N_local x K
+ * doubles, device; -inf encodes the reference's null density). */
+int nemb200_density(nemb200_plan* plan, const uint32_t* bits, double* logf, void* stream);
+
+/* E-step, part 2 (nem_alg.c:2412-2489, :2630-2701): posterior sweep over rows [0, N) of logf/T (full-length arrays),
+ * reading T_old and writing T_new; maxdiff_bits receives max |T_new - T_old| as float bits (atomicMax).
+ * beta_now lets the caller run the "blind" beta = 0 pass of nem_alg.c:2043-2050. */
+int nemb200_sweep(nemb200_plan* plan, int64_t N, const double* logf, const float* T_old, float* T_new,
+                  const int32_t* rowptr, const int32_t* col, const float* w,
+                  const int32_t* sched_level_ptr, const int32_t* sched_rows, int32_t n_levels,
+                  float beta_now, uint32_t* maxdiff_bits, void* stream);
+
+/* nem_alg.c:2764-2843: criteria U, D, L, M, Z for final posteriors T (host output, synchronises the stream). */
+int nemb200_criteria(nemb200_plan* plan, int64_t N, const double* logf, const float* T,
+                     const int32_t* rowptr, const int32_t* col, const float* w, float beta, double crit_out[5],
+                     void* stream);
+
+/* Copy the plan's current parameters / status to host buffers (mu, eps: K*D; pk: K; any may be NULL). */
+int nemb200_get_params(nemb200_plan* plan, float* mu, float* eps, float* pk, int32_t* status, void* stream);
+
+/* partition.py:206-231 on the "%5.3f" text of nem_exe.c:1682, on the device: labels[i] = class 0..K-1, or -1 for "S_"
+ * (tie or max < 0.5); *entropy = sum p ln p over the 3-decimal posteriors (partition.py:212-220).  T: device. */
+int nemb200_labels(const float* T, int64_t N, int32_t K, int32_t* labels_dev, double* entropy_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEMB200_H */

@@ -1,0 +1,558 @@
+// nemb200.cu -- C ABI (include/nemb200.h) and host-side EM driver of the B200-native NEM path.
+//
+// Host control flow restates /root/reference/ppanggolin/nem/NEM/nem_alg.c:1174-1193 (INIT_PARAM_FILE start:
+// densities from the initial parameters, a "blind" beta = 0 sweep, then a sweep with beta) and :1783-1938 (NemAlgo:
+// M-step from the previous posteriors, E-step, convergence on max |c - c_old| < threshold).  All arithmetic is in the
+// kernels (nemb200_kernels.cuh); the host only sequences launches and reads back two words per iteration.
+#include "../../include/nemb200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nemb200_kernels.cuh"
+
+using namespace nemb200;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      return fail(e_ == cudaErrorMemoryAllocation ? NEMB200_ERR_NOMEM : NEMB200_ERR_CUDA, "%s:%d %s: %s", \
+                  __FILE__, __LINE__, #call, cudaGetErrorString(e_));                                 \
+  } while (0)
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+    g_num_sms = p.multiProcessorCount;
+  }
+  return g_num_sms;
+}
+
+struct nemb200_plan {
+  long long N_local = 0, N_total = 0;
+  int D = 0, Ws = 0, Dpad = 0, K = 0, free_disp = 0;
+  uint32_t flags = 0;
+  Params P{};
+  // statistics
+  int* cnt = nullptr;       // [K][Dpad]
+  double* fsum = nullptr;   // [K][Dpad]
+  int* nk_cnt = nullptr;    // [K]
+  double* nk_fz = nullptr;  // [K]
+  int* hist = nullptr;      // [K+1]
+  int* offsets = nullptr;   // [K+2]
+  int* cursor = nullptr;    // [K+1]
+  int* cls = nullptr;       // [N_local]
+  int* perm = nullptr;      // [N_local]
+  double* Lword = nullptr;  // [K][Ws] (skd)
+  float* eps_init = nullptr;
+  double* crit_partial = nullptr;
+  double* crit4 = nullptr;
+  int crit_blocks = 0;
+  std::vector<void*> allocs;
+};
+
+template <typename T>
+static int dalloc(nemb200_plan* pl, T** p, size_t n) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+  pl->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+extern "C" int nemb200_abi_version(void) { return NEMB200_ABI_VERSION; }
+extern "C" const char* nemb200_last_error(void) { return g_err.c_str(); }
+extern "C" int nemb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int nemb200_plan_create(nemb200_plan** out, int64_t N_local, int64_t N_total, int64_t D,
+                                   int64_t row_stride_words, int32_t K, int32_t free_disp, uint32_t flags) {
+  if (!out || N_local < 0 || N_total < 1 || D < 1 || K < 1 || K > NEMB200_MAX_K || row_stride_words % 4 != 0 ||
+      row_stride_words * 32 < D || N_total > 0x7fffffffLL)
+    return fail(NEMB200_ERR_ARG, "plan_create: bad shape N_local=%lld N_total=%lld D=%lld stride=%lld K=%d",
+                (long long)N_local, (long long)N_total, (long long)D, (long long)row_stride_words, K);
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  nemb200_plan* pl = new nemb200_plan();
+  pl->N_local = N_local; pl->N_total = N_total; pl->D = (int)D; pl->Ws = (int)row_stride_words;
+  pl->Dpad = pl->Ws * 32; pl->K = K; pl->free_disp = free_disp ? 1 : 0; pl->flags = flags;
+  Params& P = pl->P;
+  P.K = K; P.D = pl->D; P.Ws = pl->Ws; P.Dpad = pl->Dpad; P.free_disp = pl->free_disp;
+  int rc = 0;
+#define A(ptr, n) if ((rc = dalloc(pl, &(ptr), (size_t)(n))) != 0) { nemb200_plan_destroy(pl); return rc; }
+  A(P.pk, K) A(P.logpk32, K) A(P.logpk64, K)
+  A(P.mu, (size_t)K * pl->D) A(P.eps, (size_t)K * pl->D)
+  A(P.m1, (size_t)K * pl->Ws) A(P.valid, (size_t)K * pl->Ws)
+  A(P.L, pl->free_disp ? (size_t)K * pl->Dpad : (size_t)K) A(P.B, K)
+  A(P.has_half, 1) A(P.status, 1)
+  A(pl->cnt, (size_t)K * pl->Dpad) A(pl->fsum, (size_t)K * pl->Dpad)
+  A(pl->nk_cnt, K) A(pl->nk_fz, K) A(pl->hist, K + 1) A(pl->offsets, K + 2) A(pl->cursor, K + 1)
+  A(pl->cls, N_local) A(pl->perm, N_local)
+  A(pl->Lword, (size_t)K * pl->Ws) A(pl->eps_init, K)
+  pl->crit_blocks = num_sms() * 4;
+  A(pl->crit_partial, (size_t)pl->crit_blocks * 4) A(pl->crit4, 4)
+#undef A
+  *out = pl;
+  return NEMB200_OK;
+}
+
+extern "C" void nemb200_plan_destroy(nemb200_plan* pl) {
+  if (!pl) return;
+  for (void* p : pl->allocs) cudaFree(p);
+  delete pl;
+}
+
+extern "C" int nemb200_init_params(nemb200_plan* pl, void* stream_) {
+  if (!pl) return fail(NEMB200_ERR_ARG, "init_params: null plan");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int K = pl->K;
+  // partition.py:65-85: the values are written as text and read back with fscanf("%f") -> float32
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.12g", 1.0 / (double)K);
+  const float base = strtof(buf, nullptr);
+  const double step = 0.5 / std::ceil((double)K / 2.0);
+  const double pich = (K == 2) ? 0.1 : 0.0;
+  std::vector<float> e(K);
+  for (int k = 1; k <= K; k++)
+    e[k - 1] = ((double)k <= (double)K / 2.0) ? (float)(step * k - pich) : (float)(step * (K - k + 1) - pich);
+  CK(cudaMemcpyAsync(pl->eps_init, e.data(), K * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // e is a stack vector
+  k_init_params<<<K, 256, 0, st>>>(pl->P, base, pl->eps_init);
+  CK(cudaGetLastError());
+  if (pl->free_disp) {
+    const int n = K * pl->Ws;
+    k_lword<<<(n + 255) / 256, 256, 0, st>>>(pl->P.L, K, pl->Ws, pl->Dpad, pl->Lword);
+    CK(cudaGetLastError());
+  }
+  return NEMB200_OK;
+}
+
+template <int KB>
+static int launch_classify(nemb200_plan* pl, const float* T, cudaStream_t st) {
+  const long long N = pl->N_local;
+  if (N > 0) {
+    k_classify<KB><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(T, N, pl->K, pl->cls, pl->hist, pl->nk_fz);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+template <int KB>
+static int launch_fuzzy(nemb200_plan* pl, const uint32_t* bits, const float* T, cudaStream_t st) {
+  dim3 grid((pl->Dpad + 255) / 256, 64);
+  k_mstep_fuzzy<KB><<<grid, 256, 0, st>>>(bits, pl->Ws, pl->K, pl->D, pl->offsets, pl->perm, T, pl->fsum, pl->Dpad);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+#define DISPATCH_KB(K, FN, ...)                    \
+  ((K) <= 3 ? FN<3>(__VA_ARGS__)                   \
+   : (K) <= 4 ? FN<4>(__VA_ARGS__)                 \
+   : (K) <= 8 ? FN<8>(__VA_ARGS__)                 \
+   : (K) <= 16 ? FN<16>(__VA_ARGS__)               \
+               : FN<32>(__VA_ARGS__))
+
+extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, const float* T, void* stream_) {
+  if (!pl || (pl->N_local > 0 && (!bits || !T))) return fail(NEMB200_ERR_ARG, "mstep_accumulate: null argument");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int K = pl->K;
+  const long long N = pl->N_local;
+  CK(cudaMemsetAsync(pl->cnt, 0, (size_t)K * pl->Dpad * sizeof(int), st));
+  CK(cudaMemsetAsync(pl->fsum, 0, (size_t)K * pl->Dpad * sizeof(double), st));
+  CK(cudaMemsetAsync(pl->hist, 0, (K + 1) * sizeof(int), st));
+  CK(cudaMemsetAsync(pl->nk_fz, 0, K * sizeof(double), st));
+  int rc = DISPATCH_KB(K, launch_classify, pl, T, st);
+  if (rc) return rc;
+  k_offsets<<<1, 32, 0, st>>>(pl->hist, K, pl->offsets, pl->cursor, pl->nk_cnt);
+  CK(cudaGetLastError());
+  if (N > 0) {
+    k_scatter<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pl->cls, N, pl->cursor, pl->perm);
+    CK(cudaGetLastError());
+    const int max_segs = (int)((N + kSeg - 1) / kSeg) + K;  // upper bound on sum_k ceil(n_k / kSeg)
+    dim3 grid((pl->Ws + kMsTpb - 1) / kMsTpb, max_segs);
+    k_mstep_onehot<<<grid, kMsTpb, 0, st>>>(bits, pl->Ws, K, pl->offsets, pl->perm, pl->cnt, pl->Dpad);
+    CK(cudaGetLastError());
+    rc = DISPATCH_KB(K, launch_fuzzy, pl, bits, T, st);
+    if (rc) return rc;
+  }
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_stats_ptrs(nemb200_plan* pl, int32_t** cnt, double** fsum, int32_t** nk_cnt, double** nk_fz,
+                                  int64_t* Dpad) {
+  if (!pl) return fail(NEMB200_ERR_ARG, "stats_ptrs: null plan");
+  if (cnt) *cnt = pl->cnt;
+  if (fsum) *fsum = pl->fsum;
+  if (nk_cnt) *nk_cnt = pl->nk_cnt;
+  if (nk_fz) *nk_fz = pl->nk_fz;
+  if (Dpad) *Dpad = pl->Dpad;
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_mstep_finalize(nemb200_plan* pl, void* stream_) {
+  if (!pl) return fail(NEMB200_ERR_ARG, "mstep_finalize: null plan");
+  cudaStream_t st = (cudaStream_t)stream_;
+  CK(cudaMemsetAsync(pl->P.has_half, 0, sizeof(int), st));
+  k_mstep_finalize<<<pl->K, 1024, 0, st>>>(pl->P, pl->cnt, pl->fsum, pl->nk_cnt, pl->nk_fz, pl->N_total);
+  CK(cudaGetLastError());
+  if (pl->free_disp) {
+    const int n = pl->K * pl->Ws;
+    k_lword<<<(n + 255) / 256, 256, 0, st>>>(pl->P.L, pl->K, pl->Ws, pl->Dpad, pl->Lword);
+    CK(cudaGetLastError());
+  }
+  return NEMB200_OK;
+}
+
+static int group_lanes(int units) {  // lanes cooperating on one row: smallest power of two >= units, capped at 32
+  int g = 1;
+  while (g < units && g < 32) g <<= 1;
+  return g;
+}
+
+template <int KB>
+static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
+  constexpr int RB = 4;
+  const int W4 = pl->Ws / 4;
+  const int G = group_lanes(W4);
+  const size_t smem = (size_t)2 * pl->K * W4 * sizeof(uint4);
+  const int in_smem = smem <= 96 * 1024;
+  auto kern = k_density_sk<KB, RB>;
+  if (in_smem && smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long rows_per_block = (long long)(256 / 32) * (32 / G) * RB;
+  long long blocks = (pl->N_local + rows_per_block - 1) / rows_per_block;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, 256, in_smem ? smem : 0, st>>>((const uint4*)bits, pl->N_local, W4, pl->K, G,
+                                                          (const uint4*)pl->P.m1, (const uint4*)pl->P.valid, pl->P.L,
+                                                          pl->P.B, pl->P.has_half, logf, in_smem);
+  CK(cudaGetLastError());
+  return 0;
+}
+template <int KB>
+static int launch_density_skd(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
+  const int G = group_lanes(pl->Ws);
+  const long long rows_per_block = (long long)(256 / 32) * (32 / G);
+  long long blocks = (pl->N_local + rows_per_block - 1) / rows_per_block;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_density_skd<KB><<<(unsigned)blocks, 256, 0, st>>>(bits, pl->N_local, pl->Ws, pl->K, pl->Dpad, G, pl->P.m1,
+                                                      pl->P.valid, pl->P.L, pl->Lword, pl->P.B, logf);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int nemb200_density(nemb200_plan* pl, const uint32_t* bits, double* logf, void* stream_) {
+  if (!pl || (pl->N_local > 0 && (!bits || !logf))) return fail(NEMB200_ERR_ARG, "density: null argument");
+  if (pl->N_local == 0) return NEMB200_OK;
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (pl->free_disp) return DISPATCH_KB(pl->K, launch_density_skd, pl, bits, logf, st);
+  return DISPATCH_KB(pl->K, launch_density_sk, pl, bits, logf, st);
+}
+
+extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, const float* T_old, float* T_new,
+                             const int32_t* rowptr, const int32_t* col, const float* w,
+                             const int32_t* sched_level_ptr, const int32_t* sched_rows, int32_t n_levels,
+                             float beta_now, uint32_t* maxdiff_bits, void* stream_) {
+  if (!pl || !logf || !T_old || !T_new || !maxdiff_bits || N < 1) return fail(NEMB200_ERR_ARG, "sweep: null argument");
+  cudaStream_t st = (cudaStream_t)stream_;
+  SweepArgs a;
+  a.N = N; a.K = pl->K; a.logf = logf; a.pk = pl->P.pk; a.logpk64 = pl->P.logpk64; a.T_old = T_old; a.T_new = T_new;
+  a.rowptr = rowptr; a.col = col; a.w = w; a.beta = beta_now;
+  a.logspace = (pl->flags & NEMB200_EPI_LOGSPACE) ? 1 : 0;
+  a.jacobi = (pl->flags & NEMB200_JACOBI) ? 1 : 0;
+  a.maxdiff_bits = maxdiff_bits;
+  const bool need_levels = (beta_now != 0.0f) && rowptr != nullptr && !a.jacobi;
+  if (need_levels && (!sched_level_ptr || !sched_rows || n_levels < 1))
+    return fail(NEMB200_ERR_ARG, "sweep: Gauss-Seidel sweep needs a level schedule (nemb200_gs_schedule)");
+  if (need_levels && n_levels > 1) {
+    a.level_ptr = sched_level_ptr; a.level_rows = sched_rows; a.n_levels = n_levels;
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep<true>, 256, 0));
+    if (per_sm < 1) return fail(NEMB200_ERR_CUDA, "sweep: kernel does not fit on an SM");
+    long long blocks = (long long)num_sms() * std::min(per_sm, 4);
+    const long long want = (N + 7) / 8;
+    if (blocks > want) blocks = std::max<long long>(want, 1);
+    void* args[] = {&a};
+    CK(cudaLaunchCooperativeKernel((void*)k_sweep<true>, dim3((unsigned)blocks), dim3(256), args, 0, st));
+  } else {
+    a.level_ptr = nullptr; a.level_rows = nullptr; a.n_levels = 1;
+    long long blocks = (N + 7) / 8;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    k_sweep<false><<<(unsigned)blocks, 256, 0, st>>>(a);
+    CK(cudaGetLastError());
+  }
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_criteria(nemb200_plan* pl, int64_t N, const double* logf, const float* T, const int32_t* rowptr,
+                                const int32_t* col, const float* w, float beta, double crit_out[5], void* stream_) {
+  if (!pl || !logf || !T || !crit_out) return fail(NEMB200_ERR_ARG, "criteria: null argument");
+  cudaStream_t st = (cudaStream_t)stream_;
+  CritArgs a;
+  a.N = N; a.K = pl->K; a.logf = logf; a.pk = pl->P.pk; a.logpk32 = pl->P.logpk32; a.logpk64 = pl->P.logpk64; a.T = T;
+  a.rowptr = rowptr; a.col = col; a.w = w; a.beta = beta; a.logspace = (pl->flags & NEMB200_EPI_LOGSPACE) ? 1 : 0;
+  a.partial = pl->crit_partial;
+  k_criteria<<<pl->crit_blocks, 256, 0, st>>>(a);
+  CK(cudaGetLastError());
+  k_crit_reduce<<<1, 32, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4);
+  CK(cudaGetLastError());
+  double h[4];
+  CK(cudaMemcpyAsync(h, pl->crit4, sizeof h, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const double cD = h[0], cG = h[1], cL = h[2], cZ = h[3];
+  crit_out[0] = cD + 0.5 * (double)beta * cG;  // U  (nem_alg.c:2834)
+  crit_out[1] = cD;
+  crit_out[2] = cL;
+  crit_out[3] = cD + (double)beta * cG + cZ;    // M  (nem_alg.c:2835)
+  crit_out[4] = cZ;
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_get_params(nemb200_plan* pl, float* mu, float* eps, float* pk, int32_t* status, void* stream_) {
+  if (!pl) return fail(NEMB200_ERR_ARG, "get_params: null plan");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const size_t kd = (size_t)pl->K * pl->D * sizeof(float);
+  if (mu) CK(cudaMemcpyAsync(mu, pl->P.mu, kd, cudaMemcpyDeviceToHost, st));
+  if (eps) CK(cudaMemcpyAsync(eps, pl->P.eps, kd, cudaMemcpyDeviceToHost, st));
+  if (pk) CK(cudaMemcpyAsync(pk, pl->P.pk, pl->K * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (status) CK(cudaMemcpyAsync(status, pl->P.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_labels(const float* T, int64_t N, int32_t K, int32_t* labels_dev, double* entropy_host,
+                              void* stream_) {
+  if (!T || !labels_dev || N < 1 || K < 1) return fail(NEMB200_ERR_ARG, "labels: bad argument");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int blocks = (int)((N + 255) / 256);
+  double* part = nullptr;
+  CK(cudaMalloc(&part, (size_t)(blocks + 1) * sizeof(double)));
+  k_labels<<<blocks, 256, 0, st>>>(T, N, K, labels_dev, part);
+  k_sum_partials<<<1, 32, 0, st>>>(part, blocks, part + blocks);
+  double e = 0.0;
+  cudaError_t err = cudaMemcpyAsync(&e, part + blocks, sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  cudaFree(part);
+  if (err != cudaSuccess) return fail(NEMB200_ERR_CUDA, "labels: %s", cudaGetErrorString(err));
+  if (entropy_host) *entropy_host = e;
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_gs_schedule(int64_t N, const int32_t* rowptr, const int32_t* col, int32_t* level_ptr_out,
+                                   int32_t* rows_out) {
+  if (N < 1 || !rowptr || !level_ptr_out || !rows_out) return fail(NEMB200_ERR_ARG, "gs_schedule: bad argument");
+  std::vector<int32_t> level((size_t)N, 0);
+  int32_t maxl = 0;
+  for (int64_t i = 0; i < N; i++) {
+    int32_t lv = 0;
+    for (int32_t n = rowptr[i]; n < rowptr[i + 1]; n++) {
+      const int32_t j = col[n];
+      if (j < 0 || j >= N) return fail(NEMB200_ERR_ARG, "gs_schedule: neighbour %d of row %lld out of range", j, (long long)i);
+      if (j < i) lv = std::max(lv, level[j] + 1);
+    }
+    level[i] = lv;
+    maxl = std::max(maxl, lv);
+  }
+  const int32_t nl = maxl + 1;
+  std::vector<int32_t> count((size_t)nl + 1, 0);
+  for (int64_t i = 0; i < N; i++) count[level[i] + 1]++;
+  for (int32_t l = 0; l < nl; l++) count[l + 1] += count[l];
+  for (int32_t l = 0; l <= nl; l++) level_ptr_out[l] = count[l];
+  std::vector<int32_t> cur(count.begin(), count.end() - 1);
+  for (int64_t i = 0; i < N; i++) rows_out[cur[level[i]]++] = (int32_t)i;
+  return nl;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// whole-run drivers
+// ------------------------------------------------------------------------------------------------------------------
+struct RunBuffers {
+  double* logf = nullptr;
+  float* Ta = nullptr;
+  float* Tb = nullptr;
+  uint32_t* flags = nullptr;  // [0] maxdiff bits
+  std::vector<void*> owned;
+  ~RunBuffers() { for (void* p : owned) cudaFree(p); }
+};
+
+static int run_em(nemb200_plan* pl, const uint32_t* bits, const int32_t* rowptr, const int32_t* col, const float* w,
+                  const int32_t* lvl_ptr, const int32_t* lvl_rows, int n_levels, float beta, int itermax, float cv_th,
+                  float* T_out, nemb200_result* res, cudaStream_t st) {
+  const long long N = pl->N_local;
+  const int K = pl->K;
+  RunBuffers rb;
+  auto alloc = [&](void** p, size_t bytes) -> int {
+    CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    rb.owned.push_back(*p);
+    return 0;
+  };
+  int rc;
+  if ((rc = alloc((void**)&rb.logf, (size_t)N * K * sizeof(double)))) return rc;
+  if ((rc = alloc((void**)&rb.Ta, (size_t)N * K * sizeof(float)))) return rc;
+  if ((rc = alloc((void**)&rb.Tb, (size_t)N * K * sizeof(float)))) return rc;
+  if ((rc = alloc((void**)&rb.flags, 4 * sizeof(uint32_t)))) return rc;
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0));
+  CK(cudaEventCreate(&ev1));
+  CK(cudaEventRecord(ev0, st));
+
+  // --- nem_alg.c:2023-2065 with Needinit = 1
+  if ((rc = nemb200_init_params(pl, st))) return rc;
+  CK(cudaMemsetAsync(rb.Ta, 0, (size_t)N * K * sizeof(float), st));  // ClassifM is calloc'ed (nem_exe.c:533-536)
+  if ((rc = nemb200_density(pl, bits, rb.logf, st))) return rc;
+  if ((rc = nemb200_sweep(pl, N, rb.logf, rb.Ta, rb.Tb, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, 0.0f, rb.flags, st))) return rc;
+  float* cur = rb.Tb;
+  float* other = rb.Ta;
+  if (beta != 0.0f) {
+    if ((rc = nemb200_sweep(pl, N, rb.logf, cur, other, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, beta, rb.flags, st))) return rc;
+    std::swap(cur, other);
+  }
+  // with beta == 0 the second sweep of the reference recomputes the same posteriors: skipped
+
+  // --- nem_alg.c:1829-1894
+  int iter = 0, converged = 0, status = NEMB200_STS_OK;
+  for (iter = 1; iter <= itermax && !converged && status == NEMB200_STS_OK; iter++) {
+    if ((rc = nemb200_mstep_accumulate(pl, bits, cur, st))) return rc;
+    if ((rc = nemb200_mstep_finalize(pl, st))) return rc;
+    if ((rc = nemb200_density(pl, bits, rb.logf, st))) return rc;
+    CK(cudaMemsetAsync(rb.flags, 0, sizeof(uint32_t), st));
+    if ((rc = nemb200_sweep(pl, N, rb.logf, cur, other, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, beta, rb.flags, st))) return rc;
+    uint32_t hflags[2] = {0, 0};
+    CK(cudaMemcpyAsync(&hflags[0], rb.flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hflags[1], pl->P.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    status = (int)hflags[1];
+    if (status != NEMB200_STS_OK) break;  // empty class: the reference stops before the E-step (nem_alg.c:1873-1892)
+    std::swap(cur, other);
+    float maxdif;
+    memcpy(&maxdif, &hflags[0], sizeof(float));
+    converged = (maxdif < cv_th);  // nem_alg.c:2160-2173
+  }
+  if (status == NEMB200_STS_OK) iter = iter - 1;
+  // --- nem_alg.c:1906
+  double crit[5] = {0, 0, 0, 0, 0};
+  if (status == NEMB200_STS_OK) {
+    if ((rc = nemb200_criteria(pl, N, rb.logf, cur, rowptr, col, w, beta, crit, st))) return rc;
+    if (std::isinf(crit[0]) && crit[0] < 0) status = NEMB200_STS_INFINITE;  // nem_alg.c:2482-2487
+  }
+  CK(cudaEventRecord(ev1, st));
+  CK(cudaEventSynchronize(ev1));
+  float ms = 0.0f;
+  CK(cudaEventElapsedTime(&ms, ev0, ev1));
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (T_out) CK(cudaMemcpyAsync(T_out, cur, (size_t)N * K * sizeof(float), cudaMemcpyDefault, st));
+  CK(cudaStreamSynchronize(st));
+  if (res) {
+    for (int q = 0; q < 5; q++) res->crit[q] = crit[q];
+    res->n_iter = iter; res->converged = converged; res->status = status; res->n_levels = n_levels; res->elapsed_ms = ms;
+  }
+  return NEMB200_OK;
+}
+
+static int copy_params_out(nemb200_plan* pl, float* mu, float* eps, float* pk, cudaStream_t st) {
+  const size_t kd = (size_t)pl->K * pl->D * sizeof(float);
+  if (mu) CK(cudaMemcpyAsync(mu, pl->P.mu, kd, cudaMemcpyDefault, st));
+  if (eps) CK(cudaMemcpyAsync(eps, pl->P.eps, kd, cudaMemcpyDefault, st));
+  if (pk) CK(cudaMemcpyAsync(pk, pl->P.pk, pl->K * sizeof(float), cudaMemcpyDefault, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int nemb200_nem_device(const uint32_t* bits, int64_t N, int64_t D, int64_t row_stride_words,
+                                  const int32_t* rowptr, const int32_t* col, const float* w,
+                                  const int32_t* sched_level_ptr, const int32_t* sched_rows, int32_t n_levels,
+                                  int32_t K, float beta, int32_t free_disp, int32_t itermax, float cv_th, uint32_t flags,
+                                  float* T_out, float* mu_out, float* eps_out, float* pk_out, nemb200_result* result,
+                                  void* stream_) {
+  if (!bits || N < 1) return fail(NEMB200_ERR_ARG, "nem_device: null matrix");
+  if (beta != 0.0f && (!rowptr || !col || !w)) return fail(NEMB200_ERR_ARG, "nem_device: beta != 0 needs the neighbour graph");
+  nemb200_plan* pl = nullptr;
+  int rc = nemb200_plan_create(&pl, N, N, D, row_stride_words, K, free_disp, flags);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream_;
+  rc = run_em(pl, bits, rowptr, col, w, sched_level_ptr, sched_rows, n_levels, beta, itermax, cv_th, T_out, result, st);
+  if (rc == 0) rc = copy_params_out(pl, mu_out, eps_out, pk_out, st);
+  nemb200_plan_destroy(pl);
+  return rc;
+}
+
+extern "C" int nemb200_nem_host(const uint32_t* bits, int64_t N, int64_t D, int64_t row_stride_words,
+                                const int32_t* rowptr, const int32_t* col, const float* w, int32_t K, float beta,
+                                int32_t free_disp, int32_t itermax, float cv_th, uint32_t flags, float* T_out,
+                                float* mu_out, float* eps_out, float* pk_out, nemb200_result* result) {
+  if (!bits || N < 1 || row_stride_words < 1) return fail(NEMB200_ERR_ARG, "nem_host: null matrix");
+  const bool graph = (beta != 0.0f);
+  if (graph && (!rowptr || !col || !w)) return fail(NEMB200_ERR_ARG, "nem_host: beta != 0 needs the neighbour graph");
+  cudaStream_t st = nullptr;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  struct Guard {
+    std::vector<void*> p; cudaStream_t s;
+    ~Guard() { for (void* q : p) cudaFree(q); cudaStreamDestroy(s); }
+  } g{{}, st};
+  auto dmal = [&](void** p, size_t bytes) -> int { CK(cudaMalloc(p, std::max<size_t>(bytes, 16))); g.p.push_back(*p); return 0; };
+  uint32_t* d_bits = nullptr; int32_t *d_rowptr = nullptr, *d_col = nullptr, *d_lp = nullptr, *d_lr = nullptr; float* d_w = nullptr;
+  float* d_T = nullptr;
+  int rc;
+  const size_t bits_bytes = (size_t)N * row_stride_words * sizeof(uint32_t);
+  if ((rc = dmal((void**)&d_bits, bits_bytes))) return rc;
+  CK(cudaMemcpyAsync(d_bits, bits, bits_bytes, cudaMemcpyHostToDevice, st));
+  int n_levels = 1;
+  if (graph) {
+    const int64_t nnz = rowptr[N];
+    std::vector<int32_t> lp((size_t)N + 1), lr((size_t)N);
+    n_levels = nemb200_gs_schedule(N, rowptr, col, lp.data(), lr.data());
+    if (n_levels < 0) return n_levels;
+    if ((rc = dmal((void**)&d_rowptr, (size_t)(N + 1) * 4))) return rc;
+    if ((rc = dmal((void**)&d_col, (size_t)nnz * 4))) return rc;
+    if ((rc = dmal((void**)&d_w, (size_t)nnz * 4))) return rc;
+    if ((rc = dmal((void**)&d_lp, (size_t)(N + 1) * 4))) return rc;
+    if ((rc = dmal((void**)&d_lr, (size_t)N * 4))) return rc;
+    CK(cudaMemcpyAsync(d_rowptr, rowptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_col, col, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_w, w, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_lp, lp.data(), (size_t)(n_levels + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_lr, lr.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // lp / lr are locals
+  }
+  if ((rc = dmal((void**)&d_T, (size_t)N * K * sizeof(float)))) return rc;
+  nemb200_plan* pl = nullptr;
+  rc = nemb200_plan_create(&pl, N, N, D, row_stride_words, K, free_disp, flags);
+  if (rc) return rc;
+  rc = run_em(pl, d_bits, d_rowptr, d_col, d_w, d_lp, d_lr, n_levels, beta, itermax, cv_th, d_T, result, st);
+  if (rc == 0 && T_out) {
+    cudaError_t e = cudaMemcpyAsync(T_out, d_T, (size_t)N * K * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = fail(NEMB200_ERR_CUDA, "nem_host: D2H %s", cudaGetErrorString(e));
+  }
+  if (rc == 0) rc = copy_params_out(pl, mu_out, eps_out, pk_out, st);
+  nemb200_plan_destroy(pl);
+  return rc;
+}

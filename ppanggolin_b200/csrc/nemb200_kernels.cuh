@@ -1,0 +1,803 @@
+// nemb200_kernels.cuh -- sm_100a kernels of the NEM partitioning hot path.
+//
+// What each kernel restates (paths relative to /root/reference/ppanggolin/nem/):
+//   k_density_sk / k_density_skd   NEM/nem_mod.c:618-689 (DensBernoulli) for all rows x classes, closed form:
+//                                  log f_k(x_i) = sum_d log(1-e_kd) - sum_{d: x_id != mu_kd} log((1-e_kd)/e_kd)
+//   k_sweep                        NEM/nem_alg.c:2412-2489 + :2630-2701 (in-place posterior sweep) via level schedule
+//   k_classify/k_scatter/k_mstep_* NEM/nem_mod.c:1270-1312, :1317-1474, :1641-1699 (sizes, medians, inertia) as
+//                                  column sums S1[k][d] = sum_i c_ik x_id over the bit-packed matrix
+//   k_mstep_finalize               NEM/nem_mod.c:1020-1076 / :1131-1170 (dispersion), :455-459 (proportions)
+//   k_criteria                     NEM/nem_alg.c:2764-2843
+//   k_labels                       partition.py:206-231 on nem_exe.c:1682's "%5.3f"
+//
+// All of it is HBM-bound integer/bit work plus small fp64 epilogues; no tensor cores on purpose (K <= 32).
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace nemb200 {
+namespace cg = cooperative_groups;
+
+constexpr double kEps = 1e-20;  // NEM/nem_typ.h:65 EPSILON
+constexpr int kFuzzy = -1;
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  // the matrix is read once per pass: keep it out of L1, let L2 decide
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Parameter block (device memory, owned by a plan)
+// ------------------------------------------------------------------------------------------------------------------
+struct Params {
+  int K, D, Ws, Dpad, free_disp;
+  float* pk;        // [K]   proportions (float32 like ModelParaT.Prop_K)
+  float* logpk32;   // [K]   (float) log((double)pk)           nem_alg.c:2350-2352
+  double* logpk64;  // [K]
+  float* mu;        // [K][D]   {0, 0.5, 1}
+  float* eps;       // [K][D]
+  uint32_t* m1;     // [K][Ws]  bit set where mu == 1
+  uint32_t* valid;  // [K][Ws]  bit set where mu != 0.5 (a 0.5 centre never mismatches: nem_mod.c:656-657)
+  double* L;        // sk_: [K]        log((1-e)/e);  skd: [K][Dpad]   (+inf where e <= 1e-20: null density on mismatch)
+  double* B;        // [K]   sum_d log(1-e_kd) over columns with e > 1e-20
+  int* has_half;    // [1]   any mu == 0.5
+  int* status;      // [1]   NEMB200_STS_*
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// E-step part 1: log densities.  A group of G lanes walks RB rows at once so that each class's centre words are
+// fetched from shared memory once per RB matrix words.
+// ------------------------------------------------------------------------------------------------------------------
+template <int KB, int RB, bool HALF>
+__device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, long long N, int W4, int K, int G,
+                                                const uint4* __restrict__ m1, const uint4* __restrict__ valid,
+                                                const double* __restrict__ L, const double* __restrict__ B,
+                                                double* __restrict__ logf) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (G - 1);
+  const int grp = lane / G;
+  const int groups_per_warp = 32 / G;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long rows_per_warp = (long long)groups_per_warp * RB;
+
+  for (long long base = warp_global * rows_per_warp; base < N; base += nwarps * rows_per_warp) {
+    const long long r0 = base + (long long)grp * RB;
+    int h[RB][KB];
+#pragma unroll
+    for (int r = 0; r < RB; r++)
+#pragma unroll
+      for (int k = 0; k < KB; k++) h[r][k] = 0;
+
+    for (int c = sub; c < W4; c += G) {
+      uint4 x[RB];
+#pragma unroll
+      for (int r = 0; r < RB; r++) {
+        x[r] = make_uint4(0, 0, 0, 0);
+        if (r0 + r < N) x[r] = ld_stream(bits + (r0 + r) * W4 + c);
+      }
+#pragma unroll
+      for (int k = 0; k < KB; k++) {
+        if (k < K) {
+          const uint4 a = m1[k * W4 + c];
+          uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+          if (HALF) v = valid[k * W4 + c];
+#pragma unroll
+          for (int r = 0; r < RB; r++) {
+            h[r][k] += __popc((x[r].x ^ a.x) & v.x) + __popc((x[r].y ^ a.y) & v.y) + __popc((x[r].z ^ a.z) & v.z) +
+                       __popc((x[r].w ^ a.w) & v.w);
+          }
+        }
+      }
+    }
+    // reduce over the G lanes of the group
+    for (int off = G >> 1; off > 0; off >>= 1) {
+#pragma unroll
+      for (int r = 0; r < RB; r++)
+#pragma unroll
+        for (int k = 0; k < KB; k++) h[r][k] += __shfl_xor_sync(0xffffffffu, h[r][k], off);
+    }
+    // lane `sub` writes classes sub, sub+G, ...
+#pragma unroll
+    for (int k = 0; k < KB; k++) {
+      if (k < K && (k & (G - 1)) == sub) {
+        const double Lk = L[k], Bk = B[k];
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+          if (r0 + r < N) {
+            // e_k <= 1e-20: L = +inf; a mismatch gives the reference's null density (nem_mod.c:663-665, :684-685)
+            const double v = (h[r][k] == 0) ? Bk : (Bk - (double)h[r][k] * Lk);
+            logf[(r0 + r) * K + k] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int KB, int RB>
+__global__ void __launch_bounds__(256)
+k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
+             const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
+             const int* __restrict__ has_half, double* __restrict__ logf, int planes_in_smem) {
+  extern __shared__ uint4 smem4[];
+  const bool half = (*has_half != 0);   // any centre at 0.5 (exact median tie): needs the `valid` plane
+  const uint4* m1 = m1g;
+  const uint4* valid = validg;
+  if (planes_in_smem) {
+    const int n = K * W4;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      smem4[t] = m1g[t];
+      if (half) smem4[n + t] = validg[t];
+    }
+    __syncthreads();
+    m1 = smem4;
+    valid = smem4 + n;
+  }
+  if (half) density_sk_body<KB, RB, true>(bits, N, W4, K, G, m1, valid, L, B, logf);
+  else      density_sk_body<KB, RB, false>(bits, N, W4, K, G, m1, valid, L, B, logf);
+}
+
+// free dispersion ("skd"): per-column log-odds.  sum over mismatching columns of L_kd, taken over the set bits of the
+// mismatch word or of its complement, whichever is sparser (Lsum holds the per-word totals).
+template <int KB>
+__global__ void __launch_bounds__(256)
+k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int Dpad, int G,
+              const uint32_t* __restrict__ m1, const uint32_t* __restrict__ valid, const double* __restrict__ Lkd,
+              const double* __restrict__ Lword, const double* __restrict__ B, double* __restrict__ logf) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (G - 1);
+  const int grp = lane / G;
+  const int groups_per_warp = 32 / G;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long base = warp_global * groups_per_warp; base < N; base += nwarps * groups_per_warp) {
+    const long long row = base + grp;
+    double s[KB];
+#pragma unroll
+    for (int k = 0; k < KB; k++) s[k] = 0.0;
+    if (row < N) {
+      for (int c = sub; c < Ws; c += G) {
+        const uint32_t x = ld_stream32(bits + row * Ws + c);
+#pragma unroll
+        for (int k = 0; k < KB; k++) {
+          if (k < K) {
+            const uint32_t v = valid[k * Ws + c];
+            uint32_t mm = (x ^ m1[k * Ws + c]) & v;   // mismatching columns
+            const double* Lrow = Lkd + (size_t)k * Dpad + (size_t)c * 32;
+            if (__popc(mm) <= 16) {
+              double a = 0.0;
+              while (mm) { const int b = __ffs(mm) - 1; a += Lrow[b]; mm &= mm - 1; }
+              s[k] += a;
+            } else {
+              uint32_t ok = ~mm & v;  // matching, valid columns (padding columns carry L = 0)
+              double a = Lword[(size_t)k * Ws + c];
+              // subtract the matches; +inf entries (e == 0) cannot be subtracted -> handle by direct sum instead
+              if (isinf(a)) {
+                a = 0.0;
+                while (mm) { const int b = __ffs(mm) - 1; a += Lrow[b]; mm &= mm - 1; }
+              } else {
+                while (ok) { const int b = __ffs(ok) - 1; a -= Lrow[b]; ok &= ok - 1; }
+                // columns with mu == 0.5 are in neither set but are part of Lword: remove them
+                uint32_t half = ~v;
+                while (half) { const int b = __ffs(half) - 1; a -= Lrow[b]; half &= half - 1; }
+              }
+              s[k] += a;
+            }
+          }
+        }
+      }
+    }
+    for (int off = G >> 1; off > 0; off >>= 1) {
+#pragma unroll
+      for (int k = 0; k < KB; k++) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+    }
+#pragma unroll
+    for (int k = 0; k < KB; k++)
+      if (k < K && (k & (G - 1)) == sub && row < N) logf[row * K + k] = B[k] - s[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// E-step part 2: posterior sweep.  One warp per row, lane k = class k.  Rows of one level are independent; levels are
+// separated by a grid-wide barrier (cooperative launch) so that neighbours with a smaller index are read from T_new
+// and the others from T_old -- exactly what the reference's in-place sweep over rows 0..N-1 sees.
+// ------------------------------------------------------------------------------------------------------------------
+struct SweepArgs {
+  long long N;
+  int K;
+  const double* logf;
+  const float* pk;
+  const double* logpk64;
+  const float* T_old;
+  float* T_new;
+  const int* rowptr;
+  const int* col;
+  const float* w;
+  const int* level_ptr;  // may be null: single level over all rows
+  const int* level_rows;
+  int n_levels;
+  float beta;
+  int logspace;
+  int jacobi;
+  unsigned* maxdiff_bits;
+};
+
+__device__ __forceinline__ void sweep_row(const SweepArgs& a, long long i, int lane, float& wmax) {
+  const int K = a.K;
+  const int k = lane < K ? lane : K - 1;
+  float ctx = 0.0f;
+  if (a.rowptr != nullptr && a.beta != 0.0f) {
+    const int n0 = a.rowptr[i], n1 = a.rowptr[i + 1];
+    for (int n = n0; n < n1; n++) {
+      const int j = a.col[n];
+      const float wt = a.w[n];
+      const float* src = (!a.jacobi && j < i) ? a.T_new : a.T_old;
+      const float c = __ldcg(src + (size_t)j * K + k);     // L2 read: T_new rows are written by other SMs in this launch
+      ctx = __fadd_rn(ctx, __fmul_rn(wt, c));               // float accumulate, no FMA (nem_alg.c:2954-2962)
+    }
+  }
+  const double lf = a.logf[(size_t)i * K + k];
+  float cnew;
+  if (!a.logspace) {
+    // reference arithmetic: nem_mod.c:677-679, nem_alg.c:2367, :2665-2698
+    const float lf32 = (float)lf;
+    const double f = (lf == -INFINITY) ? 0.0 : exp((double)lf32);
+    double num = (double)a.pk[k] * f * 1.0;
+    num = num * exp((double)a.beta * (double)ctx);
+    if (lane >= K) num = 0.0;
+    double cum = 0.0;
+    for (int kk = 0; kk < K; kk++) cum = cum + __shfl_sync(0xffffffffu, num, kk);  // sequential, like the reference
+    if (cum > 0) {
+      if (cum > kEps) { const double invZ = 1 / cum; cnew = (float)(invZ * num); }
+      else { const double invZ = 1 / (cum / kEps); cnew = (float)(invZ * (num / kEps)); }
+    } else {
+      cnew = (float)(1.0 / K);
+    }
+  } else {
+    double av = a.logpk64[k] + lf + (double)a.beta * (double)ctx;
+    if (lane >= K) av = -INFINITY;
+    double m = av;
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (m == -INFINITY) {
+      cnew = (float)(1.0 / K);
+    } else {
+      const double e = (lane < K) ? exp(av - m) : 0.0;
+      double s = 0.0;
+      for (int kk = 0; kk < K; kk++) s = s + __shfl_sync(0xffffffffu, e, kk);
+      cnew = (float)(e / s);
+    }
+  }
+  if (lane < K) {
+    const float old = a.T_old[(size_t)i * K + lane];
+    __stcg(a.T_new + (size_t)i * K + lane, cnew);
+    float dif = cnew - old;
+    if (dif < 0) dif = -dif;
+    wmax = fmaxf(wmax, dif);
+  }
+}
+
+template <bool COOP>
+__global__ void __launch_bounds__(256) k_sweep(SweepArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float wmax = 0.0f;
+  if (a.level_ptr == nullptr) {
+    for (long long i = warp_global; i < a.N; i += nwarps) sweep_row(a, i, lane, wmax);
+  } else {
+    for (int L = 0; L < a.n_levels; L++) {
+      const int b = a.level_ptr[L], e = a.level_ptr[L + 1];
+      for (long long idx = b + warp_global; idx < e; idx += nwarps) sweep_row(a, a.level_rows[idx], lane, wmax);
+      if (COOP && L + 1 < a.n_levels) {
+        __threadfence();
+        cg::this_grid().sync();
+      }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+  if (lane == 0 && wmax > 0.0f) atomicMax(a.maxdiff_bits, __float_as_uint(wmax));  // non-negative floats order as uints
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// M-step.  Rows whose posterior is exactly one-hot in float32 (the vast majority after the first iteration) only add
+// their bit pattern to one class: they are grouped per class (k_classify -> k_offsets -> k_scatter) and summed with
+// bit-sliced carry-save counters (k_mstep_onehot).  The remaining fuzzy rows take the fp64 path (k_mstep_fuzzy).
+// ------------------------------------------------------------------------------------------------------------------
+template <int KB>
+__global__ void __launch_bounds__(256)
+k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ cls, int* __restrict__ hist /*[K+1]*/,
+           double* __restrict__ nk_fz /*[K]*/) {
+  __shared__ int s_hist[KB + 1];
+  __shared__ double s_fz[KB];
+  for (int t = threadIdx.x; t <= KB; t += blockDim.x) s_hist[t] = 0;
+  for (int t = threadIdx.x; t < KB; t += blockDim.x) s_fz[t] = 0.0;
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    float t[KB];
+    int ones = 0, zeros = 0, arg = 0;
+#pragma unroll
+    for (int k = 0; k < KB; k++) {
+      t[k] = 0.0f;
+      if (k < K) {
+        t[k] = T[(size_t)i * K + k];
+        if (t[k] == 1.0f) { ones++; arg = k; }
+        else if (t[k] == 0.0f) zeros++;
+      }
+    }
+    int key;
+    if (ones == 1 && zeros == K - 1) key = arg;
+    else {
+      key = K;
+#pragma unroll
+      for (int k = 0; k < KB; k++)
+        if (k < K && t[k] != 0.0f) atomicAdd(&s_fz[k], (double)t[k]);
+    }
+    cls[i] = key;
+    atomicAdd(&s_hist[key], 1);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t <= K; t += blockDim.x)
+    if (s_hist[t]) atomicAdd(&hist[t], s_hist[t]);
+  for (int t = threadIdx.x; t < K; t += blockDim.x)
+    if (s_fz[t] != 0.0) atomicAdd(&nk_fz[t], s_fz[t]);
+}
+
+// offsets[k] = first slot of class k in perm (k = K: fuzzy rows); cursor = running copy for k_scatter;
+// nk_cnt[k] = one-hot rows of class k
+__global__ void k_offsets(const int* __restrict__ hist, int K, int* __restrict__ offsets /*[K+2]*/,
+                          int* __restrict__ cursor /*[K+1]*/, int* __restrict__ nk_cnt) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k <= K; k++) {
+      offsets[k] = acc;
+      cursor[k] = acc;
+      if (k < K) nk_cnt[k] = hist[k];
+      acc += hist[k];
+    }
+    offsets[K + 1] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_scatter(const int* __restrict__ cls, long long N, int* __restrict__ cursor, int* __restrict__ perm) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    const int pos = atomicAdd(&cursor[cls[i]], 1);
+    perm[pos] = (int)i;
+  }
+}
+
+// carry-save adder on 32 bit-columns at once
+__device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
+  const uint32_t u = a ^ b;
+  hi = (a & b) | (u & c);
+  lo = u ^ c;
+}
+
+constexpr int kSeg = 2048;     // rows per one-hot segment; counters have 12 planes (max 4095)
+constexpr int kPlanes = 12;
+constexpr int kMsTpb = 128;    // threads (= matrix words per row) per CTA
+
+// One thread owns one 32-bit word column (32 genomes).  blockIdx.y walks segments of at most kSeg rows of one class.
+__global__ void __launch_bounds__(kMsTpb)
+k_mstep_onehot(const uint32_t* __restrict__ bits, int Ws, int K, const int* __restrict__ offsets,
+               const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad) {
+  __shared__ int s_rows[kSeg];
+  __shared__ int s_cnt[kMsTpb * 33];
+  // map blockIdx.y -> (class, segment start)
+  int seg = blockIdx.y, k = 0, start = 0, len = 0;
+  bool found = false;
+  for (k = 0; k < K; k++) {
+    const int n = offsets[k + 1] - offsets[k];
+    const int nseg = (n + kSeg - 1) / kSeg;
+    if (seg < nseg) {
+      start = offsets[k] + seg * kSeg;
+      len = min(kSeg, offsets[k + 1] - start);
+      found = true;
+      break;
+    }
+    seg -= nseg;
+  }
+  if (!found) return;
+  for (int t = threadIdx.x; t < len; t += blockDim.x) s_rows[t] = perm[start + t];
+  __syncthreads();
+  const int word = blockIdx.x * kMsTpb + threadIdx.x;
+  const bool active = word < Ws;
+  uint32_t p[kPlanes];
+#pragma unroll
+  for (int j = 0; j < kPlanes; j++) p[j] = 0;
+  if (active) {
+    const uint32_t* colp = bits + word;
+    int r = 0;
+    for (; r + 16 <= len; r += 16) {
+      uint32_t x[16];
+#pragma unroll
+      for (int q = 0; q < 16; q++) x[q] = ld_stream32(colp + (size_t)s_rows[r + q] * Ws);
+      // Harley-Seal: 16 words -> one carry of weight 16
+      uint32_t t2a, t2b, t2c, t2d, t2e, t2f, t2g, t2h, t4a, t4b, t4c, t4d, t8a, t8b, c16;
+      csa(t2a, p[0], p[0], x[0], x[1]);
+      csa(t2b, p[0], p[0], x[2], x[3]);
+      csa(t2c, p[0], p[0], x[4], x[5]);
+      csa(t2d, p[0], p[0], x[6], x[7]);
+      csa(t2e, p[0], p[0], x[8], x[9]);
+      csa(t2f, p[0], p[0], x[10], x[11]);
+      csa(t2g, p[0], p[0], x[12], x[13]);
+      csa(t2h, p[0], p[0], x[14], x[15]);
+      csa(t4a, p[1], p[1], t2a, t2b);
+      csa(t4b, p[1], p[1], t2c, t2d);
+      csa(t4c, p[1], p[1], t2e, t2f);
+      csa(t4d, p[1], p[1], t2g, t2h);
+      csa(t8a, p[2], p[2], t4a, t4b);
+      csa(t8b, p[2], p[2], t4c, t4d);
+      csa(c16, p[3], p[3], t8a, t8b);
+      // ripple the weight-16 carry into planes 4..11
+      uint32_t carry = c16;
+#pragma unroll
+      for (int j = 4; j < kPlanes; j++) {
+        const uint32_t nc = p[j] & carry;
+        p[j] ^= carry;
+        carry = nc;
+      }
+    }
+    for (; r < len; r++) {  // tail rows: ripple through all planes
+      uint32_t carry = ld_stream32(colp + (size_t)s_rows[r] * Ws);
+#pragma unroll
+      for (int j = 0; j < kPlanes; j++) {
+        const uint32_t nc = p[j] & carry;
+        p[j] ^= carry;
+        carry = nc;
+      }
+    }
+  }
+  // expand the planes into 32 integer counts, transpose through shared memory, add to global with coalesced REDs
+#pragma unroll 4
+  for (int b = 0; b < 32; b++) {
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kPlanes; j++) c += (int)((p[j] >> b) & 1u) << j;
+    s_cnt[threadIdx.x * 33 + b] = c;
+  }
+  __syncthreads();
+  const int col0 = blockIdx.x * kMsTpb * 32;
+  for (int t = threadIdx.x; t < kMsTpb * 32; t += blockDim.x) {
+    const int c = s_cnt[(t >> 5) * 33 + (t & 31)];
+    if (c != 0 && col0 + t < Dpad) atomicAdd(&cnt[(size_t)k * Dpad + col0 + t], c);
+  }
+}
+
+// Fuzzy rows: one thread per genome column, fp64 accumulators per class; blockIdx.y strides over the fuzzy list.
+template <int KB>
+__global__ void __launch_bounds__(256)
+k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int* __restrict__ offsets,
+              const int* __restrict__ perm, const float* __restrict__ T, double* __restrict__ fsum /*[K][Dpad]*/,
+              int Dpad) {
+  const int f0 = offsets[K], f1 = offsets[K + 1];
+  if (f0 + (int)blockIdx.y >= f1) return;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int word = d >> 5, bit = d & 31;
+  double acc[KB];
+#pragma unroll
+  for (int k = 0; k < KB; k++) acc[k] = 0.0;
+  for (int f = f0 + blockIdx.y; f < f1; f += gridDim.y) {
+    const int row = perm[f];
+    uint32_t x = 0;
+    if (word < Ws) x = __ldg(bits + (size_t)row * Ws + word);
+    if ((x >> bit) & 1u) {
+#pragma unroll
+      for (int k = 0; k < KB; k++)
+        if (k < K) acc[k] += (double)__ldg(T + (size_t)row * K + k);
+    }
+  }
+  if (d < D) {
+#pragma unroll
+    for (int k = 0; k < KB; k++)
+      if (k < K && acc[k] != 0.0) atomicAdd(&fsum[(size_t)k * Dpad + d], acc[k]);
+  }
+}
+
+// One CTA per class: centres, inertia, dispersion, proportions and the derived E-step tables.
+__global__ void __launch_bounds__(1024)
+k_mstep_finalize(Params P, const int* __restrict__ cnt, const double* __restrict__ fsum, const int* __restrict__ nk_cnt,
+                 const double* __restrict__ nk_fz, long long N_total) {
+  __shared__ double s_red[32];
+  __shared__ double s_bcast;
+  __shared__ int s_half;
+  const int k = blockIdx.x, K = P.K, D = P.D, Dpad = P.Dpad, Ws = P.Ws;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const double nk = (double)nk_cnt[k] + nk_fz[k];
+  if (threadIdx.x == 0) s_half = 0;
+  __syncthreads();
+  if (!(nk > kEps)) {  // empty class: nem_mod.c:1399-1403 -> STS_W_EMPTYCLASS, parameters kept
+    if (threadIdx.x == 0) atomicMax(P.status, 1);
+    return;
+  }
+  // pass 1: centres (weighted median of a 0/1 column, nem_mod.c:1417-1474) and inertia (nem_mod.c:1641-1699)
+  double iner_sum = 0.0;
+  int any_half = 0;
+  for (int d0 = 0; d0 < Dpad; d0 += blockDim.x) {
+    const int d = d0 + threadIdx.x;
+    float m = 0.0f;
+    double iner = 0.0;
+    if (d < D) {
+      const double s1 = (double)cnt[(size_t)k * Dpad + d] + fsum[(size_t)k * Dpad + d];
+      const double s0 = nk - s1;
+      if (s1 > s0) { m = 1.0f; iner = s0; }
+      else if (s1 < s0) { m = 0.0f; iner = s1; }
+      else { m = 0.5f; iner = 0.5 * nk; any_half = 1; }   // exact tie: midway between a 0 and a 1 (nem_mod.c:1463-1471)
+      P.mu[(size_t)k * D + d] = m;
+      if (P.free_disp) {
+        const float e = (float)(iner / nk);                // nem_mod.c:1162-1163
+        P.eps[(size_t)k * D + d] = e;
+      }
+    }
+    iner_sum += iner;
+    const unsigned b1 = __ballot_sync(0xffffffffu, m == 1.0f);
+    const unsigned bv = __ballot_sync(0xffffffffu, m != 0.5f);
+    if (lane == 0 && (d >> 5) < Ws) {
+      P.m1[(size_t)k * Ws + (d >> 5)] = b1;
+      P.valid[(size_t)k * Ws + (d >> 5)] = bv;
+    }
+    if (!P.free_disp) {
+      // stash per-column inertia is not needed for sk_: only the sum
+    }
+  }
+  if (any_half) atomicOr(&s_half, 1);
+  // block reduction of iner_sum (fixed order: deterministic)
+  for (int off = 16; off > 0; off >>= 1) iner_sum += __shfl_xor_sync(0xffffffffu, iner_sum, off);
+  if (lane == 0) s_red[wid] = iner_sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < nw; q++) t += s_red[q];
+    s_bcast = t;
+    const float pkf = (float)(nk / (double)N_total);       // nem_mod.c:455-459
+    P.pk[k] = pkf;
+    const double lp = ((double)pkf > kEps) ? log((double)pkf) : -INFINITY;  // nem_alg.c:2350-2356
+    P.logpk32[k] = (float)lp;
+    P.logpk64[k] = lp;
+    if (s_half) atomicOr(P.has_half, 1);
+  }
+  __syncthreads();
+  if (!P.free_disp) {
+    // one dispersion per class: sum_d Iner / sum_d N_kd (nem_mod.c:1053-1068, MISSING_IGNORE)
+    const float e = (float)(s_bcast / ((double)D * nk));
+    for (int d = threadIdx.x; d < D; d += blockDim.x) P.eps[(size_t)k * D + d] = e;
+    if (threadIdx.x == 0) {
+      if (e > kEps) {
+        P.L[k] = log((double)((1.0f - e) / e));            // float ratio, double log (nem_mod.c:660)
+        P.B[k] = (double)D * log((double)(1.0f - e));
+      } else {
+        P.L[k] = INFINITY;
+        P.B[k] = 0.0;
+      }
+    }
+  } else {
+    __syncthreads();
+    double bsum = 0.0;
+    for (int d0 = 0; d0 < Dpad; d0 += blockDim.x) {
+      const int d = d0 + threadIdx.x;
+      double Lv = 0.0;
+      if (d < D) {
+        const float e = P.eps[(size_t)k * D + d];
+        if (e > kEps) { Lv = log((double)((1.0f - e) / e)); bsum += log((double)(1.0f - e)); }
+        else Lv = INFINITY;
+      }
+      if (d < Dpad) P.L[(size_t)k * Dpad + d] = Lv;
+    }
+    for (int off = 16; off > 0; off >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+    __syncthreads();
+    if (lane == 0) s_red[wid] = bsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int q = 0; q < nw; q++) t += s_red[q];
+      P.B[k] = t;
+    }
+  }
+}
+
+// per-word totals of L_kd for the complement trick of k_density_skd
+__global__ void k_lword(const double* __restrict__ Lkd, int K, int Ws, int Dpad, double* __restrict__ Lword) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= K * Ws) return;
+  const int k = t / Ws, c = t % Ws;
+  const double* p = Lkd + (size_t)k * Dpad + (size_t)c * 32;
+  double s = 0.0;
+  for (int b = 0; b < 32; b++) s += p[b];
+  Lword[t] = s;
+}
+
+// initial parameters: partition.py:65-85 (values) + nem_exe.c:1023-1040 (last proportion by subtraction)
+__global__ void k_init_params(Params P, float base_prop, const float* __restrict__ eps_k /*[K] host-computed*/) {
+  const int K = P.K, D = P.D, Ws = P.Ws, Dpad = P.Dpad;
+  const int k = blockIdx.x;
+  const bool one = (double)(k + 1) <= (double)K / 2.0;
+  const float e = eps_k[k];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    P.mu[(size_t)k * D + d] = one ? 1.0f : 0.0f;
+    P.eps[(size_t)k * D + d] = e;
+  }
+  for (int c = threadIdx.x; c < Ws; c += blockDim.x) {
+    uint32_t m = 0;
+    if (one) {
+      const int lo = c * 32;
+      const int n = D - lo;
+      m = n >= 32 ? 0xffffffffu : (n > 0 ? ((1u << n) - 1u) : 0u);
+    }
+    P.m1[(size_t)k * Ws + c] = m;
+    P.valid[(size_t)k * Ws + c] = 0xffffffffu;
+  }
+  const double Lv = (e > kEps) ? log((double)((1.0f - e) / e)) : INFINITY;
+  const double l1 = (e > kEps) ? log((double)(1.0f - e)) : 0.0;
+  if (P.free_disp) {
+    for (int d = threadIdx.x; d < Dpad; d += blockDim.x) P.L[(size_t)k * Dpad + d] = d < D ? Lv : 0.0;
+  }
+  if (threadIdx.x == 0) {
+    float pK = 1.0f;
+    for (int q = 0; q < K - 1; q++) pK = pK - base_prop;
+    const float pkf = (k < K - 1) ? base_prop : pK;
+    P.pk[k] = pkf;
+    const double lp = ((double)pkf > kEps) ? log((double)pkf) : -INFINITY;
+    P.logpk32[k] = (float)lp;
+    P.logpk64[k] = lp;
+    if (!P.free_disp) P.L[k] = Lv;
+    P.B[k] = (double)D * l1;
+    if (k == 0) { *P.has_half = 0; *P.status = 0; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Criteria (nem_alg.c:2764-2843).  One warp per row, lane k = class k; per-block partial sums, reduced by k_crit_reduce.
+// ------------------------------------------------------------------------------------------------------------------
+struct CritArgs {
+  long long N;
+  int K;
+  const double* logf;
+  const float* pk;
+  const float* logpk32;
+  const double* logpk64;
+  const float* T;
+  const int* rowptr;
+  const int* col;
+  const float* w;
+  float beta;
+  int logspace;
+  double* partial;  // [gridDim.x][4]  D, G, L, Z
+};
+
+__global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
+  __shared__ double s_part[8][4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int K = a.K;
+  const int k = lane < K ? lane : K - 1;
+  double accD = 0, accG = 0, accL = 0, accZ = 0;
+  for (long long i = warp_global; i < a.N; i += nwarps) {
+    const float cik = a.T[(size_t)i * K + k];
+    float pik = 0.0f;
+    if (a.rowptr != nullptr) {
+      const int n0 = a.rowptr[i], n1 = a.rowptr[i + 1];
+      for (int n = n0; n < n1; n++) pik = __fadd_rn(pik, __fmul_rn(a.w[n], a.T[(size_t)a.col[n] * K + k]));
+    }
+    const double lf = a.logf[(size_t)i * K + k];
+    double dik = 0.0, gik = 0.0, term_l, zterm;
+    if (!a.logspace) {
+      const float lf32 = (lf == -INFINITY) ? -FLT_MAX : (float)lf;
+      const double f = (lf == -INFINITY) ? 0.0 : exp((double)lf32);
+      const double pkf = (double)a.pk[k] * f;
+      const float lpf32 = __fadd_rn(a.logpk32[k], lf32);
+      if (cik > FLT_MIN) {
+        dik = (double)(float)((double)cik * ((double)lpf32 - log((double)cik)));
+        gik = (double)__fmul_rn(cik, pik);
+      }
+      term_l = pkf;
+      zterm = exp((double)__fmul_rn(a.beta, pik));
+    } else {
+      const double av = a.logpk64[k] + lf;
+      if (cik > FLT_MIN) {
+        dik = (double)cik * (av - log((double)cik));
+        gik = (double)cik * (double)pik;
+      }
+      term_l = av;
+      zterm = exp((double)a.beta * (double)pik);
+    }
+    if (lane >= K) { dik = 0; gik = 0; zterm = 0; term_l = a.logspace ? -INFINITY : 0.0; }
+    double rowD = 0, rowG = 0, rowL, rowZ;
+    if (!a.logspace) {
+      double fi = 0.0;
+      float zi = 0.0f;
+      for (int kk = 0; kk < K; kk++) {
+        fi = fi + __shfl_sync(0xffffffffu, term_l, kk);
+        zi = (float)((double)zi + __shfl_sync(0xffffffffu, zterm, kk));
+        rowD += __shfl_sync(0xffffffffu, dik, kk);
+        rowG += __shfl_sync(0xffffffffu, gik, kk);
+      }
+      rowL = log(fi);
+      rowZ = -log((double)zi);
+    } else {
+      double m = term_l;
+      for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+      double s = 0.0, zi = 0.0;
+      const double e = (lane < K && m > -INFINITY) ? exp(term_l - m) : 0.0;
+      for (int kk = 0; kk < K; kk++) {
+        s += __shfl_sync(0xffffffffu, e, kk);
+        zi += __shfl_sync(0xffffffffu, zterm, kk);
+        rowD += __shfl_sync(0xffffffffu, dik, kk);
+        rowG += __shfl_sync(0xffffffffu, gik, kk);
+      }
+      rowL = (m > -INFINITY) ? m + log(s) : -INFINITY;
+      rowZ = -log(zi);
+    }
+    accD += rowD; accG += rowG; accL += rowL; accZ += rowZ;
+  }
+  if (lane == 0) { s_part[wid][0] = accD; s_part[wid][1] = accG; s_part[wid][2] = accL; s_part[wid][3] = accZ; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += s_part[q][threadIdx.x];
+    a.partial[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
+  }
+}
+
+__global__ void k_crit_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ out4) {
+  if (threadIdx.x < 4 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; b++) t += partial[(size_t)b * 4 + threadIdx.x];
+    out4[threadIdx.x] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Labels + entropy from "%5.3f"-rounded posteriors (partition.py:206-231, nem_exe.c:1682).
+// v * 1000 is exact in double for a float32 v (24 + 10 significant bits), so rint() (ties to even) reproduces printf.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_labels(const float* __restrict__ T, long long N, int K, int* __restrict__ labels, double* __restrict__ ent_partial) {
+  __shared__ double s_e[8];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double ent = 0.0;
+  if (i < N) {
+    double mx = -1.0;
+    int arg = -1, nmax = 0;
+    for (int k = 0; k < K; k++) {
+      const double v = rint((double)T[(size_t)i * K + k] * 1000.0) / 1000.0;
+      if (v > 0) ent += log(v) * v;
+      if (v > mx) { mx = v; arg = k; nmax = 1; }
+      else if (v == mx) nmax++;
+    }
+    labels[i] = (nmax > 1 || mx < 0.5) ? -1 : arg;
+  }
+  for (int off = 16; off > 0; off >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, off);
+  if ((threadIdx.x & 31) == 0) s_e[threadIdx.x >> 5] = ent;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += s_e[q];
+    ent_partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void k_sum_partials(const double* __restrict__ p, int n, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < n; i++) t += p[i];
+    *out = t;
+  }
+}
+
+}  // namespace nemb200

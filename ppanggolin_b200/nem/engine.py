@@ -1,0 +1,350 @@
+"""Python side of the C ABI in ``include/nemb200.h`` (``libnemb200.so``: hand-written sm_100a CUDA).
+
+PyTorch is plumbing here: device memory (tensors), the current CUDA stream and ``torch.distributed``.  The compute
+entry points are registered as ``torch.library`` custom ops (``ppanggolin_b200::nem_run``) whose implementation passes
+raw device pointers to the C ABI through ctypes.  There is no CPU fallback: if the shared library is missing or no
+CUDA device is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent.parent
+LIB_PATH = PKG_DIR / "libnemb200.so"
+
+EPI_REF = 0
+EPI_LOGSPACE = 1
+JACOBI = 2
+MAX_K = 32
+
+STS_OK, STS_EMPTYCLASS, STS_INFINITE = 0, 1, 2
+
+
+class NemB200Error(RuntimeError):
+    pass
+
+
+class _Result(ctypes.Structure):
+    _fields_ = [("crit", ctypes.c_double * 5), ("n_iter", ctypes.c_int32), ("converged", ctypes.c_int32),
+                ("status", ctypes.c_int32), ("n_levels", ctypes.c_int32), ("elapsed_ms", ctypes.c_float)]
+
+
+_lib = None
+_vp, _i64, _i32, _u32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_float
+
+# every symbol include/nemb200.h declares, with its ctypes signature
+SIGNATURES = {
+    "nemb200_abi_version": (ctypes.c_int, []),
+    "nemb200_last_error": (ctypes.c_char_p, []),
+    "nemb200_device_count": (ctypes.c_int, []),
+    "nemb200_nem_host": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _f32, _u32,
+                                        _vp, _vp, _vp, _vp, ctypes.POINTER(_Result)]),
+    "nemb200_nem_device": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _i32,
+                                          _f32, _u32, _vp, _vp, _vp, _vp, ctypes.POINTER(_Result), _vp]),
+    "nemb200_gs_schedule": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp]),
+    "nemb200_plan_create": (ctypes.c_int, [ctypes.POINTER(_vp), _i64, _i64, _i64, _i64, _i32, _i32, _u32]),
+    "nemb200_plan_destroy": (None, [_vp]),
+    "nemb200_init_params": (ctypes.c_int, [_vp, _vp]),
+    "nemb200_mstep_accumulate": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "nemb200_stats_ptrs": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                                          ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
+    "nemb200_mstep_finalize": (ctypes.c_int, [_vp, _vp]),
+    "nemb200_density": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "nemb200_sweep": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp]),
+    "nemb200_criteria": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f32, ctypes.POINTER(ctypes.c_double * 5), _vp]),
+    "nemb200_get_params": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.POINTER(_i32), _vp]),
+    "nemb200_labels": (ctypes.c_int, [_vp, _i64, _i32, _vp, ctypes.POINTER(ctypes.c_double), _vp]),
+}
+
+
+def lib():
+    """Load ``libnemb200.so`` (built in-tree by ``__graft_entry__.build()``).  Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.is_file():
+            raise NemB200Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback for the NEM path)")
+        L = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().nemb200_last_error()
+        raise NemB200Error(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise NemB200Error("no CUDA device: the NEM path runs only on the GPU (no CPU fallback)")
+    return torch
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else int(t.data_ptr())
+
+
+def _stream() -> int:
+    return int(_torch().cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class NemRun:
+    """Outcome of one NEM instance (what nem() leaves in .uf/.mf, nem_exe.c:1601-1786)."""
+    T: object                      # (N, K) float32 posteriors: torch tensor (device run) or numpy array (host run)
+    mu: np.ndarray                 # (K, D) float32 in {0, 0.5, 1}
+    eps: np.ndarray                # (K, D) float32
+    pk: np.ndarray                 # (K,) float32
+    crit: list                     # U, D, L, M, Z
+    n_iter: int
+    converged: bool
+    status: int
+    n_levels: int
+    elapsed_ms: float
+
+    @property
+    def ok(self) -> bool:
+        return self.status == STS_OK
+
+
+def gs_schedule(rowptr: np.ndarray, col: np.ndarray):
+    """Level schedule of the in-place (Gauss-Seidel) sweep; host helper."""
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    col = np.ascontiguousarray(col, np.int32)
+    N = len(rowptr) - 1
+    lp = np.zeros(N + 1, np.int32)
+    rows = np.zeros(N, np.int32)
+    nl = lib().nemb200_gs_schedule(N, rowptr.ctypes.data, col.ctypes.data if len(col) else 0, lp.ctypes.data, rows.ctypes.data)
+    if nl < 0:
+        _check(nl, "nemb200_gs_schedule")
+    return lp[: nl + 1].copy(), rows, nl
+
+
+def nem_run_host(bits: np.ndarray, D: int, rowptr, col, w, K: int, beta: float, free_dispersion: bool = False,
+                 itermax: int = 100, cv_th: float = 0.01, flags: int = EPI_REF) -> NemRun:
+    """Whole run through the host-buffer entry (host<->device copies inside): the drop-in for ``nem_stats.nem``."""
+    _require_cuda()
+    bits = np.ascontiguousarray(bits).view(np.uint32)
+    N, Ws = bits.shape
+    T = np.empty((N, K), np.float32); mu = np.empty((K, D), np.float32); eps = np.empty((K, D), np.float32)
+    pk = np.empty(K, np.float32)
+    res = _Result()
+    if beta != 0:
+        rowptr = np.ascontiguousarray(rowptr, np.int32); col = np.ascontiguousarray(col, np.int32)
+        w = np.ascontiguousarray(w, np.float32)
+        rp, cp, wp = rowptr.ctypes.data, col.ctypes.data, w.ctypes.data
+    else:
+        rp = cp = wp = 0
+    rc = lib().nemb200_nem_host(bits.ctypes.data, N, D, Ws, rp, cp, wp, K, float(np.float32(beta)), int(free_dispersion),
+                                itermax, cv_th, flags, T.ctypes.data, mu.ctypes.data, eps.ctypes.data, pk.ctypes.data,
+                                ctypes.byref(res))
+    _check(rc, "nemb200_nem_host")
+    return NemRun(T, mu, eps, pk, list(res.crit), res.n_iter, bool(res.converged), res.status, res.n_levels, res.elapsed_ms)
+
+
+@dataclass
+class DeviceInput:
+    """One NEM instance resident in HBM."""
+    bits: object                   # torch int32 (N, Ws) on cuda
+    D: int
+    rowptr: Optional[object] = None
+    col: Optional[object] = None
+    w: Optional[object] = None
+    sched_ptr: Optional[object] = None
+    sched_rows: Optional[object] = None
+    n_levels: int = 1
+
+    @property
+    def N(self) -> int:
+        return int(self.bits.shape[0])
+
+    @staticmethod
+    def from_numpy(bits: np.ndarray, D: int, rowptr=None, col=None, w=None, device="cuda") -> "DeviceInput":
+        torch = _require_cuda()
+        b = torch.from_numpy(np.ascontiguousarray(bits).view(np.int32)).to(device)
+        di = DeviceInput(b, D)
+        if rowptr is not None and len(col) > 0:
+            lp, rows, nl = gs_schedule(rowptr, col)
+            di.rowptr = torch.from_numpy(np.ascontiguousarray(rowptr, np.int32)).to(device)
+            di.col = torch.from_numpy(np.ascontiguousarray(col, np.int32)).to(device)
+            di.w = torch.from_numpy(np.ascontiguousarray(w, np.float32)).to(device)
+            di.sched_ptr = torch.from_numpy(lp).to(device)
+            di.sched_rows = torch.from_numpy(rows).to(device)
+            di.n_levels = nl
+        return di
+
+
+def _nem_run_device_impl(bits, rowptr, col, w, sched_ptr, sched_rows, D: int, n_levels: int, K: int, beta: float,
+                         free_disp: int, itermax: int, cv_th: float, flags: int):
+    torch = _torch()
+    N, Ws = bits.shape
+    dev = bits.device
+    T = torch.empty((N, K), dtype=torch.float32, device=dev)
+    mu = torch.empty((K, D), dtype=torch.float32, device=dev)
+    eps = torch.empty((K, D), dtype=torch.float32, device=dev)
+    pk = torch.empty((K,), dtype=torch.float32, device=dev)
+    res = _Result()
+    with torch.cuda.device(dev):
+        rc = lib().nemb200_nem_device(_ptr(bits), N, D, Ws, _ptr(rowptr), _ptr(col), _ptr(w), _ptr(sched_ptr),
+                                      _ptr(sched_rows), n_levels, K, beta, free_disp, itermax, cv_th, flags, _ptr(T),
+                                      _ptr(mu), _ptr(eps), _ptr(pk), ctypes.byref(res), _stream())
+    _check(rc, "nemb200_nem_device")
+    stats = torch.tensor(list(res.crit) + [res.n_iter, res.converged, res.status, res.n_levels, res.elapsed_ms],
+                         dtype=torch.float64)
+    return T, mu, eps, pk, stats
+
+
+_op_registered = False
+
+
+def _register_op():
+    """``ppanggolin_b200::nem_run`` as a torch.library custom op (opaque to autograd/compile; CUDA only)."""
+    global _op_registered
+    if _op_registered:
+        return
+    torch = _torch()
+    torch.library.define(
+        "ppanggolin_b200::nem_run",
+        "(Tensor bits, Tensor? rowptr, Tensor? col, Tensor? w, Tensor? sched_ptr, Tensor? sched_rows, int D, "
+        "int n_levels, int K, float beta, int free_disp, int itermax, float cv_th, int flags) "
+        "-> (Tensor, Tensor, Tensor, Tensor, Tensor)")
+
+    @torch.library.impl("ppanggolin_b200::nem_run", "CUDA")
+    def nem_run(bits, rowptr, col, w, sched_ptr, sched_rows, D, n_levels, K, beta, free_disp, itermax, cv_th, flags):
+        return _nem_run_device_impl(bits, rowptr, col, w, sched_ptr, sched_rows, D, n_levels, K, beta, free_disp,
+                                    itermax, cv_th, flags)
+
+    _op_registered = True
+
+
+def nem_run_device(inp: DeviceInput, K: int, beta: float, free_dispersion: bool = False, itermax: int = 100,
+                   cv_th: float = 0.01, flags: int = EPI_REF) -> NemRun:
+    """Whole run with the instance already resident in HBM (the custom op)."""
+    torch = _require_cuda()
+    if not (1 <= K <= MAX_K):
+        raise NemB200Error(f"K={K} outside 1..{MAX_K}")
+    _register_op()
+    beta32 = float(np.float32(beta))
+    use_graph = beta32 != 0.0 and inp.rowptr is not None
+    if beta32 != 0.0 and inp.rowptr is None:
+        raise NemB200Error("beta != 0 needs the neighbour graph")
+    T, mu, eps, pk, stats = torch.ops.ppanggolin_b200.nem_run(
+        inp.bits, inp.rowptr if use_graph else None, inp.col if use_graph else None, inp.w if use_graph else None,
+        inp.sched_ptr if use_graph else None, inp.sched_rows if use_graph else None, inp.D,
+        inp.n_levels if use_graph else 1, K, beta32, int(free_dispersion), itermax, cv_th, flags)
+    s = stats.tolist()
+    return NemRun(T, mu.cpu().numpy(), eps.cpu().numpy(), pk.cpu().numpy(), s[:5], int(s[5]), bool(s[6]), int(s[7]),
+                  int(s[8]), float(s[9]))
+
+
+def labels_device(T):
+    """(labels int32 tensor with -1 for "S_", entropy) from ``%5.3f``-rounded posteriors (partition.py:206-231)."""
+    torch = _require_cuda()
+    N, K = T.shape
+    lab = torch.empty((N,), dtype=torch.int32, device=T.device)
+    ent = ctypes.c_double(0.0)
+    with torch.cuda.device(T.device):
+        rc = lib().nemb200_labels(_ptr(T), N, K, _ptr(lab), ctypes.byref(ent), _stream())
+    _check(rc, "nemb200_labels")
+    return lab, float(ent.value)
+
+
+class Plan:
+    """Stepwise interface (one rank's rows): used by the row-sharded multi-GPU driver and the kernel parity tests."""
+
+    def __init__(self, N_local: int, N_total: int, D: int, Ws: int, K: int, free_dispersion: bool = False, flags: int = EPI_REF):
+        torch = _require_cuda()
+        self.N_local, self.N_total, self.D, self.Ws, self.K = N_local, N_total, D, Ws, K
+        self.free_dispersion, self.flags = bool(free_dispersion), flags
+        h = _vp()
+        _check(lib().nemb200_plan_create(ctypes.byref(h), N_local, N_total, D, Ws, K, int(free_dispersion), flags), "plan_create")
+        self._h = h
+        cnt, fsum, nkc, nkf, dpad = _vp(), _vp(), _vp(), _vp(), _i64()
+        _check(lib().nemb200_stats_ptrs(self._h, ctypes.byref(cnt), ctypes.byref(fsum), ctypes.byref(nkc),
+                                        ctypes.byref(nkf), ctypes.byref(dpad)), "stats_ptrs")
+        self.Dpad = int(dpad.value)
+        self._stat_ptrs = (cnt.value, fsum.value, nkc.value, nkf.value)
+        self._views = None
+
+    def close(self):
+        if self._h is not None:
+            lib().nemb200_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats_tensors(self):
+        """Torch views (no copy) of the plan's statistic buffers, for in-place all-reduce: cnt int32 [K, Dpad],
+        fsum float64 [K, Dpad], nk_cnt int32 [K], nk_fz float64 [K]."""
+        if self._views is None:
+            torch = _torch()
+            K, Dp = self.K, self.Dpad
+            dev = torch.cuda.current_device()
+
+            def view(ptr, shape, typestr):
+                class _A:
+                    pass
+                a = _A()
+                a.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+                return torch.as_tensor(a, device=f"cuda:{dev}")
+            cnt, fsum, nkc, nkf = self._stat_ptrs
+            self._views = (view(cnt, (K, Dp), "<i4"), view(fsum, (K, Dp), "<f8"), view(nkc, (K,), "<i4"), view(nkf, (K,), "<f8"))
+        return self._views
+
+    def init_params(self):
+        _check(lib().nemb200_init_params(self._h, _stream()), "init_params")
+
+    def mstep_accumulate(self, bits, T):
+        _check(lib().nemb200_mstep_accumulate(self._h, _ptr(bits), _ptr(T), _stream()), "mstep_accumulate")
+
+    def mstep_finalize(self):
+        _check(lib().nemb200_mstep_finalize(self._h, _stream()), "mstep_finalize")
+
+    def density(self, bits, logf):
+        _check(lib().nemb200_density(self._h, _ptr(bits), _ptr(logf), _stream()), "density")
+
+    def sweep(self, N, logf, T_old, T_new, inp: Optional[DeviceInput], beta_now: float, maxdiff):
+        g = inp is not None and inp.rowptr is not None
+        _check(lib().nemb200_sweep(self._h, N, _ptr(logf), _ptr(T_old), _ptr(T_new), _ptr(inp.rowptr) if g else 0,
+                                   _ptr(inp.col) if g else 0, _ptr(inp.w) if g else 0, _ptr(inp.sched_ptr) if g else 0,
+                                   _ptr(inp.sched_rows) if g else 0, inp.n_levels if g else 1,
+                                   float(np.float32(beta_now)), _ptr(maxdiff), _stream()), "sweep")
+
+    def criteria(self, N, logf, T, inp: Optional[DeviceInput], beta: float):
+        g = inp is not None and inp.rowptr is not None
+        out = (ctypes.c_double * 5)()
+        _check(lib().nemb200_criteria(self._h, N, _ptr(logf), _ptr(T), _ptr(inp.rowptr) if g else 0, _ptr(inp.col) if g else 0,
+                                      _ptr(inp.w) if g else 0, float(np.float32(beta)), ctypes.byref(out), _stream()), "criteria")
+        return list(out)
+
+    def get_params_status(self) -> int:
+        st = _i32(0)
+        _check(lib().nemb200_get_params(self._h, 0, 0, 0, ctypes.byref(st), _stream()), "get_params")
+        return int(st.value)
+
+    def get_params(self):
+        mu = np.empty((self.K, self.D), np.float32); eps = np.empty((self.K, self.D), np.float32)
+        pk = np.empty(self.K, np.float32); st = _i32(0)
+        _check(lib().nemb200_get_params(self._h, mu.ctypes.data, eps.ctypes.data, pk.ctypes.data, ctypes.byref(st), _stream()), "get_params")
+        return mu, eps, pk, int(st.value)

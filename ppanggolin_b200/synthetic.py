@@ -167,25 +167,35 @@ def backbone_graph(N: int, p: np.ndarray, rng, sm_degree: float = 10):
     return rowptr, c.astype(np.int32), wr.astype(np.float32), edges_weight
 
 
-def synth_pangenome_large(N: int, D: int, seed: int = 42, device="cuda", rows_per_block: int = 4096) -> SynthPangenome:
-    """Bit-packed matrix generated block by block on ``device`` (torch); graph from :func:`backbone_graph`."""
+def synth_pangenome_large(N: int, D: int, seed: int = 42, device="cuda", rows=None, rows_per_block: int = 2048) -> SynthPangenome:
+    """Bit-packed matrix generated block by block on ``device`` (torch); graph from :func:`backbone_graph`.
+
+    ``rows=(lo, hi)`` generates only that row range (one rank's shard of a row-sharded run); blocks are seeded by their
+    absolute position, so the union of the shards is the same matrix for every world size."""
     import torch
 
     rng = np.random.default_rng(seed)
     cls, p = _family_probs(N, rng)
+    lo, hi = (0, N) if rows is None else rows
     W = row_stride_words(D)
-    gen = torch.Generator(device=device); gen.manual_seed(seed)
-    bits = torch.empty((N, W), dtype=torch.int32, device=device)
+    gen = torch.Generator(device=device)
+    bits = torch.empty((hi - lo, W), dtype=torch.int32, device=device)
     shifts = torch.arange(32, device=device, dtype=torch.int64)
     pt = torch.from_numpy(p.astype(np.float32)).to(device)
-    for r0 in range(0, N, rows_per_block):
+    b0 = (lo // rows_per_block) * rows_per_block
+    for r0 in range(b0, hi, rows_per_block):
         r1 = min(N, r0 + rows_per_block)
+        gen.manual_seed(seed * 1_000_003 + r0)
         u = torch.rand((r1 - r0, W * 32), device=device, generator=gen)
         x = (u < pt[r0:r1, None])
+        del u
         x[:, D:] = False
         none = ~x.any(1)
         x[none, 0] = True  # all-zero families get one gene (they would not be in the matrix, partition.py:384)
         words = (x.view(r1 - r0, W, 32).to(torch.int64) << shifts).sum(-1)
-        bits[r0:r1] = (words & 0xFFFFFFFF).to(torch.int64).where(words < 2**31, words - 2**32).to(torch.int32)
+        words = torch.where(words >= 2**31, words - 2**32, words).to(torch.int32)
+        a, b = max(r0, lo), min(r1, hi)
+        bits[a - lo:b - lo] = words[a - r0:b - r0]
+        del x, words
     rowptr, col, w, ew = backbone_graph(N, p, rng)
     return SynthPangenome(None, bits, rowptr, col, w, ew, cls, N, D)

@@ -1,0 +1,67 @@
+"""numpy closed forms of the individual kernels (test helpers; not product code)."""
+import numpy as np
+
+
+def init_params(K, D):
+    import math
+    base = np.float32(float(format(1.0 / K, ".12g")))
+    pk = np.full(K, base, np.float32)
+    pK = np.float32(1.0)
+    for _ in range(K - 1):
+        pK = np.float32(pK - base)
+    pk[K - 1] = pK
+    step = 0.5 / math.ceil(K / 2)
+    pich = 0.1 if K == 2 else 0
+    mu = np.zeros((K, D), np.float32); eps = np.zeros((K, D), np.float32)
+    for k in range(1, K + 1):
+        if k <= K / 2:
+            mu[k - 1] = 1; eps[k - 1] = np.float32(step * k - pich)
+        else:
+            eps[k - 1] = np.float32(step * (K - k + 1) - pich)
+    return pk, mu, eps
+
+
+def logf(X, mu, eps):
+    """log f_k(x_i) in float64 with the float32 ratio of nem_mod.c:660."""
+    X = X.astype(np.float64)
+    K, D = mu.shape
+    out = np.zeros((X.shape[0], K))
+    for k in range(K):
+        e = eps[k].astype(np.float32)
+        pos = e > 1e-20
+        with np.errstate(divide="ignore"):
+            L = np.where(pos, np.log(((np.float32(1) - e) / np.where(pos, e, 1)).astype(np.float64)), np.inf)
+            l1 = np.where(pos, np.log((np.float32(1) - e).astype(np.float64)), 0.0)
+        mism = (X != mu[k][None, :]) & (mu[k][None, :] != 0.5)
+        with np.errstate(invalid="ignore"):
+            s = np.where(mism, L[None, :], 0.0).sum(1)
+        out[:, k] = l1.sum() - s
+    return out
+
+
+def softmax_ref_epilogue(lf, pk):
+    """beta = 0 posterior with the reference arithmetic (float32 logf, double exp, S == 0 -> 1/K)."""
+    K = lf.shape[1]
+    f = np.exp(lf.astype(np.float32).astype(np.float64))
+    num = pk.astype(np.float64)[None, :] * f
+    S = num.sum(1, keepdims=True)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        T = np.where(S > 0, num / S, 1.0 / K)
+    return T.astype(np.float32)
+
+
+def mstep(X, T, free_disp):
+    """fp64 M-step: centres by weighted median of a binary column, inertia, dispersion, proportions."""
+    X = X.astype(np.float64); Td = T.astype(np.float64)
+    N, D = X.shape; K = T.shape[1]
+    nk = Td.sum(0)
+    s1 = Td.T @ X
+    s0 = nk[:, None] - s1
+    mu = np.where(s1 > s0, 1.0, np.where(s1 < s0, 0.0, 0.5)).astype(np.float32)
+    iner = np.where(s1 > s0, s0, np.where(s1 < s0, s1, 0.5 * nk[:, None]))
+    if free_disp:
+        eps = (iner / nk[:, None]).astype(np.float32)
+    else:
+        eps = np.repeat((iner.sum(1) / (D * nk)).astype(np.float32)[:, None], D, 1)
+    pk = (nk / N).astype(np.float32)
+    return mu, eps, pk, s1, nk
