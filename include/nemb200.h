@@ -117,11 +117,16 @@ int nemb200_density(nemb200_plan* plan, const uint32_t* bits, double* logf, void
 
 /* E-step, part 2 (nem_alg.c:2412-2489, :2630-2701): posterior sweep over rows [0, N) of logf/T (full-length arrays),
  * reading T_old and writing T_new; maxdiff_bits receives max |T_new - T_old| as float bits (atomicMax).
- * beta_now lets the caller run the "blind" beta = 0 pass of nem_alg.c:2043-2050. */
+ * beta_now lets the caller run the "blind" beta = 0 pass of nem_alg.c:2043-2050.  maxdiff_bits == NULL uses (and first
+ * resets) the plan's own convergence word, which nemb200_read_flags returns together with the status word. */
 int nemb200_sweep(nemb200_plan* plan, int64_t N, const double* logf, const float* T_old, float* T_new,
                   const int32_t* rowptr, const int32_t* col, const float* w,
                   const int32_t* sched_level_ptr, const int32_t* sched_rows, int32_t n_levels,
                   float beta_now, uint32_t* maxdiff_bits, void* stream);
+
+/* nem_alg.c:2160-2173 (HasConverged, CVTEST_CLAS) needs max |T_new - T_old|; nem_alg.c:1873-1892 needs the empty-class
+ * status.  Both in one 8-byte device->host read (synchronises the stream). */
+int nemb200_read_flags(nemb200_plan* plan, float* maxdiff, int32_t* status, void* stream);
 
 /* nem_alg.c:2764-2843: criteria U, D, L, M, Z for final posteriors T (host output, synchronises the stream). */
 int nemb200_criteria(nemb200_plan* plan, int64_t N, const double* logf, const float* T,

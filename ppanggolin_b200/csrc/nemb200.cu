@@ -67,6 +67,10 @@ struct nemb200_plan {
   int* cls = nullptr;       // [N_local]
   int* perm = nullptr;      // [N_local]
   double* Lword = nullptr;  // [K][Ws] (skd)
+  double* fin_partial = nullptr;  // [K][nchunk][2]
+  int* fin_tickets = nullptr;     // [K]
+  uint32_t* flags2 = nullptr;     // [0] max |T_new - T_old| as float bits, [1] status (P.status points here)
+  int fin_chunks = 0;
   float* eps_init = nullptr;
   double* crit_partial = nullptr;
   double* crit4 = nullptr;
@@ -110,11 +114,15 @@ extern "C" int nemb200_plan_create(nemb200_plan** out, int64_t N_local, int64_t 
   A(P.mu, (size_t)K * pl->D) A(P.eps, (size_t)K * pl->D)
   A(P.m1, (size_t)K * pl->Ws) A(P.valid, (size_t)K * pl->Ws)
   A(P.L, pl->free_disp ? (size_t)K * pl->Dpad : (size_t)K) A(P.B, K)
-  A(P.has_half, 1) A(P.status, 1)
+  A(P.has_half, 1) A(pl->flags2, 2)
+  P.status = (int*)(pl->flags2 + 1);
   A(pl->cnt, (size_t)K * pl->Dpad) A(pl->fsum, (size_t)K * pl->Dpad)
   A(pl->nk_cnt, K) A(pl->nk_fz, K) A(pl->hist, K + 1) A(pl->offsets, K + 2) A(pl->cursor, K + 1)
   A(pl->cls, N_local) A(pl->perm, N_local)
-  A(pl->Lword, (size_t)K * pl->Ws) A(pl->eps_init, K)
+  A(pl->Lword, (size_t)K * pl->Ws) A(pl->eps_init, K) A(P.eps_k, K)
+  pl->fin_chunks = (pl->Dpad + kFinCols - 1) / kFinCols;
+  A(pl->fin_partial, (size_t)K * pl->fin_chunks * 2) A(pl->fin_tickets, K)
+  if (cudaMemset(pl->fin_tickets, 0, K * sizeof(int)) != cudaSuccess) { nemb200_plan_destroy(pl); return fail(NEMB200_ERR_CUDA, "plan_create: memset"); }
   pl->crit_blocks = num_sms() * 4;
   A(pl->crit_partial, (size_t)pl->crit_blocks * 4) A(pl->crit4, 4)
 #undef A
@@ -194,8 +202,9 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
     k_scatter<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pl->cls, N, pl->cursor, pl->perm);
     CK(cudaGetLastError());
     const int max_segs = (int)((N + kSeg - 1) / kSeg) + K;  // upper bound on sum_k ceil(n_k / kSeg)
-    dim3 grid((pl->Ws + kMsTpb - 1) / kMsTpb, max_segs);
-    k_mstep_onehot<<<grid, kMsTpb, 0, st>>>(bits, pl->Ws, K, pl->offsets, pl->perm, pl->cnt, pl->Dpad);
+    const int W2 = pl->Ws / 2;
+    dim3 grid((W2 + kMsTpb - 1) / kMsTpb, max_segs);
+    k_mstep_onehot<<<grid, kMsTpb, 0, st>>>((const uint2*)bits, W2, K, pl->offsets, pl->perm, pl->cnt, pl->Dpad);
     CK(cudaGetLastError());
     rc = DISPATCH_KB(K, launch_fuzzy, pl, bits, T, st);
     if (rc) return rc;
@@ -218,7 +227,8 @@ extern "C" int nemb200_mstep_finalize(nemb200_plan* pl, void* stream_) {
   if (!pl) return fail(NEMB200_ERR_ARG, "mstep_finalize: null plan");
   cudaStream_t st = (cudaStream_t)stream_;
   CK(cudaMemsetAsync(pl->P.has_half, 0, sizeof(int), st));
-  k_mstep_finalize<<<pl->K, 1024, 0, st>>>(pl->P, pl->cnt, pl->fsum, pl->nk_cnt, pl->nk_fz, pl->N_total);
+  k_mstep_finalize<<<dim3(pl->fin_chunks, pl->K), 256, 0, st>>>(pl->P, pl->cnt, pl->fsum, pl->nk_cnt, pl->nk_fz, pl->N_total,
+                                                             pl->fin_partial, pl->fin_tickets);
   CK(cudaGetLastError());
   if (pl->free_disp) {
     const int n = pl->K * pl->Ws;
@@ -236,7 +246,7 @@ static int group_lanes(int units) {  // lanes cooperating on one row: smallest p
 
 template <int KB>
 static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
-  constexpr int RB = 4;
+  constexpr int RB = KB <= 4 ? 4 : (KB <= 8 ? 2 : 1);  // rows per lane group: bounded by registers (3 * RB * KB)
   const int W4 = pl->Ws / 4;
   const int G = group_lanes(W4);
   const size_t smem = (size_t)2 * pl->K * W4 * sizeof(uint4);
@@ -280,8 +290,12 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
                              const int32_t* rowptr, const int32_t* col, const float* w,
                              const int32_t* sched_level_ptr, const int32_t* sched_rows, int32_t n_levels,
                              float beta_now, uint32_t* maxdiff_bits, void* stream_) {
-  if (!pl || !logf || !T_old || !T_new || !maxdiff_bits || N < 1) return fail(NEMB200_ERR_ARG, "sweep: null argument");
+  if (!pl || !logf || !T_old || !T_new || N < 1) return fail(NEMB200_ERR_ARG, "sweep: null argument");
   cudaStream_t st = (cudaStream_t)stream_;
+  if (!maxdiff_bits) {  // use (and reset) the plan's own convergence word, read back with nemb200_read_flags
+    maxdiff_bits = pl->flags2;
+    CK(cudaMemsetAsync(pl->flags2, 0, sizeof(uint32_t), st));
+  }
   SweepArgs a;
   a.N = N; a.K = pl->K; a.logf = logf; a.pk = pl->P.pk; a.logpk64 = pl->P.logpk64; a.T_old = T_old; a.T_new = T_new;
   a.rowptr = rowptr; a.col = col; a.w = w; a.beta = beta_now;
@@ -291,22 +305,29 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
   const bool need_levels = (beta_now != 0.0f) && rowptr != nullptr && !a.jacobi;
   if (need_levels && (!sched_level_ptr || !sched_rows || n_levels < 1))
     return fail(NEMB200_ERR_ARG, "sweep: Gauss-Seidel sweep needs a level schedule (nemb200_gs_schedule)");
+  const int GS = pl->K <= 4 ? 4 : (pl->K <= 8 ? 8 : (pl->K <= 16 ? 16 : 32));
+  const long long rows_per_block = 8LL * (32 / GS);
   if (need_levels && n_levels > 1) {
     a.level_ptr = sched_level_ptr; a.level_rows = sched_rows; a.n_levels = n_levels;
+    void* fn = GS == 4 ? (void*)k_sweep<true, 4> : GS == 8 ? (void*)k_sweep<true, 8> : GS == 16 ? (void*)k_sweep<true, 16>
+                                                                                             : (void*)k_sweep<true, 32>;
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep<true>, 256, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
     if (per_sm < 1) return fail(NEMB200_ERR_CUDA, "sweep: kernel does not fit on an SM");
-    long long blocks = (long long)num_sms() * std::min(per_sm, 4);
-    const long long want = (N + 7) / 8;
+    long long blocks = (long long)num_sms() * std::min(per_sm, 2);   // few CTAs: the grid barrier is the fixed cost
+    const long long want = (N + rows_per_block - 1) / rows_per_block;
     if (blocks > want) blocks = std::max<long long>(want, 1);
     void* args[] = {&a};
-    CK(cudaLaunchCooperativeKernel((void*)k_sweep<true>, dim3((unsigned)blocks), dim3(256), args, 0, st));
+    CK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(256), args, 0, st));
   } else {
     a.level_ptr = nullptr; a.level_rows = nullptr; a.n_levels = 1;
-    long long blocks = (N + 7) / 8;
+    long long blocks = (N + rows_per_block - 1) / rows_per_block;
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    k_sweep<false><<<(unsigned)blocks, 256, 0, st>>>(a);
+    if (GS == 4) k_sweep<false, 4><<<(unsigned)blocks, 256, 0, st>>>(a);
+    else if (GS == 8) k_sweep<false, 8><<<(unsigned)blocks, 256, 0, st>>>(a);
+    else if (GS == 16) k_sweep<false, 16><<<(unsigned)blocks, 256, 0, st>>>(a);
+    else k_sweep<false, 32><<<(unsigned)blocks, 256, 0, st>>>(a);
     CK(cudaGetLastError());
   }
   return NEMB200_OK;
@@ -340,11 +361,26 @@ extern "C" int nemb200_get_params(nemb200_plan* pl, float* mu, float* eps, float
   if (!pl) return fail(NEMB200_ERR_ARG, "get_params: null plan");
   cudaStream_t st = (cudaStream_t)stream_;
   const size_t kd = (size_t)pl->K * pl->D * sizeof(float);
+  if (eps && !pl->free_disp) {
+    k_expand_eps<<<dim3(std::max(1, std::min(64, (pl->D + 255) / 256)), pl->K), 256, 0, st>>>(pl->P);
+    CK(cudaGetLastError());
+  }
   if (mu) CK(cudaMemcpyAsync(mu, pl->P.mu, kd, cudaMemcpyDeviceToHost, st));
   if (eps) CK(cudaMemcpyAsync(eps, pl->P.eps, kd, cudaMemcpyDeviceToHost, st));
   if (pk) CK(cudaMemcpyAsync(pk, pl->P.pk, pl->K * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (status) CK(cudaMemcpyAsync(status, pl->P.status, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_read_flags(nemb200_plan* pl, float* maxdiff, int32_t* status, void* stream_) {
+  if (!pl) return fail(NEMB200_ERR_ARG, "read_flags: null plan");
+  cudaStream_t st = (cudaStream_t)stream_;
+  uint32_t h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, pl->flags2, sizeof h, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (maxdiff) memcpy(maxdiff, &h[0], sizeof(float));
+  if (status) *status = (int32_t)h[1];
   return NEMB200_OK;
 }
 
@@ -443,17 +479,13 @@ static int run_em(nemb200_plan* pl, const uint32_t* bits, const int32_t* rowptr,
     if ((rc = nemb200_mstep_accumulate(pl, bits, cur, st))) return rc;
     if ((rc = nemb200_mstep_finalize(pl, st))) return rc;
     if ((rc = nemb200_density(pl, bits, rb.logf, st))) return rc;
-    CK(cudaMemsetAsync(rb.flags, 0, sizeof(uint32_t), st));
-    if ((rc = nemb200_sweep(pl, N, rb.logf, cur, other, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, beta, rb.flags, st))) return rc;
-    uint32_t hflags[2] = {0, 0};
-    CK(cudaMemcpyAsync(&hflags[0], rb.flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&hflags[1], pl->P.status, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    status = (int)hflags[1];
+    if ((rc = nemb200_sweep(pl, N, rb.logf, cur, other, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, beta, nullptr, st))) return rc;
+    float maxdif = 0.0f;
+    int32_t sts = 0;
+    if ((rc = nemb200_read_flags(pl, &maxdif, &sts, st))) return rc;   // the one device->host read of the iteration
+    status = sts;
     if (status != NEMB200_STS_OK) break;  // empty class: the reference stops before the E-step (nem_alg.c:1873-1892)
     std::swap(cur, other);
-    float maxdif;
-    memcpy(&maxdif, &hflags[0], sizeof(float));
     converged = (maxdif < cv_th);  // nem_alg.c:2160-2173
   }
   if (status == NEMB200_STS_OK) iter = iter - 1;
@@ -480,6 +512,10 @@ static int run_em(nemb200_plan* pl, const uint32_t* bits, const int32_t* rowptr,
 
 static int copy_params_out(nemb200_plan* pl, float* mu, float* eps, float* pk, cudaStream_t st) {
   const size_t kd = (size_t)pl->K * pl->D * sizeof(float);
+  if (eps && !pl->free_disp) {
+    k_expand_eps<<<dim3(std::max(1, std::min(64, (pl->D + 255) / 256)), pl->K), 256, 0, st>>>(pl->P);
+    CK(cudaGetLastError());
+  }
   if (mu) CK(cudaMemcpyAsync(mu, pl->P.mu, kd, cudaMemcpyDefault, st));
   if (eps) CK(cudaMemcpyAsync(eps, pl->P.eps, kd, cudaMemcpyDefault, st));
   if (pk) CK(cudaMemcpyAsync(pk, pl->P.pk, pl->K * sizeof(float), cudaMemcpyDefault, st));

@@ -48,6 +48,7 @@ struct Params {
   double* logpk64;  // [K]
   float* mu;        // [K][D]   {0, 0.5, 1}
   float* eps;       // [K][D]
+  float* eps_k;     // [K]   "sk_": the shared dispersion of each class
   uint32_t* m1;     // [K][Ws]  bit set where mu == 1
   uint32_t* valid;  // [K][Ws]  bit set where mu != 0.5 (a 0.5 centre never mismatches: nem_mod.c:656-657)
   double* L;        // sk_: [K]        log((1-e)/e);  skd: [K][Dpad]   (+inf where e <= 1e-20: null density on mismatch)
@@ -60,6 +61,16 @@ struct Params {
 // E-step part 1: log densities.  A group of G lanes walks RB rows at once so that each class's centre words are
 // fetched from shared memory once per RB matrix words.
 // ------------------------------------------------------------------------------------------------------------------
+// carry-save adder on 32 bit-columns at once: a + b + c = 2 * hi + lo
+__device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
+  const uint32_t u = a ^ b;
+  hi = (a & b) | (u & c);
+  lo = u ^ c;
+}
+
+// POPC issues on the quarter-rate XU pipe (measured: 80 % XU utilisation with one POPC per word and class), so the
+// mismatch words are first compressed with carry-save adders on the ALU pipe: per 4 words and class 3 CSAs (6 LOP3) and
+// a single POPC of the weight-4 carry; `ones`/`twos` carry the remainder across the row.
 template <int KB, int RB, bool HALF>
 __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, long long N, int W4, int K, int G,
                                                 const uint4* __restrict__ m1, const uint4* __restrict__ valid,
@@ -76,11 +87,13 @@ __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, 
   for (long long base = warp_global * rows_per_warp; base < N; base += nwarps * rows_per_warp) {
     const long long r0 = base + (long long)grp * RB;
     int h[RB][KB];
+    uint32_t ones[RB][KB], twos[RB][KB];
 #pragma unroll
     for (int r = 0; r < RB; r++)
 #pragma unroll
-      for (int k = 0; k < KB; k++) h[r][k] = 0;
+      for (int k = 0; k < KB; k++) { h[r][k] = 0; ones[r][k] = 0; twos[r][k] = 0; }
 
+#pragma unroll 2
     for (int c = sub; c < W4; c += G) {
       uint4 x[RB];
 #pragma unroll
@@ -96,12 +109,21 @@ __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, 
           if (HALF) v = valid[k * W4 + c];
 #pragma unroll
           for (int r = 0; r < RB; r++) {
-            h[r][k] += __popc((x[r].x ^ a.x) & v.x) + __popc((x[r].y ^ a.y) & v.y) + __popc((x[r].z ^ a.z) & v.z) +
-                       __popc((x[r].w ^ a.w) & v.w);
+            const uint32_t m0 = (x[r].x ^ a.x) & v.x, m1w = (x[r].y ^ a.y) & v.y;
+            const uint32_t m2 = (x[r].z ^ a.z) & v.z, m3 = (x[r].w ^ a.w) & v.w;
+            uint32_t c1, c2, c4;
+            csa(c1, ones[r][k], ones[r][k], m0, m1w);
+            csa(c2, ones[r][k], ones[r][k], m2, m3);
+            csa(c4, twos[r][k], twos[r][k], c1, c2);
+            h[r][k] += __popc(c4);
           }
         }
       }
     }
+#pragma unroll
+    for (int r = 0; r < RB; r++)
+#pragma unroll
+      for (int k = 0; k < KB; k++) h[r][k] = 4 * h[r][k] + 2 * __popc(twos[r][k]) + __popc(ones[r][k]);
     // reduce over the G lanes of the group
     for (int off = G >> 1; off > 0; off >>= 1) {
 #pragma unroll
@@ -235,11 +257,14 @@ struct SweepArgs {
   unsigned* maxdiff_bits;
 };
 
-__device__ __forceinline__ void sweep_row(const SweepArgs& a, long long i, int lane, float& wmax) {
+// One group of GS lanes (GS = power of two >= K) updates one row; lane `sub` of the group owns class `sub`.
+template <int GS>
+__device__ __forceinline__ void sweep_row(const SweepArgs& a, long long i, bool valid, int sub, float& wmax) {
   const int K = a.K;
-  const int k = lane < K ? lane : K - 1;
+  const int k = sub < K ? sub : K - 1;
+  if (!valid) i = 0;
   float ctx = 0.0f;
-  if (a.rowptr != nullptr && a.beta != 0.0f) {
+  if (valid && a.rowptr != nullptr && a.beta != 0.0f) {
     const int n0 = a.rowptr[i], n1 = a.rowptr[i + 1];
     for (int n = n0; n < n1; n++) {
       const int j = a.col[n];
@@ -255,11 +280,11 @@ __device__ __forceinline__ void sweep_row(const SweepArgs& a, long long i, int l
     // reference arithmetic: nem_mod.c:677-679, nem_alg.c:2367, :2665-2698
     const float lf32 = (float)lf;
     const double f = (lf == -INFINITY) ? 0.0 : exp((double)lf32);
-    double num = (double)a.pk[k] * f * 1.0;
+    double num = (double)a.pk[k] * f;
     num = num * exp((double)a.beta * (double)ctx);
-    if (lane >= K) num = 0.0;
+    if (sub >= K) num = 0.0;
     double cum = 0.0;
-    for (int kk = 0; kk < K; kk++) cum = cum + __shfl_sync(0xffffffffu, num, kk);  // sequential, like the reference
+    for (int kk = 0; kk < K; kk++) cum = cum + __shfl_sync(0xffffffffu, num, kk, GS);  // sequential, like the reference
     if (cum > 0) {
       if (cum > kEps) { const double invZ = 1 / cum; cnew = (float)(invZ * num); }
       else { const double invZ = 1 / (cum / kEps); cnew = (float)(invZ * (num / kEps)); }
@@ -268,39 +293,45 @@ __device__ __forceinline__ void sweep_row(const SweepArgs& a, long long i, int l
     }
   } else {
     double av = a.logpk64[k] + lf + (double)a.beta * (double)ctx;
-    if (lane >= K) av = -INFINITY;
+    if (sub >= K) av = -INFINITY;
     double m = av;
-    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if (m == -INFINITY) {
-      cnew = (float)(1.0 / K);
-    } else {
-      const double e = (lane < K) ? exp(av - m) : 0.0;
-      double s = 0.0;
-      for (int kk = 0; kk < K; kk++) s = s + __shfl_sync(0xffffffffu, e, kk);
-      cnew = (float)(e / s);
-    }
+#pragma unroll
+    for (int off = GS >> 1; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off, GS));
+    const double e = (sub < K && m > -INFINITY) ? exp(av - m) : 0.0;
+    double sum = 0.0;
+    for (int kk = 0; kk < K; kk++) sum = sum + __shfl_sync(0xffffffffu, e, kk, GS);
+    cnew = (m == -INFINITY) ? (float)(1.0 / K) : (float)(e / sum);
   }
-  if (lane < K) {
-    const float old = a.T_old[(size_t)i * K + lane];
-    __stcg(a.T_new + (size_t)i * K + lane, cnew);
+  if (valid && sub < K) {
+    const float old = a.T_old[(size_t)i * K + sub];
+    __stcg(a.T_new + (size_t)i * K + sub, cnew);
     float dif = cnew - old;
     if (dif < 0) dif = -dif;
     wmax = fmaxf(wmax, dif);
   }
 }
 
-template <bool COOP>
+template <bool COOP, int GS>
 __global__ void __launch_bounds__(256) k_sweep(SweepArgs a) {
   const int lane = threadIdx.x & 31;
+  const int sub = lane & (GS - 1), grp = lane / GS;
+  constexpr int RPW = 32 / GS;  // rows per warp
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   float wmax = 0.0f;
   if (a.level_ptr == nullptr) {
-    for (long long i = warp_global; i < a.N; i += nwarps) sweep_row(a, i, lane, wmax);
+    for (long long i0 = warp_global * RPW; i0 < a.N; i0 += nwarps * RPW) {
+      const long long i = i0 + grp;
+      sweep_row<GS>(a, i, i < a.N, sub, wmax);
+    }
   } else {
     for (int L = 0; L < a.n_levels; L++) {
       const int b = a.level_ptr[L], e = a.level_ptr[L + 1];
-      for (long long idx = b + warp_global; idx < e; idx += nwarps) sweep_row(a, a.level_rows[idx], lane, wmax);
+      for (long long idx0 = b + warp_global * RPW; idx0 < e; idx0 += nwarps * RPW) {
+        const long long idx = idx0 + grp;
+        const bool valid = idx < e;
+        sweep_row<GS>(a, valid ? a.level_rows[idx] : 0, valid, sub, wmax);
+      }
       if (COOP && L + 1 < a.n_levels) {
         __threadfence();
         cg::this_grid().sync();
@@ -372,31 +403,81 @@ __global__ void k_offsets(const int* __restrict__ hist, int K, int* __restrict__
   }
 }
 
+// rows -> perm, grouped by class.  One atomic per (warp, class present in the warp) instead of one per row: the 3-20
+// cursors are shared by all rows, and per-row atomics on them serialise (measured 70 us for 200 000 rows).
 __global__ void __launch_bounds__(256)
 k_scatter(const int* __restrict__ cls, long long N, int* __restrict__ cursor, int* __restrict__ perm) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) {
-    const int pos = atomicAdd(&cursor[cls[i]], 1);
-    perm[pos] = (int)i;
-  }
-}
-
-// carry-save adder on 32 bit-columns at once
-__device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
-  const uint32_t u = a ^ b;
-  hi = (a & b) | (u & c);
-  lo = u ^ c;
+  const int lane = threadIdx.x & 31;
+  const bool valid = i < N;
+  const int key = valid ? cls[i] : -1;
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  const int leader = __ffs(peers) - 1;
+  const int rank = __popc(peers & ((1u << lane) - 1u));
+  int base = 0;
+  if (valid && lane == leader) base = atomicAdd(&cursor[key], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (valid) perm[base + rank] = (int)i;
 }
 
 constexpr int kSeg = 2048;     // rows per one-hot segment; counters have 12 planes (max 4095)
 constexpr int kPlanes = 12;
-constexpr int kMsTpb = 128;    // threads (= matrix words per row) per CTA
+constexpr int kMsTpb = 128;    // threads per CTA; each owns one 64-bit matrix word (64 genomes) of every row
+constexpr int kBatch = 16;     // rows per Harley-Seal block
 
-// One thread owns one 32-bit word column (32 genomes).  blockIdx.y walks segments of at most kSeg rows of one class.
+__device__ __forceinline__ uint2 ld_stream64(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
+// 16 words -> the weight-16 carry, rippled into planes 4..11 (Harley-Seal)
+__device__ __forceinline__ void hs16(uint32_t (&p)[kPlanes], const uint32_t (&x)[kBatch]) {
+  uint32_t t2a, t2b, t2c, t2d, t2e, t2f, t2g, t2h, t4a, t4b, t4c, t4d, t8a, t8b, c16;
+  csa(t2a, p[0], p[0], x[0], x[1]);
+  csa(t2b, p[0], p[0], x[2], x[3]);
+  csa(t2c, p[0], p[0], x[4], x[5]);
+  csa(t2d, p[0], p[0], x[6], x[7]);
+  csa(t2e, p[0], p[0], x[8], x[9]);
+  csa(t2f, p[0], p[0], x[10], x[11]);
+  csa(t2g, p[0], p[0], x[12], x[13]);
+  csa(t2h, p[0], p[0], x[14], x[15]);
+  csa(t4a, p[1], p[1], t2a, t2b);
+  csa(t4b, p[1], p[1], t2c, t2d);
+  csa(t4c, p[1], p[1], t2e, t2f);
+  csa(t4d, p[1], p[1], t2g, t2h);
+  csa(t8a, p[2], p[2], t4a, t4b);
+  csa(t8b, p[2], p[2], t4c, t4d);
+  csa(c16, p[3], p[3], t8a, t8b);
+  uint32_t carry = c16;
+#pragma unroll
+  for (int j = 4; j < kPlanes; j++) {
+    const uint32_t nc = p[j] & carry;
+    p[j] ^= carry;
+    carry = nc;
+  }
+}
+
+__device__ __forceinline__ void load_batch(uint32_t (&lo)[kBatch], uint32_t (&hi)[kBatch], const uint2* __restrict__ colp,
+                                           const int* s_rows, int r, int W2) {
+#pragma unroll
+  for (int q = 0; q < kBatch; q += 4) {
+    const int4 rows = *reinterpret_cast<const int4*>(s_rows + r + q);
+    const uint2 v0 = ld_stream64(colp + (size_t)rows.x * W2);
+    const uint2 v1 = ld_stream64(colp + (size_t)rows.y * W2);
+    const uint2 v2 = ld_stream64(colp + (size_t)rows.z * W2);
+    const uint2 v3 = ld_stream64(colp + (size_t)rows.w * W2);
+    lo[q] = v0.x; hi[q] = v0.y; lo[q + 1] = v1.x; hi[q + 1] = v1.y;
+    lo[q + 2] = v2.x; hi[q + 2] = v2.y; lo[q + 3] = v3.x; hi[q + 3] = v3.y;
+  }
+}
+
+// One thread owns one 64-bit word column (64 genomes).  blockIdx.y walks segments of at most kSeg rows of one class.
+// Rows are streamed in batches of 16 with the next batch's loads issued before the current batch is summed.
 __global__ void __launch_bounds__(kMsTpb)
-k_mstep_onehot(const uint32_t* __restrict__ bits, int Ws, int K, const int* __restrict__ offsets,
+k_mstep_onehot(const uint2* __restrict__ bits2, int W2, int K, const int* __restrict__ offsets,
                const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad) {
-  __shared__ int s_rows[kSeg];
+  __shared__ __align__(16) int s_rows[kSeg];
   __shared__ int s_cnt[kMsTpb * 33];
   // map blockIdx.y -> (class, segment start)
   int seg = blockIdx.y, k = 0, start = 0, len = 0;
@@ -416,66 +497,54 @@ k_mstep_onehot(const uint32_t* __restrict__ bits, int Ws, int K, const int* __re
   for (int t = threadIdx.x; t < len; t += blockDim.x) s_rows[t] = perm[start + t];
   __syncthreads();
   const int word = blockIdx.x * kMsTpb + threadIdx.x;
-  const bool active = word < Ws;
-  uint32_t p[kPlanes];
+  const bool active = word < W2;
+  uint32_t plo[kPlanes], phi[kPlanes];
 #pragma unroll
-  for (int j = 0; j < kPlanes; j++) p[j] = 0;
+  for (int j = 0; j < kPlanes; j++) { plo[j] = 0; phi[j] = 0; }
   if (active) {
-    const uint32_t* colp = bits + word;
-    int r = 0;
-    for (; r + 16 <= len; r += 16) {
-      uint32_t x[16];
-#pragma unroll
-      for (int q = 0; q < 16; q++) x[q] = ld_stream32(colp + (size_t)s_rows[r + q] * Ws);
-      // Harley-Seal: 16 words -> one carry of weight 16
-      uint32_t t2a, t2b, t2c, t2d, t2e, t2f, t2g, t2h, t4a, t4b, t4c, t4d, t8a, t8b, c16;
-      csa(t2a, p[0], p[0], x[0], x[1]);
-      csa(t2b, p[0], p[0], x[2], x[3]);
-      csa(t2c, p[0], p[0], x[4], x[5]);
-      csa(t2d, p[0], p[0], x[6], x[7]);
-      csa(t2e, p[0], p[0], x[8], x[9]);
-      csa(t2f, p[0], p[0], x[10], x[11]);
-      csa(t2g, p[0], p[0], x[12], x[13]);
-      csa(t2h, p[0], p[0], x[14], x[15]);
-      csa(t4a, p[1], p[1], t2a, t2b);
-      csa(t4b, p[1], p[1], t2c, t2d);
-      csa(t4c, p[1], p[1], t2e, t2f);
-      csa(t4d, p[1], p[1], t2g, t2h);
-      csa(t8a, p[2], p[2], t4a, t4b);
-      csa(t8b, p[2], p[2], t4c, t4d);
-      csa(c16, p[3], p[3], t8a, t8b);
-      // ripple the weight-16 carry into planes 4..11
-      uint32_t carry = c16;
-#pragma unroll
-      for (int j = 4; j < kPlanes; j++) {
-        const uint32_t nc = p[j] & carry;
-        p[j] ^= carry;
-        carry = nc;
+    const uint2* colp = bits2 + word;
+    const int nb = len / kBatch;
+    uint32_t alo[kBatch], ahi[kBatch], blo[kBatch], bhi[kBatch];
+    if (nb > 0) load_batch(alo, ahi, colp, s_rows, 0, W2);
+    for (int b = 0; b < nb; b += 2) {
+      if (b + 1 < nb) load_batch(blo, bhi, colp, s_rows, (b + 1) * kBatch, W2);
+      hs16(plo, alo);
+      hs16(phi, ahi);
+      if (b + 1 < nb) {
+        if (b + 2 < nb) load_batch(alo, ahi, colp, s_rows, (b + 2) * kBatch, W2);
+        hs16(plo, blo);
+        hs16(phi, bhi);
       }
     }
-    for (; r < len; r++) {  // tail rows: ripple through all planes
-      uint32_t carry = ld_stream32(colp + (size_t)s_rows[r] * Ws);
+    for (int r = nb * kBatch; r < len; r++) {  // tail rows: ripple through all planes
+      const uint2 v = ld_stream64(colp + (size_t)s_rows[r] * W2);
+      uint32_t c0 = v.x, c1 = v.y;
 #pragma unroll
       for (int j = 0; j < kPlanes; j++) {
-        const uint32_t nc = p[j] & carry;
-        p[j] ^= carry;
-        carry = nc;
+        const uint32_t n0 = plo[j] & c0, n1 = phi[j] & c1;
+        plo[j] ^= c0; phi[j] ^= c1;
+        c0 = n0; c1 = n1;
       }
     }
   }
-  // expand the planes into 32 integer counts, transpose through shared memory, add to global with coalesced REDs
-#pragma unroll 4
-  for (int b = 0; b < 32; b++) {
-    int c = 0;
+  // expand the planes into integer counts, transpose through shared memory, add to global with coalesced REDs
 #pragma unroll
-    for (int j = 0; j < kPlanes; j++) c += (int)((p[j] >> b) & 1u) << j;
-    s_cnt[threadIdx.x * 33 + b] = c;
-  }
-  __syncthreads();
-  const int col0 = blockIdx.x * kMsTpb * 32;
-  for (int t = threadIdx.x; t < kMsTpb * 32; t += blockDim.x) {
-    const int c = s_cnt[(t >> 5) * 33 + (t & 31)];
-    if (c != 0 && col0 + t < Dpad) atomicAdd(&cnt[(size_t)k * Dpad + col0 + t], c);
+  for (int half = 0; half < 2; half++) {
+    if (half) __syncthreads();
+#pragma unroll 4
+    for (int b = 0; b < 32; b++) {
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < kPlanes; j++) c += (int)(((half ? phi[j] : plo[j]) >> b) & 1u) << j;
+      s_cnt[threadIdx.x * 33 + b] = c;
+    }
+    __syncthreads();
+    // thread t of the CTA owns columns 64 * (block word) ..: word w = blockIdx.x*kMsTpb + (t >> 5), bit (t & 31)
+    for (int t = threadIdx.x; t < kMsTpb * 32; t += blockDim.x) {
+      const int c = s_cnt[(t >> 5) * 33 + (t & 31)];
+      const int col = (blockIdx.x * kMsTpb + (t >> 5)) * 64 + half * 32 + (t & 31);
+      if (c != 0 && col < Dpad) atomicAdd(&cnt[(size_t)k * Dpad + col], c);
+    }
   }
 }
 
@@ -509,27 +578,32 @@ k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int
   }
 }
 
-// One CTA per class: centres, inertia, dispersion, proportions and the derived E-step tables.
-__global__ void __launch_bounds__(1024)
+// Parameters from the column statistics.  grid = (column chunks, K); every CTA handles kFinCols columns of one class:
+// centres (weighted median of a 0/1 column, nem_mod.c:1417-1474), inertia (nem_mod.c:1641-1699), centre bit planes and,
+// for "skd", the per-column dispersion and log-odds.  The last CTA of a class to finish (ticket counter) adds the chunk
+// partials in chunk order (deterministic) and derives the class scalars: proportion (nem_mod.c:455-459), the shared
+// dispersion of "sk_" (nem_mod.c:1053-1068, MISSING_IGNORE) and the E-step constants L_k, B_k.
+constexpr int kFinCols = 1024;
+
+__global__ void __launch_bounds__(256)
 k_mstep_finalize(Params P, const int* __restrict__ cnt, const double* __restrict__ fsum, const int* __restrict__ nk_cnt,
-                 const double* __restrict__ nk_fz, long long N_total) {
-  __shared__ double s_red[32];
-  __shared__ double s_bcast;
-  __shared__ int s_half;
-  const int k = blockIdx.x, K = P.K, D = P.D, Dpad = P.Dpad, Ws = P.Ws;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+                 const double* __restrict__ nk_fz, long long N_total, double* __restrict__ partial /*[K][nchunk][2]*/,
+                 int* __restrict__ tickets /*[K]*/) {
+  __shared__ double s_red[8][2];
+  __shared__ int s_last;
+  const int k = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const int D = P.D, Dpad = P.Dpad, Ws = P.Ws;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const double nk = (double)nk_cnt[k] + nk_fz[k];
-  if (threadIdx.x == 0) s_half = 0;
-  __syncthreads();
   if (!(nk > kEps)) {  // empty class: nem_mod.c:1399-1403 -> STS_W_EMPTYCLASS, parameters kept
-    if (threadIdx.x == 0) atomicMax(P.status, 1);
+    if (threadIdx.x == 0 && chunk == 0) atomicMax(P.status, 1);
     return;
   }
-  // pass 1: centres (weighted median of a 0/1 column, nem_mod.c:1417-1474) and inertia (nem_mod.c:1641-1699)
-  double iner_sum = 0.0;
+  double iner_sum = 0.0, b_sum = 0.0;
   int any_half = 0;
-  for (int d0 = 0; d0 < Dpad; d0 += blockDim.x) {
-    const int d = d0 + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < kFinCols / 256; j++) {
+    const int d = chunk * kFinCols + j * 256 + threadIdx.x;
     float m = 0.0f;
     double iner = 0.0;
     if (d < D) {
@@ -542,7 +616,13 @@ k_mstep_finalize(Params P, const int* __restrict__ cnt, const double* __restrict
       if (P.free_disp) {
         const float e = (float)(iner / nk);                // nem_mod.c:1162-1163
         P.eps[(size_t)k * D + d] = e;
+        double Lv;
+        if (e > kEps) { Lv = log((double)((1.0f - e) / e)); b_sum += log((double)(1.0f - e)); }  // nem_mod.c:660
+        else Lv = INFINITY;
+        P.L[(size_t)k * Dpad + d] = Lv;
       }
+    } else if (P.free_disp && d < Dpad) {
+      P.L[(size_t)k * Dpad + d] = 0.0;
     }
     iner_sum += iner;
     const unsigned b1 = __ballot_sync(0xffffffffu, m == 1.0f);
@@ -551,63 +631,56 @@ k_mstep_finalize(Params P, const int* __restrict__ cnt, const double* __restrict
       P.m1[(size_t)k * Ws + (d >> 5)] = b1;
       P.valid[(size_t)k * Ws + (d >> 5)] = bv;
     }
-    if (!P.free_disp) {
-      // stash per-column inertia is not needed for sk_: only the sum
-    }
   }
-  if (any_half) atomicOr(&s_half, 1);
-  // block reduction of iner_sum (fixed order: deterministic)
-  for (int off = 16; off > 0; off >>= 1) iner_sum += __shfl_xor_sync(0xffffffffu, iner_sum, off);
-  if (lane == 0) s_red[wid] = iner_sum;
+  if (__any_sync(0xffffffffu, any_half) && lane == 0) atomicOr(P.has_half, 1);
+  for (int off = 16; off > 0; off >>= 1) {
+    iner_sum += __shfl_xor_sync(0xffffffffu, iner_sum, off);
+    b_sum += __shfl_xor_sync(0xffffffffu, b_sum, off);
+  }
+  if (lane == 0) { s_red[wid][0] = iner_sum; s_red[wid][1] = b_sum; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int q = 0; q < nw; q++) t += s_red[q];
-    s_bcast = t;
-    const float pkf = (float)(nk / (double)N_total);       // nem_mod.c:455-459
-    P.pk[k] = pkf;
-    const double lp = ((double)pkf > kEps) ? log((double)pkf) : -INFINITY;  // nem_alg.c:2350-2356
-    P.logpk32[k] = (float)lp;
-    P.logpk64[k] = lp;
-    if (s_half) atomicOr(P.has_half, 1);
+    double t0 = 0.0, t1 = 0.0;
+    for (int q = 0; q < 8; q++) { t0 += s_red[q][0]; t1 += s_red[q][1]; }
+    partial[((size_t)k * nchunk + chunk) * 2 + 0] = t0;
+    partial[((size_t)k * nchunk + chunk) * 2 + 1] = t1;
+    __threadfence();
+    s_last = (atomicAdd(&tickets[k], 1) == nchunk - 1);
   }
   __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  tickets[k] = 0;  // ready for the next M-step
+  double tot_iner = 0.0, tot_b = 0.0;
+  for (int c = 0; c < nchunk; c++) {
+    tot_iner += __ldcg(&partial[((size_t)k * nchunk + c) * 2 + 0]);
+    tot_b += __ldcg(&partial[((size_t)k * nchunk + c) * 2 + 1]);
+  }
+  const float pkf = (float)(nk / (double)N_total);       // nem_mod.c:455-459
+  P.pk[k] = pkf;
+  const double lp = ((double)pkf > kEps) ? log((double)pkf) : -INFINITY;  // nem_alg.c:2350-2356
+  P.logpk32[k] = (float)lp;
+  P.logpk64[k] = lp;
   if (!P.free_disp) {
-    // one dispersion per class: sum_d Iner / sum_d N_kd (nem_mod.c:1053-1068, MISSING_IGNORE)
-    const float e = (float)(s_bcast / ((double)D * nk));
-    for (int d = threadIdx.x; d < D; d += blockDim.x) P.eps[(size_t)k * D + d] = e;
-    if (threadIdx.x == 0) {
-      if (e > kEps) {
-        P.L[k] = log((double)((1.0f - e) / e));            // float ratio, double log (nem_mod.c:660)
-        P.B[k] = (double)D * log((double)(1.0f - e));
-      } else {
-        P.L[k] = INFINITY;
-        P.B[k] = 0.0;
-      }
+    const float e = (float)(tot_iner / ((double)D * nk));
+    P.eps_k[k] = e;                                       // expanded to eps[k][:] on demand (k_expand_eps)
+    if (e > kEps) {
+      P.L[k] = log((double)((1.0f - e) / e));            // float ratio, double log (nem_mod.c:660)
+      P.B[k] = (double)D * log((double)(1.0f - e));
+    } else {
+      P.L[k] = INFINITY;
+      P.B[k] = 0.0;
     }
   } else {
-    __syncthreads();
-    double bsum = 0.0;
-    for (int d0 = 0; d0 < Dpad; d0 += blockDim.x) {
-      const int d = d0 + threadIdx.x;
-      double Lv = 0.0;
-      if (d < D) {
-        const float e = P.eps[(size_t)k * D + d];
-        if (e > kEps) { Lv = log((double)((1.0f - e) / e)); bsum += log((double)(1.0f - e)); }
-        else Lv = INFINITY;
-      }
-      if (d < Dpad) P.L[(size_t)k * Dpad + d] = Lv;
-    }
-    for (int off = 16; off > 0; off >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
-    __syncthreads();
-    if (lane == 0) s_red[wid] = bsum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int q = 0; q < nw; q++) t += s_red[q];
-      P.B[k] = t;
-    }
+    P.B[k] = tot_b;
   }
+}
+
+// "sk_": the dispersion is one scalar per class; the K x D table PPanGGOLiN reads from .mf is materialised on demand
+__global__ void k_expand_eps(Params P) {
+  const int k = blockIdx.y;
+  const float e = P.eps_k[k];
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < P.D; d += gridDim.x * blockDim.x) P.eps[(size_t)k * P.D + d] = e;
 }
 
 // per-word totals of L_kd for the complement trick of k_density_skd
@@ -655,6 +728,7 @@ __global__ void k_init_params(Params P, float base_prop, const float* __restrict
     P.logpk32[k] = (float)lp;
     P.logpk64[k] = lp;
     if (!P.free_disp) P.L[k] = Lv;
+    P.eps_k[k] = e;
     P.B[k] = (double)D * l1;
     if (k == 0) { *P.has_half = 0; *P.status = 0; }
   }

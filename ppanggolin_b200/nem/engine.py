@@ -57,6 +57,7 @@ SIGNATURES = {
     "nemb200_mstep_finalize": (ctypes.c_int, [_vp, _vp]),
     "nemb200_density": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "nemb200_sweep": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp]),
+    "nemb200_read_flags": (ctypes.c_int, [_vp, ctypes.POINTER(_f32), ctypes.POINTER(_i32), _vp]),
     "nemb200_criteria": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f32, ctypes.POINTER(ctypes.c_double * 5), _vp]),
     "nemb200_get_params": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.POINTER(_i32), _vp]),
     "nemb200_labels": (ctypes.c_int, [_vp, _i64, _i32, _vp, ctypes.POINTER(ctypes.c_double), _vp]),
@@ -329,7 +330,13 @@ class Plan:
         _check(lib().nemb200_sweep(self._h, N, _ptr(logf), _ptr(T_old), _ptr(T_new), _ptr(inp.rowptr) if g else 0,
                                    _ptr(inp.col) if g else 0, _ptr(inp.w) if g else 0, _ptr(inp.sched_ptr) if g else 0,
                                    _ptr(inp.sched_rows) if g else 0, inp.n_levels if g else 1,
-                                   float(np.float32(beta_now)), _ptr(maxdiff), _stream()), "sweep")
+                                   float(np.float32(beta_now)), _ptr(maxdiff) if maxdiff is not None else 0, _stream()), "sweep")
+
+    def read_flags(self):
+        """(max |T_new - T_old| of the last sweep that used the plan's own convergence word, status): one 8-byte read."""
+        md, st = _f32(0.0), _i32(0)
+        _check(lib().nemb200_read_flags(self._h, ctypes.byref(md), ctypes.byref(st), _stream()), "read_flags")
+        return float(md.value), int(st.value)
 
     def criteria(self, N, logf, T, inp: Optional[DeviceInput], beta: float):
         g = inp is not None and inp.rowptr is not None

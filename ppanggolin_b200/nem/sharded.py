@@ -47,7 +47,6 @@ class CudaBackend:
         dev = bits_local.device
         self.logf_full = torch.empty((N_total, K), dtype=torch.float64, device=dev)
         self.T = [torch.zeros((N_total, K), dtype=torch.float32, device=dev) for _ in range(2)]
-        self.maxdiff = torch.zeros(4, dtype=torch.int32, device=dev)
         self.launches = 0
 
     def init_params(self):
@@ -66,13 +65,11 @@ class CudaBackend:
         self.plan.density(self.bits, logf_local); self.launches += 1
 
     def sweep(self, T_old, T_new, beta_now):
-        self.maxdiff.zero_()
-        self.plan.sweep(self.N, self.logf_full, T_old, T_new, self.graph, beta_now, self.maxdiff); self.launches += 1
+        self.plan.sweep(self.N, self.logf_full, T_old, T_new, self.graph, beta_now, None); self.launches += 1
 
     def read_flags(self):
         """(max |T_new - T_old|, status) -- the only per-iteration device->host read."""
-        md = float(self.maxdiff[:1].view(self.torch.float32).item())
-        return md, self.plan.get_params_status()
+        return self.plan.read_flags()
 
     def criteria(self, T, beta):
         return self.plan.criteria(self.N, self.logf_full, T, self.graph, beta)
