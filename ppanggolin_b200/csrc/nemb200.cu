@@ -61,11 +61,13 @@ struct nemb200_plan {
   double* fsum = nullptr;   // [K][Dpad]
   int* nk_cnt = nullptr;    // [K]
   double* nk_fz = nullptr;  // [K]
-  int* hist = nullptr;      // [K+1]
-  int* offsets = nullptr;   // [K+2]
-  int* cursor = nullptr;    // [K+1]
-  int* cls = nullptr;       // [N_local]
-  int* perm = nullptr;      // [N_local]
+  int* cnt_local = nullptr; // [K][Dpad] this rank's running one-hot column counts (kept across iterations)
+  int* hist = nullptr;      // [2K+1]  add buckets, remove buckets, fuzzy bucket
+  int* offsets = nullptr;   // [2K+2]
+  int* cursor = nullptr;    // [2K+1]
+  int* prev = nullptr;      // [N_local] key of every row at the previous M-step (kNone before the first)
+  int2* ent = nullptr;      // [N_local] bucket entries of the current M-step
+  int* perm = nullptr;      // [2 * N_local] rows grouped by bucket
   double* Lword = nullptr;  // [K][Ws] (skd)
   double* fin_partial = nullptr;  // [K][nchunk][2]
   int* fin_tickets = nullptr;     // [K]
@@ -117,8 +119,9 @@ extern "C" int nemb200_plan_create(nemb200_plan** out, int64_t N_local, int64_t 
   A(P.has_half, 1) A(pl->flags2, 2)
   P.status = (int*)(pl->flags2 + 1);
   A(pl->cnt, (size_t)K * pl->Dpad) A(pl->fsum, (size_t)K * pl->Dpad)
-  A(pl->nk_cnt, K) A(pl->nk_fz, K) A(pl->hist, K + 1) A(pl->offsets, K + 2) A(pl->cursor, K + 1)
-  A(pl->cls, N_local) A(pl->perm, N_local)
+  A(pl->cnt_local, (size_t)K * pl->Dpad)
+  A(pl->nk_cnt, K) A(pl->nk_fz, K) A(pl->hist, 2 * K + 1) A(pl->offsets, 2 * K + 2) A(pl->cursor, 2 * K + 1)
+  A(pl->prev, N_local) A(pl->ent, N_local) A(pl->perm, 2 * N_local)
   A(pl->Lword, (size_t)K * pl->Ws) A(pl->eps_init, K) A(P.eps_k, K)
   pl->fin_chunks = (pl->Dpad + kFinCols - 1) / kFinCols;
   A(pl->fin_partial, (size_t)K * pl->fin_chunks * 2) A(pl->fin_tickets, K)
@@ -153,6 +156,9 @@ extern "C" int nemb200_init_params(nemb200_plan* pl, void* stream_) {
   CK(cudaStreamSynchronize(st));  // e is a stack vector
   k_init_params<<<K, 256, 0, st>>>(pl->P, base, pl->eps_init);
   CK(cudaGetLastError());
+  // a new run: no row is counted yet (kNone == -2 is the byte pattern 0xFE repeated)
+  CK(cudaMemsetAsync(pl->prev, 0xFE, (size_t)std::max<long long>(pl->N_local, 1) * sizeof(int), st));
+  CK(cudaMemsetAsync(pl->cnt_local, 0, (size_t)K * pl->Dpad * sizeof(int), st));
   if (pl->free_disp) {
     const int n = K * pl->Ws;
     k_lword<<<(n + 255) / 256, 256, 0, st>>>(pl->P.L, K, pl->Ws, pl->Dpad, pl->Lword);
@@ -165,7 +171,7 @@ template <int KB>
 static int launch_classify(nemb200_plan* pl, const float* T, cudaStream_t st) {
   const long long N = pl->N_local;
   if (N > 0) {
-    k_classify<KB><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(T, N, pl->K, pl->cls, pl->hist, pl->nk_fz);
+    k_classify<KB><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(T, N, pl->K, pl->prev, pl->ent, pl->hist, pl->nk_cnt, pl->nk_fz);
     CK(cudaGetLastError());
   }
   return 0;
@@ -190,25 +196,35 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
   cudaStream_t st = (cudaStream_t)stream_;
   const int K = pl->K;
   const long long N = pl->N_local;
-  CK(cudaMemsetAsync(pl->cnt, 0, (size_t)K * pl->Dpad * sizeof(int), st));
   CK(cudaMemsetAsync(pl->fsum, 0, (size_t)K * pl->Dpad * sizeof(double), st));
-  CK(cudaMemsetAsync(pl->hist, 0, (K + 1) * sizeof(int), st));
+  CK(cudaMemsetAsync(pl->hist, 0, (2 * K + 1) * sizeof(int), st));
+  CK(cudaMemsetAsync(pl->nk_cnt, 0, K * sizeof(int), st));
   CK(cudaMemsetAsync(pl->nk_fz, 0, K * sizeof(double), st));
   int rc = DISPATCH_KB(K, launch_classify, pl, T, st);
   if (rc) return rc;
-  k_offsets<<<1, 32, 0, st>>>(pl->hist, K, pl->offsets, pl->cursor, pl->nk_cnt);
+  k_offsets<<<1, 32, 0, st>>>(pl->hist, 2 * K + 1, pl->offsets, pl->cursor);
   CK(cudaGetLastError());
   if (N > 0) {
-    k_scatter<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pl->cls, N, pl->cursor, pl->perm);
+    k_scatter<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pl->ent, N, pl->cursor, pl->perm);
     CK(cudaGetLastError());
-    const int max_segs = (int)((N + kSeg - 1) / kSeg) + K;  // upper bound on sum_k ceil(n_k / kSeg)
+    // column tiles of equal width; row slices sized so that the whole grid is one resident wave
     const int W2 = pl->Ws / 2;
-    dim3 grid((W2 + kMsTpb - 1) / kMsTpb, max_segs);
-    k_mstep_onehot<<<grid, kMsTpb, 0, st>>>((const uint2*)bits, W2, K, pl->offsets, pl->perm, pl->cnt, pl->Dpad);
+    const int ntiles = (W2 + kMsTpb - 1) / kMsTpb;
+    const int tile_w = (W2 + ntiles - 1) / ntiles;
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mstep_onehot, kMsTpb, 0));
+    const long long slots = (long long)num_sms() * std::max(per_sm, 1);
+    long long slices = std::max<long long>(slots / ntiles, 1);
+    const long long need = (2 * N + kMaxRun - 1) / kMaxRun;      // keeps a slice within a few counter runs
+    if (slices < need) slices = std::min<long long>(need, 65535);
+    dim3 grid(ntiles, (unsigned)slices);
+    k_mstep_onehot<<<grid, kMsTpb, 0, st>>>((const uint2*)bits, W2, tile_w, K, pl->offsets, pl->perm, pl->cnt_local, pl->Dpad);
     CK(cudaGetLastError());
     rc = DISPATCH_KB(K, launch_fuzzy, pl, bits, T, st);
     if (rc) return rc;
   }
+  // the exposed statistics (all-reduced in place by a multi-GPU driver) start from this rank's running counts
+  CK(cudaMemcpyAsync(pl->cnt, pl->cnt_local, (size_t)K * pl->Dpad * sizeof(int), cudaMemcpyDeviceToDevice, st));
   return NEMB200_OK;
 }
 
@@ -244,25 +260,43 @@ static int group_lanes(int units) {  // lanes cooperating on one row: smallest p
   return g;
 }
 
-template <int KB>
+template <int KB, int KX>
 static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
-  constexpr int RB = KB <= 4 ? 4 : (KB <= 8 ? 2 : 1);  // rows per lane group: bounded by registers (3 * RB * KB)
+  constexpr int RB = KB <= 4 ? 4 : (KB <= 8 ? 2 : 1);  // rows per lane group: bounded by registers (2 * RB * KB + 4 * RB)
   const int W4 = pl->Ws / 4;
   const int G = group_lanes(W4);
   const size_t smem = (size_t)2 * pl->K * W4 * sizeof(uint4);
-  const int in_smem = smem <= 96 * 1024;
-  auto kern = k_density_sk<KB, RB>;
+  const int in_smem = smem <= 100 * 1024;
+  auto kern = k_density_sk<KB, KX, RB>;
   if (in_smem && smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long rows_per_block = (long long)(256 / 32) * (32 / G) * RB;
+  const long long rows_per_block = (long long)(kDensTpb / 32) * (32 / G) * RB;
   long long blocks = (pl->N_local + rows_per_block - 1) / rows_per_block;
-  const long long cap = (long long)num_sms() * 8;
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDensTpb, in_smem ? smem : 0));
+  const long long cap = (long long)num_sms() * std::max(per_sm, 1) * 2;  // two waves of resident CTAs, grid-stride inside
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  kern<<<(unsigned)blocks, 256, in_smem ? smem : 0, st>>>((const uint4*)bits, pl->N_local, W4, pl->K, G,
+  kern<<<(unsigned)blocks, kDensTpb, in_smem ? smem : 0, st>>>((const uint4*)bits, pl->N_local, W4, pl->K, G,
                                                           (const uint4*)pl->P.m1, (const uint4*)pl->P.valid, pl->P.L,
                                                           pl->P.B, pl->P.has_half, logf, in_smem);
   CK(cudaGetLastError());
   return 0;
+}
+static int dispatch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
+  switch (pl->K) {  // exact-K kernels for the common small K (no per-class predicates), buckets above
+    case 1: case 2: return launch_density_sk<2, 0>(pl, bits, logf, st);
+    case 3: return launch_density_sk<3, 3>(pl, bits, logf, st);
+    case 4: return launch_density_sk<4, 4>(pl, bits, logf, st);
+    case 5: return launch_density_sk<5, 5>(pl, bits, logf, st);
+    case 6: return launch_density_sk<6, 6>(pl, bits, logf, st);
+    case 7: return launch_density_sk<7, 7>(pl, bits, logf, st);
+    case 8: return launch_density_sk<8, 8>(pl, bits, logf, st);
+    default: break;
+  }
+  if (pl->K <= 12) return launch_density_sk<12, 0>(pl, bits, logf, st);
+  if (pl->K <= 16) return launch_density_sk<16, 0>(pl, bits, logf, st);
+  if (pl->K <= 20) return launch_density_sk<20, 0>(pl, bits, logf, st);
+  return launch_density_sk<32, 0>(pl, bits, logf, st);
 }
 template <int KB>
 static int launch_density_skd(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
@@ -283,7 +317,7 @@ extern "C" int nemb200_density(nemb200_plan* pl, const uint32_t* bits, double* l
   if (pl->N_local == 0) return NEMB200_OK;
   cudaStream_t st = (cudaStream_t)stream_;
   if (pl->free_disp) return DISPATCH_KB(pl->K, launch_density_skd, pl, bits, logf, st);
-  return DISPATCH_KB(pl->K, launch_density_sk, pl, bits, logf, st);
+  return dispatch_density_sk(pl, bits, logf, st);
 }
 
 extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, const float* T_old, float* T_new,
@@ -314,7 +348,7 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
     if (per_sm < 1) return fail(NEMB200_ERR_CUDA, "sweep: kernel does not fit on an SM");
-    long long blocks = (long long)num_sms() * std::min(per_sm, 2);   // few CTAs: the grid barrier is the fixed cost
+    long long blocks = (long long)num_sms() * std::min(per_sm, 4);
     const long long want = (N + rows_per_block - 1) / rows_per_block;
     if (blocks > want) blocks = std::max<long long>(want, 1);
     void* args[] = {&a};

@@ -68,14 +68,17 @@ __device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint
   lo = u ^ c;
 }
 
-// POPC issues on the quarter-rate XU pipe (measured: 80 % XU utilisation with one POPC per word and class), so the
-// mismatch words are first compressed with carry-save adders on the ALU pipe: per 4 words and class 3 CSAs (6 LOP3) and
-// a single POPC of the weight-4 carry; `ones`/`twos` carry the remainder across the row.
-template <int KB, int RB, bool HALF>
-__device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, long long N, int W4, int K, int G,
-                                                const uint4* __restrict__ m1, const uint4* __restrict__ valid,
-                                                const double* __restrict__ L, const double* __restrict__ B,
-                                                double* __restrict__ logf) {
+// Pipe balance (measured with ncu on B200): one POPC per word and class saturates the quarter-rate XU pipe (80 % XU at
+// 53 % DRAM); a full carry-save tree moves the bottleneck to the ALU pipe instead.  Middle ground used here, per 4
+// mismatch words and class: 2 carry-save adders (4 LOP3, ALU) folding into a running `ones` word + 2 POPC of the
+// weight-2 carries (XU).  Hamming distance = 2 * sum popc(carries) + popc(ones).
+//
+// KX > 0: K is the compile-time constant KX (no per-class predicates); KX == 0: runtime K <= KB.
+template <int KB, int KX, int RB, bool HALF, typename PlanePtr>
+__device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, long long N, int W4, int Krt, int G,
+                                                PlanePtr m1, PlanePtr valid, const double* __restrict__ L,
+                                                const double* __restrict__ B, double* __restrict__ logf) {
+  const int K = KX > 0 ? KX : Krt;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
   const int grp = lane / G;
@@ -86,44 +89,46 @@ __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, 
 
   for (long long base = warp_global * rows_per_warp; base < N; base += nwarps * rows_per_warp) {
     const long long r0 = base + (long long)grp * RB;
-    int h[RB][KB];
-    uint32_t ones[RB][KB], twos[RB][KB];
+    const uint4* rowp[RB];   // running pointers (advanced by G per step): keeps the 64-bit row arithmetic out of the loop
+#pragma unroll
+    for (int r = 0; r < RB; r++) rowp[r] = bits + (r0 + r < N ? r0 + r : N - 1) * W4 + sub;  // clamp: tail rows re-read the last row
+    int h2[RB][KB];
+    uint32_t ones[RB][KB];
 #pragma unroll
     for (int r = 0; r < RB; r++)
 #pragma unroll
-      for (int k = 0; k < KB; k++) { h[r][k] = 0; ones[r][k] = 0; twos[r][k] = 0; }
+      for (int k = 0; k < KB; k++) { h2[r][k] = 0; ones[r][k] = 0; }
 
+    PlanePtr pm = m1 + sub, pv = valid + sub;
 #pragma unroll 2
     for (int c = sub; c < W4; c += G) {
       uint4 x[RB];
 #pragma unroll
-      for (int r = 0; r < RB; r++) {
-        x[r] = make_uint4(0, 0, 0, 0);
-        if (r0 + r < N) x[r] = ld_stream(bits + (r0 + r) * W4 + c);
-      }
+      for (int r = 0; r < RB; r++) { x[r] = ld_stream(rowp[r]); rowp[r] += G; }
 #pragma unroll
       for (int k = 0; k < KB; k++) {
-        if (k < K) {
-          const uint4 a = m1[k * W4 + c];
+        if (KX > 0 || k < K) {
+          const uint4 a = pm[k * W4];
           uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
-          if (HALF) v = valid[k * W4 + c];
+          if (HALF) v = pv[k * W4];
 #pragma unroll
           for (int r = 0; r < RB; r++) {
             const uint32_t m0 = (x[r].x ^ a.x) & v.x, m1w = (x[r].y ^ a.y) & v.y;
             const uint32_t m2 = (x[r].z ^ a.z) & v.z, m3 = (x[r].w ^ a.w) & v.w;
-            uint32_t c1, c2, c4;
+            uint32_t c1, c2;
             csa(c1, ones[r][k], ones[r][k], m0, m1w);
             csa(c2, ones[r][k], ones[r][k], m2, m3);
-            csa(c4, twos[r][k], twos[r][k], c1, c2);
-            h[r][k] += __popc(c4);
+            h2[r][k] += __popc(c1) + __popc(c2);
           }
         }
       }
+      pm += G; pv += G;
     }
+    int h[RB][KB];
 #pragma unroll
     for (int r = 0; r < RB; r++)
 #pragma unroll
-      for (int k = 0; k < KB; k++) h[r][k] = 4 * h[r][k] + 2 * __popc(twos[r][k]) + __popc(ones[r][k]);
+      for (int k = 0; k < KB; k++) h[r][k] = 2 * h2[r][k] + __popc(ones[r][k]);
     // reduce over the G lanes of the group
     for (int off = G >> 1; off > 0; off >>= 1) {
 #pragma unroll
@@ -149,15 +154,15 @@ __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, 
   }
 }
 
-template <int KB, int RB>
-__global__ void __launch_bounds__(256)
+constexpr int kDensTpb = 128;
+
+template <int KB, int KX, int RB>
+__global__ void __launch_bounds__(kDensTpb)
 k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
              const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
              const int* __restrict__ has_half, double* __restrict__ logf, int planes_in_smem) {
   extern __shared__ uint4 smem4[];
   const bool half = (*has_half != 0);   // any centre at 0.5 (exact median tie): needs the `valid` plane
-  const uint4* m1 = m1g;
-  const uint4* valid = validg;
   if (planes_in_smem) {
     const int n = K * W4;
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
@@ -165,11 +170,14 @@ k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, 
       if (half) smem4[n + t] = validg[t];
     }
     __syncthreads();
-    m1 = smem4;
-    valid = smem4 + n;
+    const uint4* sm1 = smem4;            // shared-memory pointers: LDS, not generic loads
+    const uint4* sval = smem4 + n;
+    if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, sm1, sval, L, B, logf);
+    else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, sm1, sval, L, B, logf);
+  } else {
+    if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, m1g, validg, L, B, logf);
+    else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, m1g, validg, L, B, logf);
   }
-  if (half) density_sk_body<KB, RB, true>(bits, N, W4, K, G, m1, valid, L, B, logf);
-  else      density_sk_body<KB, RB, false>(bits, N, W4, K, G, m1, valid, L, B, logf);
 }
 
 // free dispersion ("skd"): per-column log-odds.  sum over mismatching columns of L_kd, taken over the set bits of the
@@ -325,14 +333,36 @@ __global__ void __launch_bounds__(256) k_sweep(SweepArgs a) {
       sweep_row<GS>(a, i, i < a.N, sub, wmax);
     }
   } else {
-    for (int L = 0; L < a.n_levels; L++) {
-      const int b = a.level_ptr[L], e = a.level_ptr[L + 1];
-      for (long long idx0 = b + warp_global * RPW; idx0 < e; idx0 += nwarps * RPW) {
-        const long long idx = idx0 + grp;
-        const bool valid = idx < e;
-        sweep_row<GS>(a, valid ? a.level_rows[idx] : 0, valid, sub, wmax);
+    // Levels are separated by grid-wide barriers; a run of consecutive small levels (deep, thin tails of the schedule)
+    // is instead walked by CTA 0 alone with block barriers, so the run costs one grid barrier instead of one per level.
+    constexpr int kSmall = 256;
+    const int block_warp = threadIdx.x >> 5, block_warps = blockDim.x >> 5;
+    int L = 0;
+    while (L < a.n_levels) {
+      int b = a.level_ptr[L], e = a.level_ptr[L + 1];
+      if (COOP && e - b <= kSmall) {
+        while (L < a.n_levels) {
+          b = a.level_ptr[L]; e = a.level_ptr[L + 1];
+          if (e - b > kSmall) break;
+          if (blockIdx.x == 0) {
+            for (long long idx0 = b + (long long)block_warp * RPW; idx0 < e; idx0 += (long long)block_warps * RPW) {
+              const long long idx = idx0 + grp;
+              const bool valid = idx < e;
+              sweep_row<GS>(a, valid ? a.level_rows[idx] : 0, valid, sub, wmax);
+            }
+            __syncthreads();
+          }
+          L++;
+        }
+      } else {
+        for (long long idx0 = b + warp_global * RPW; idx0 < e; idx0 += nwarps * RPW) {
+          const long long idx = idx0 + grp;
+          const bool valid = idx < e;
+          sweep_row<GS>(a, valid ? a.level_rows[idx] : 0, valid, sub, wmax);
+        }
+        L++;
       }
-      if (COOP && L + 1 < a.n_levels) {
+      if (COOP && L < a.n_levels) {
         __threadfence();
         cg::this_grid().sync();
       }
@@ -344,17 +374,27 @@ __global__ void __launch_bounds__(256) k_sweep(SweepArgs a) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // M-step.  Rows whose posterior is exactly one-hot in float32 (the vast majority after the first iteration) only add
-// their bit pattern to one class: they are grouped per class (k_classify -> k_offsets -> k_scatter) and summed with
-// bit-sliced carry-save counters (k_mstep_onehot).  The remaining fuzzy rows take the fp64 path (k_mstep_fuzzy).
+// their bit pattern to one class; they are summed with bit-sliced carry-save counters (k_mstep_onehot), the remaining
+// fuzzy rows take the fp64 path (k_mstep_fuzzy).
+//
+// The integer column counts are kept across EM iterations and updated incrementally: a row whose one-hot class did not
+// change since the previous M-step contributes nothing new, so only rows that entered a class ("add" bucket k) or
+// left one ("remove" bucket K + k) are streamed again.  Integer arithmetic makes this bit-identical to a full recount;
+// the first M-step of a run (prev = kNone everywhere) is the full pass.  Fuzzy rows (bucket 2K) are always recomputed.
+// Buckets are materialised as index lists: k_classify (bucket histogram) -> k_offsets -> k_scatter.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kNone = -2;  // prev key of a row that is not counted anywhere yet
+
 template <int KB>
 __global__ void __launch_bounds__(256)
-k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ cls, int* __restrict__ hist /*[K+1]*/,
-           double* __restrict__ nk_fz /*[K]*/) {
-  __shared__ int s_hist[KB + 1];
+k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ prev /*[N] in/out: key of last M-step*/,
+           int2* __restrict__ ent /*[N]: (remove bucket | -1, add/fuzzy bucket | -1)*/, int* __restrict__ hist /*[2K+1]*/,
+           int* __restrict__ nk_cnt /*[K]*/, double* __restrict__ nk_fz /*[K]*/) {
+  __shared__ int s_hist[2 * KB + 1];
+  __shared__ int s_nk[KB];
   __shared__ double s_fz[KB];
-  for (int t = threadIdx.x; t <= KB; t += blockDim.x) s_hist[t] = 0;
-  for (int t = threadIdx.x; t < KB; t += blockDim.x) s_fz[t] = 0.0;
+  for (int t = threadIdx.x; t < 2 * KB + 1; t += blockDim.x) s_hist[t] = 0;
+  for (int t = threadIdx.x; t < KB; t += blockDim.x) { s_fz[t] = 0.0; s_nk[t] = 0; }
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) {
@@ -370,57 +410,70 @@ k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ cl
       }
     }
     int key;
-    if (ones == 1 && zeros == K - 1) key = arg;
+    if (ones == 1 && zeros == K - 1) { key = arg; atomicAdd(&s_nk[key], 1); }
     else {
       key = K;
 #pragma unroll
       for (int k = 0; k < KB; k++)
         if (k < K && t[k] != 0.0f) atomicAdd(&s_fz[k], (double)t[k]);
     }
-    cls[i] = key;
-    atomicAdd(&s_hist[key], 1);
+    const int old = prev[i];
+    int e0 = -1, e1 = -1;
+    if (key == K) e1 = 2 * K;                   // fuzzy: always recomputed
+    if (old != key) {
+      if (old >= 0 && old < K) e0 = K + old;    // leaves class `old`
+      if (key < K) e1 = key;                     // enters class `key`
+      prev[i] = key;
+    }
+    ent[i] = make_int2(e0, e1);
+    if (e0 >= 0) atomicAdd(&s_hist[e0], 1);
+    if (e1 >= 0) atomicAdd(&s_hist[e1], 1);
   }
   __syncthreads();
-  for (int t = threadIdx.x; t <= K; t += blockDim.x)
+  for (int t = threadIdx.x; t < 2 * K + 1; t += blockDim.x)
     if (s_hist[t]) atomicAdd(&hist[t], s_hist[t]);
-  for (int t = threadIdx.x; t < K; t += blockDim.x)
+  for (int t = threadIdx.x; t < K; t += blockDim.x) {
+    if (s_nk[t]) atomicAdd(&nk_cnt[t], s_nk[t]);
     if (s_fz[t] != 0.0) atomicAdd(&nk_fz[t], s_fz[t]);
-}
-
-// offsets[k] = first slot of class k in perm (k = K: fuzzy rows); cursor = running copy for k_scatter;
-// nk_cnt[k] = one-hot rows of class k
-__global__ void k_offsets(const int* __restrict__ hist, int K, int* __restrict__ offsets /*[K+2]*/,
-                          int* __restrict__ cursor /*[K+1]*/, int* __restrict__ nk_cnt) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int acc = 0;
-    for (int k = 0; k <= K; k++) {
-      offsets[k] = acc;
-      cursor[k] = acc;
-      if (k < K) nk_cnt[k] = hist[k];
-      acc += hist[k];
-    }
-    offsets[K + 1] = acc;
   }
 }
 
-// rows -> perm, grouped by class.  One atomic per (warp, class present in the warp) instead of one per row: the 3-20
-// cursors are shared by all rows, and per-row atomics on them serialise (measured 70 us for 200 000 rows).
-__global__ void __launch_bounds__(256)
-k_scatter(const int* __restrict__ cls, long long N, int* __restrict__ cursor, int* __restrict__ perm) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const bool valid = i < N;
-  const int key = valid ? cls[i] : -1;
+// offsets[b] = first slot of bucket b in perm (b = 0..2K; offsets[2K+1] = total); cursor = running copy for k_scatter
+__global__ void k_offsets(const int* __restrict__ hist, int nb, int* __restrict__ offsets /*[nb+1]*/,
+                          int* __restrict__ cursor /*[nb]*/) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < nb; b++) {
+      offsets[b] = acc;
+      cursor[b] = acc;
+      acc += hist[b];
+    }
+    offsets[nb] = acc;
+  }
+}
+
+// rows -> perm, grouped by bucket.  One atomic per (warp, bucket present in the warp) instead of one per entry: the
+// handful of cursors is shared by all rows, and per-row atomics on them serialise (measured 70 us for 200 000 rows).
+__device__ __forceinline__ void scatter_one(int key, long long i, int lane, int* __restrict__ cursor, int* __restrict__ perm) {
   const unsigned peers = __match_any_sync(0xffffffffu, key);
   const int leader = __ffs(peers) - 1;
   const int rank = __popc(peers & ((1u << lane) - 1u));
   int base = 0;
-  if (valid && lane == leader) base = atomicAdd(&cursor[key], __popc(peers));
+  if (key >= 0 && lane == leader) base = atomicAdd(&cursor[key], __popc(peers));
   base = __shfl_sync(0xffffffffu, base, leader);
-  if (valid) perm[base + rank] = (int)i;
+  if (key >= 0) perm[base + rank] = (int)i;
 }
 
-constexpr int kSeg = 2048;     // rows per one-hot segment; counters have 12 planes (max 4095)
+__global__ void __launch_bounds__(256)
+k_scatter(const int2* __restrict__ ent, long long N, int* __restrict__ cursor, int* __restrict__ perm) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int2 e = make_int2(-1, -1);
+  if (i < N) e = ent[i];
+  scatter_one(e.x, i, lane, cursor, perm);
+  scatter_one(e.y, i, lane, cursor, perm);
+}
+
 constexpr int kPlanes = 12;
 constexpr int kMsTpb = 128;    // threads per CTA; each owns one 64-bit matrix word (64 genomes) of every row
 constexpr int kBatch = 16;     // rows per Harley-Seal block
@@ -472,78 +525,82 @@ __device__ __forceinline__ void load_batch(uint32_t (&lo)[kBatch], uint32_t (&hi
   }
 }
 
-// One thread owns one 64-bit word column (64 genomes).  blockIdx.y walks segments of at most kSeg rows of one class.
-// Rows are streamed in batches of 16 with the next batch's loads issued before the current batch is summed.
-__global__ void __launch_bounds__(kMsTpb)
-k_mstep_onehot(const uint2* __restrict__ bits2, int W2, int K, const int* __restrict__ offsets,
+// One thread owns one 64-bit word column (64 genomes) of a column tile; blockIdx.y owns slice y of the add/remove
+// entries [offsets[0], offsets[2K]) -- equal shares, so every CTA streams the same number of rows and the grid is sized
+// by the host to one resident wave (no tail).  A slice that straddles bucket boundaries flushes its counters once per
+// bucket: +count for an "add" bucket, -count for a "remove" bucket.  Rows are streamed in batches of 16 with the next
+// batch's loads issued before the current batch is summed; a bucket run longer than kMaxRun rows is flushed in pieces
+// (12 counter planes hold up to 4095).
+constexpr int kMaxRun = 4080;
+
+__global__ void __launch_bounds__(kMsTpb, 5)
+k_mstep_onehot(const uint2* __restrict__ bits2, int W2, int tile_w, int K, const int* __restrict__ offsets,
                const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad) {
-  __shared__ __align__(16) int s_rows[kSeg];
+  __shared__ __align__(16) int s_rows[kMaxRun];
   __shared__ int s_cnt[kMsTpb * 33];
-  // map blockIdx.y -> (class, segment start)
-  int seg = blockIdx.y, k = 0, start = 0, len = 0;
-  bool found = false;
-  for (k = 0; k < K; k++) {
-    const int n = offsets[k + 1] - offsets[k];
-    const int nseg = (n + kSeg - 1) / kSeg;
-    if (seg < nseg) {
-      start = offsets[k] + seg * kSeg;
-      len = min(kSeg, offsets[k + 1] - start);
-      found = true;
-      break;
-    }
-    seg -= nseg;
-  }
-  if (!found) return;
-  for (int t = threadIdx.x; t < len; t += blockDim.x) s_rows[t] = perm[start + t];
-  __syncthreads();
-  const int word = blockIdx.x * kMsTpb + threadIdx.x;
-  const bool active = word < W2;
-  uint32_t plo[kPlanes], phi[kPlanes];
+  const int total = offsets[2 * K];                       // add + remove entries
+  const long long S = gridDim.y;
+  const int lo = (int)((long long)total * blockIdx.y / S), hi = (int)((long long)total * (blockIdx.y + 1) / S);
+  if (lo >= hi) return;
+  const int word = blockIdx.x * tile_w + threadIdx.x;
+  const bool active = threadIdx.x < tile_w && word < W2;
+  const uint2* colp = bits2 + (active ? word : 0);
+
+  for (int b = 0; b < 2 * K; b++) {
+    const int b0 = max(lo, offsets[b]), b1 = min(hi, offsets[b + 1]);
+    for (int start = b0; start < b1; start += kMaxRun) {
+      const int len = min(kMaxRun, b1 - start);
+      __syncthreads();                                    // s_rows / s_cnt of the previous run are no longer read
+      for (int t = threadIdx.x; t < len; t += blockDim.x) s_rows[t] = perm[start + t];
+      __syncthreads();
+      uint32_t plo[kPlanes], phi[kPlanes];
 #pragma unroll
-  for (int j = 0; j < kPlanes; j++) { plo[j] = 0; phi[j] = 0; }
-  if (active) {
-    const uint2* colp = bits2 + word;
-    const int nb = len / kBatch;
-    uint32_t alo[kBatch], ahi[kBatch], blo[kBatch], bhi[kBatch];
-    if (nb > 0) load_batch(alo, ahi, colp, s_rows, 0, W2);
-    for (int b = 0; b < nb; b += 2) {
-      if (b + 1 < nb) load_batch(blo, bhi, colp, s_rows, (b + 1) * kBatch, W2);
-      hs16(plo, alo);
-      hs16(phi, ahi);
-      if (b + 1 < nb) {
-        if (b + 2 < nb) load_batch(alo, ahi, colp, s_rows, (b + 2) * kBatch, W2);
-        hs16(plo, blo);
-        hs16(phi, bhi);
+      for (int j = 0; j < kPlanes; j++) { plo[j] = 0; phi[j] = 0; }
+      if (active) {
+        const int nb = len / kBatch;
+        uint32_t alo[kBatch], ahi[kBatch], blo[kBatch], bhi[kBatch];
+        if (nb > 0) load_batch(alo, ahi, colp, s_rows, 0, W2);
+        for (int q = 0; q < nb; q += 2) {
+          if (q + 1 < nb) load_batch(blo, bhi, colp, s_rows, (q + 1) * kBatch, W2);
+          hs16(plo, alo);
+          hs16(phi, ahi);
+          if (q + 1 < nb) {
+            if (q + 2 < nb) load_batch(alo, ahi, colp, s_rows, (q + 2) * kBatch, W2);
+            hs16(plo, blo);
+            hs16(phi, bhi);
+          }
+        }
+        for (int r = nb * kBatch; r < len; r++) {  // tail rows: ripple through all planes
+          const uint2 v = ld_stream64(colp + (size_t)s_rows[r] * W2);
+          uint32_t c0 = v.x, c1 = v.y;
+#pragma unroll
+          for (int j = 0; j < kPlanes; j++) {
+            const uint32_t n0 = plo[j] & c0, n1 = phi[j] & c1;
+            plo[j] ^= c0; phi[j] ^= c1;
+            c0 = n0; c1 = n1;
+          }
+        }
       }
-    }
-    for (int r = nb * kBatch; r < len; r++) {  // tail rows: ripple through all planes
-      const uint2 v = ld_stream64(colp + (size_t)s_rows[r] * W2);
-      uint32_t c0 = v.x, c1 = v.y;
+      // expand the planes into integer counts, transpose through shared memory, add to global with coalesced REDs
+      const int cls = b < K ? b : b - K;
+      const int sign = b < K ? 1 : -1;
 #pragma unroll
-      for (int j = 0; j < kPlanes; j++) {
-        const uint32_t n0 = plo[j] & c0, n1 = phi[j] & c1;
-        plo[j] ^= c0; phi[j] ^= c1;
-        c0 = n0; c1 = n1;
-      }
-    }
-  }
-  // expand the planes into integer counts, transpose through shared memory, add to global with coalesced REDs
-#pragma unroll
-  for (int half = 0; half < 2; half++) {
-    if (half) __syncthreads();
+      for (int half = 0; half < 2; half++) {
+        if (half) __syncthreads();
 #pragma unroll 4
-    for (int b = 0; b < 32; b++) {
-      int c = 0;
+        for (int bit = 0; bit < 32; bit++) {
+          int c = 0;
 #pragma unroll
-      for (int j = 0; j < kPlanes; j++) c += (int)(((half ? phi[j] : plo[j]) >> b) & 1u) << j;
-      s_cnt[threadIdx.x * 33 + b] = c;
-    }
-    __syncthreads();
-    // thread t of the CTA owns columns 64 * (block word) ..: word w = blockIdx.x*kMsTpb + (t >> 5), bit (t & 31)
-    for (int t = threadIdx.x; t < kMsTpb * 32; t += blockDim.x) {
-      const int c = s_cnt[(t >> 5) * 33 + (t & 31)];
-      const int col = (blockIdx.x * kMsTpb + (t >> 5)) * 64 + half * 32 + (t & 31);
-      if (c != 0 && col < Dpad) atomicAdd(&cnt[(size_t)k * Dpad + col], c);
+          for (int j = 0; j < kPlanes; j++) c += (int)(((half ? phi[j] : plo[j]) >> bit) & 1u) << j;
+          s_cnt[threadIdx.x * 33 + bit] = c;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < tile_w * 32; t += blockDim.x) {
+          const int c = s_cnt[(t >> 5) * 33 + (t & 31)];
+          const int col = (blockIdx.x * tile_w + (t >> 5)) * 64 + half * 32 + (t & 31);
+          if (c != 0 && col < Dpad) atomicAdd(&cnt[(size_t)cls * Dpad + col], sign * c);
+        }
+      }
     }
   }
 }
@@ -554,7 +611,7 @@ __global__ void __launch_bounds__(256)
 k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int* __restrict__ offsets,
               const int* __restrict__ perm, const float* __restrict__ T, double* __restrict__ fsum /*[K][Dpad]*/,
               int Dpad) {
-  const int f0 = offsets[K], f1 = offsets[K + 1];
+  const int f0 = offsets[2 * K], f1 = offsets[2 * K + 1];   // the fuzzy bucket
   if (f0 + (int)blockIdx.y >= f1) return;
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   const int word = d >> 5, bit = d & 31;
