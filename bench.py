@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=400)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--incremental", action="store_true", help="time the incremental M-step (product default) as the headline")
     return ap.parse_args()
 
 
@@ -228,7 +229,8 @@ def run_ours(a):
     beta = float(np.float32(sp.beta_eff(BETA)))
     graph = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), D, sp.rowptr, sp.col, sp.w, device=dev)
     nnz = int(len(sp.col))
-    be = CudaBackend(sp.bits, D, N, K, False, engine.EPI_LOGSPACE, graph)
+    mflags = engine.EPI_LOGSPACE | (0 if a.incremental else engine.FULL_RECOUNT)
+    be = CudaBackend(sp.bits, D, N, K, False, mflags, graph)
     em = ShardedEM(be, N, K, rank, world, group)
     em.start(beta)
 

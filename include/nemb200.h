@@ -46,8 +46,11 @@ enum {
   NEMB200_EPI_REF      = 0,      /* E-step epilogue with the reference's arithmetic: float32 log-density, double
                                     exp() that may underflow, S==0 -> 1/K (nem_alg.c:2660-2698)                  */
   NEMB200_EPI_LOGSPACE = 1 << 0, /* log-sum-exp epilogue: valid for any number of genomes */
-  NEMB200_JACOBI       = 1 << 1  /* parallel posterior update instead of the reference's in-place Gauss-Seidel
+  NEMB200_JACOBI       = 1 << 1, /* parallel posterior update instead of the reference's in-place Gauss-Seidel
                                     sweep (nem_alg.c:2459-2464); off by default                                  */
+  NEMB200_FULL_RECOUNT = 1 << 2  /* M-step: recount every one-hot row at every iteration instead of updating the integer
+                                    column counts with the rows that changed class (same result bit for bit; this is
+                                    the mode the benchmark times as its headline)                                */
 };
 
 typedef struct nemb200_result {

@@ -196,6 +196,10 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
   cudaStream_t st = (cudaStream_t)stream_;
   const int K = pl->K;
   const long long N = pl->N_local;
+  if (pl->flags & NEMB200_FULL_RECOUNT) {  // forget the running counts: every one-hot row is streamed again
+    CK(cudaMemsetAsync(pl->prev, 0xFE, (size_t)std::max<long long>(N, 1) * sizeof(int), st));
+    CK(cudaMemsetAsync(pl->cnt_local, 0, (size_t)K * pl->Dpad * sizeof(int), st));
+  }
   CK(cudaMemsetAsync(pl->fsum, 0, (size_t)K * pl->Dpad * sizeof(double), st));
   CK(cudaMemsetAsync(pl->hist, 0, (2 * K + 1) * sizeof(int), st));
   CK(cudaMemsetAsync(pl->nk_cnt, 0, K * sizeof(int), st));
@@ -214,9 +218,7 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mstep_onehot, kMsTpb, 0));
     const long long slots = (long long)num_sms() * std::max(per_sm, 1);
-    long long slices = std::max<long long>(slots / ntiles, 1);
-    const long long need = (2 * N + kMaxRun - 1) / kMaxRun;      // keeps a slice within a few counter runs
-    if (slices < need) slices = std::min<long long>(need, 65535);
+    const long long slices = std::min<long long>(std::max<long long>(slots / ntiles, 1), 65535);  // longer slices are walked in kMaxRun pieces
     dim3 grid(ntiles, (unsigned)slices);
     k_mstep_onehot<<<grid, kMsTpb, 0, st>>>((const uint2*)bits, W2, tile_w, K, pl->offsets, pl->perm, pl->cnt_local, pl->Dpad);
     CK(cudaGetLastError());

@@ -100,11 +100,19 @@ __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, 
       for (int k = 0; k < KB; k++) { h2[r][k] = 0; ones[r][k] = 0; }
 
     PlanePtr pm = m1 + sub, pv = valid + sub;
-#pragma unroll 2
+    // software pipeline: the matrix words of step t+1 are requested before the words of step t are consumed
+    uint4 xn[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) { xn[r] = make_uint4(0, 0, 0, 0); if (sub < W4) { xn[r] = ld_stream(rowp[r]); rowp[r] += G; } }
+#pragma unroll 1
     for (int c = sub; c < W4; c += G) {
       uint4 x[RB];
 #pragma unroll
-      for (int r = 0; r < RB; r++) { x[r] = ld_stream(rowp[r]); rowp[r] += G; }
+      for (int r = 0; r < RB; r++) x[r] = xn[r];
+      if (c + G < W4) {
+#pragma unroll
+        for (int r = 0; r < RB; r++) { xn[r] = ld_stream(rowp[r]); rowp[r] += G; }
+      }
 #pragma unroll
       for (int k = 0; k < KB; k++) {
         if (KX > 0 || k < K) {
@@ -533,13 +541,16 @@ __device__ __forceinline__ void load_batch(uint32_t (&lo)[kBatch], uint32_t (&hi
 // (12 counter planes hold up to 4095).
 constexpr int kMaxRun = 4080;
 
-__global__ void __launch_bounds__(kMsTpb, 5)
+__global__ void __launch_bounds__(kMsTpb)
 k_mstep_onehot(const uint2* __restrict__ bits2, int W2, int tile_w, int K, const int* __restrict__ offsets,
                const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad) {
   __shared__ __align__(16) int s_rows[kMaxRun];
   __shared__ int s_cnt[kMsTpb * 33];
   const int total = offsets[2 * K];                       // add + remove entries
-  const long long S = gridDim.y;
+  // few entries (steady state of the incremental update): fewer, fuller slices -- the per-run counter flush is the
+  // fixed cost of a CTA
+  const long long S = min((long long)gridDim.y, max(1LL, ((long long)total + 63) / 64));
+  if (blockIdx.y >= S) return;
   const int lo = (int)((long long)total * blockIdx.y / S), hi = (int)((long long)total * (blockIdx.y + 1) / S);
   if (lo >= hi) return;
   const int word = blockIdx.x * tile_w + threadIdx.x;
@@ -605,27 +616,48 @@ k_mstep_onehot(const uint2* __restrict__ bits2, int W2, int tile_w, int K, const
   }
 }
 
-// Fuzzy rows: one thread per genome column, fp64 accumulators per class; blockIdx.y strides over the fuzzy list.
+// Fuzzy rows: one thread per genome column, fp64 accumulators per class; blockIdx.y owns an equal share of the fuzzy
+// list.  The share's row ids and posteriors are staged in shared memory first, so the matrix loads of consecutive rows
+// are independent (unrolled) instead of a chain of dependent loads per row.
+constexpr int kFzRows = 64;
+
 template <int KB>
 __global__ void __launch_bounds__(256)
 k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int* __restrict__ offsets,
               const int* __restrict__ perm, const float* __restrict__ T, double* __restrict__ fsum /*[K][Dpad]*/,
               int Dpad) {
+  __shared__ int s_row[kFzRows];
+  __shared__ float s_t[kFzRows][KB];
   const int f0 = offsets[2 * K], f1 = offsets[2 * K + 1];   // the fuzzy bucket
-  if (f0 + (int)blockIdx.y >= f1) return;
+  const int nf = f1 - f0;
+  const long long S = gridDim.y;
+  const int lo = f0 + (int)((long long)nf * blockIdx.y / S), hi = f0 + (int)((long long)nf * (blockIdx.y + 1) / S);
+  if (lo >= hi) return;
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   const int word = d >> 5, bit = d & 31;
+  const bool in_range = word < Ws;
   double acc[KB];
 #pragma unroll
   for (int k = 0; k < KB; k++) acc[k] = 0.0;
-  for (int f = f0 + blockIdx.y; f < f1; f += gridDim.y) {
-    const int row = perm[f];
-    uint32_t x = 0;
-    if (word < Ws) x = __ldg(bits + (size_t)row * Ws + word);
-    if ((x >> bit) & 1u) {
+  for (int base = lo; base < hi; base += kFzRows) {
+    const int n = min(kFzRows, hi - base);
+    __syncthreads();
+    for (int t = threadIdx.x; t < n * K; t += blockDim.x) {
+      const int r = t / K, k = t - r * K;
+      const int row = perm[base + r];
+      if (k == 0) s_row[r] = row;
+      s_t[r][k] = T[(size_t)row * K + k];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < n; r++) {
+      uint32_t x = 0;
+      if (in_range) x = __ldg(bits + (size_t)s_row[r] * Ws + word);
+      if ((x >> bit) & 1u) {
 #pragma unroll
-      for (int k = 0; k < KB; k++)
-        if (k < K) acc[k] += (double)__ldg(T + (size_t)row * K + k);
+        for (int k = 0; k < KB; k++)
+          if (k < K) acc[k] += (double)s_t[r][k];
+      }
     }
   }
   if (d < D) {

@@ -21,6 +21,7 @@ LIB_PATH = PKG_DIR / "libnemb200.so"
 EPI_REF = 0
 EPI_LOGSPACE = 1
 JACOBI = 2
+FULL_RECOUNT = 4
 MAX_K = 32
 
 STS_OK, STS_EMPTYCLASS, STS_INFINITE = 0, 1, 2
