@@ -322,6 +322,33 @@ def run_ours(a):
                        "d2h_bytes_per_step": int(N * K * 4 + 2 * K * D * 4) // its, "iterations": its, "wall_s": dt,
                        "em_device_ms": run.elapsed_ms, "converged": run.converged,
                        "call": "nemb200_nem_host (pinned host matrix -> H2D -> EM to convergence -> posteriors D2H)"}
+    elif not a.no_e2e:
+        # N > 1: the same job through the row-sharded driver -- every rank's shard starts in pinned host memory, is copied
+        # to its GPU, EM runs to convergence (NCCL all-reduce / all-gather inside), rank 0 reads the posteriors back
+        host_bits = torch.empty(sp.bits.shape, dtype=torch.int32, pin_memory=True)
+        host_bits.copy_(sp.bits)
+        del be, em
+        sp.bits = None
+        torch.cuda.empty_cache()
+        barrier()
+        t0 = time.perf_counter()
+        dbits = host_bits.to(dev, non_blocking=True)
+        g2 = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), D, sp.rowptr, sp.col, sp.w, device=dev)
+        be2 = CudaBackend(dbits, D, N, K, False, engine.EPI_LOGSPACE, g2)
+        out = ShardedEM(be2, N, K, rank, world, group).run(beta, 100, 0.01)
+        if rank == 0:
+            _ = out.T.cpu()
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        if rank == 0:
+            its = max(out.n_iter, 1)
+            line["e2e"] = {"value": its / float(t.item()), "unit": "EM iterations/s",
+                           "h2d_bytes_per_step": int(host_bits.numel() * 4 * world + sp.col.nbytes * 2 + sp.rowptr.nbytes) // its,
+                           "d2h_bytes_per_step": int(N * K * 4) // its, "iterations": its, "wall_s": float(t.item()),
+                           "converged": out.converged,
+                           "call": "ShardedEM.run (pinned host shards -> H2D -> row-sharded EM to convergence -> posteriors D2H)"}
     elif rank == 0:
         line["e2e"] = None
     if rank == 0 and not a.no_cpu:

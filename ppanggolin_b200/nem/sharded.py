@@ -103,14 +103,24 @@ class ShardedEM:
     def _allgather_logf(self):
         if self.world == 1:
             return
+        import torch
         import torch.distributed as dist
         full = self.b.logf_full
-        sizes = [shard_rows(self.N, self.world, r) for r in range(self.world)]
-        if all((hi - lo) == (sizes[0][1] - sizes[0][0]) for lo, hi in sizes):
+        spans = [shard_rows(self.N, self.world, r) for r in range(self.world)]
+        rows = max(hi - lo for lo, hi in spans)
+        if all((hi - lo) == rows for lo, hi in spans):
             dist.all_gather_into_tensor(full, full[self.lo:self.hi].clone(), group=self.group)
-        else:
-            outs = [full[lo:hi] for lo, hi in sizes]
-            dist.all_gather(outs, full[self.lo:self.hi].clone(), group=self.group)
+            return
+        # uneven shards (N not a multiple of the world size): gather equal-size padded blocks, then unpack
+        if getattr(self, "_pad", None) is None:
+            self._pad = (torch.zeros((rows, self.K), dtype=full.dtype, device=full.device),
+                         torch.zeros((self.world, rows, self.K), dtype=full.dtype, device=full.device))
+        mine, gathered = self._pad
+        mine[: self.hi - self.lo].copy_(full[self.lo:self.hi])
+        dist.all_gather_into_tensor(gathered.view(self.world * rows, self.K), mine, group=self.group)
+        for r, (lo, hi) in enumerate(spans):
+            if r != self.rank:
+                full[lo:hi].copy_(gathered[r, : hi - lo])
 
     # -- algorithm -----------------------------------------------------------------------------------------------
     def e_step(self, beta_now: float):

@@ -1,0 +1,67 @@
+"""Row-sharded EM driver under gloo, world_size 2, on CPU: the sharded run must reproduce the single-process run bit
+for bit (the M-step statistics are all-reduced, the log-densities all-gathered, the sweep replicated)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _run(rank, world, port, N, D, K, beta, iters, out):
+    for p in (str(ROOT), str(ROOT / "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from npbackend import NumpyBackend
+    from ppanggolin_b200.nem.sharded import ShardedEM, shard_rows
+    from ppanggolin_b200.synthetic import synth_pangenome
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    group = None
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        group = dist.group.WORLD
+    sp = synth_pangenome(N, D, seed=3)
+    lo, hi = shard_rows(N, world, rank)
+    be = NumpyBackend(sp.X[lo:hi], D, N, K, False, (sp.rowptr, sp.col, sp.w))
+    em = ShardedEM(be, N, K, rank, world, group)
+    b = float(np.float32(sp.beta_eff(beta)))
+    em.start(b)
+    flags = [em.iterate(b) for _ in range(iters)]
+    np.save(f"{out}/T_{world}_{rank}.npy", be.T[em.cur].numpy())
+    np.save(f"{out}/mu_{world}_{rank}.npy", be.mu)
+    np.save(f"{out}/flags_{world}_{rank}.npy", np.array(flags))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N", [301, 400])   # uneven and even shards (all_gather list path / all_gather_into_tensor path)
+def test_two_rank_gloo_run_equals_single_process(tmp_path, N):
+    D, K, beta, iters = 40, 3, 2.5, 3
+    _run(0, 1, _free_port(), N, D, K, beta, iters, str(tmp_path))
+    port = _free_port()
+    mp.start_processes(_run, args=(2, port, N, D, K, beta, iters, str(tmp_path)), nprocs=2, join=True, start_method="fork")
+    T1 = np.load(tmp_path / "T_1_0.npy")
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"T_2_{r}.npy"), T1)              # replicated, identical posteriors
+        assert np.array_equal(np.load(tmp_path / f"mu_2_{r}.npy"), np.load(tmp_path / "mu_1_0.npy"))
+        assert np.allclose(np.load(tmp_path / f"flags_2_{r}.npy"), np.load(tmp_path / "flags_1_0.npy"))
+    assert (T1.argmax(1) == 0).sum() > 0 and (T1.argmax(1) == K - 1).sum() > 0
