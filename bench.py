@@ -40,8 +40,8 @@ BETA = 2.5
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--families", type=int, default=200_000)
     ap.add_argument("--genomes", type=int, default=50_000)
@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02)
 
     def stop(self):
         self._halt.set()
@@ -240,13 +240,14 @@ def run_ours(a):
             dist.barrier(group=group)
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()   # started before the warm-up so that the short timed region is covered by several samples
     for _ in range(a.warmup):
         em.iterate(beta)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     be.launches = 0
+    be.plan.timing(True)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
     st = torch.cuda.current_stream()
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
@@ -264,6 +265,7 @@ def run_ours(a):
     t_end.record(st)
     barrier()
     clocks = sampler.stop() if sampler else None
+    onehot_ms, onehot_n = be.plan.timing(False)
     ms_total = t_start.elapsed_time(t_end)
     stage = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in ev])  # accumulate, finalize, density, sweep
     launches = be.launches
@@ -282,29 +284,62 @@ def run_ours(a):
     if rank == 0:
         peak, peak_src = measured_peaks()
         st_mean = stage.mean(0)
-        names = ["mstep_accumulate (k_mstep_onehot + classify/scatter/fuzzy)", "mstep_finalize", "density (k_density_sk)",
-                 "sweep (k_sweep, level-scheduled)"]
+        names = ["mstep_accumulate (classify/offsets/scatter + k_mstep_onehot + k_mstep_fuzzy)", "mstep_finalize (+ all-reduce)",
+                 "density (k_density_sk)", "sweep (k_sweep, level-scheduled; + all-gather)"]
         n_loc = hi - lo
         x_bytes = n_loc * ((D + 7) // 8)
-        alg = {0: x_bytes + n_loc * K * 4 + n_loc * 4 + K * D * 4,          # matrix + posteriors + row->class + counts out
-               2: x_bytes + n_loc * K * 8 + 2 * K * ((D + 7) // 8)}         # matrix + log-densities out + centre planes
-        dom = int(np.argmax(st_mean))
-        if dom not in alg:
-            dom = 2 if st_mean[2] >= st_mean[0] else 0
-        achieved = alg[dom] / (st_mean[dom] / 1000.0) / 1e9
+        traffic = {}
+        tp = ROOT / "profiles" / "r01_traffic.json"
+        if tp.is_file():
+            traffic = json.loads(tp.read_text())
+        kernels = {
+            "k_density_sk": {"ms": float(st_mean[2]), "bytes": x_bytes + n_loc * K * 8 + 2 * K * ((D + 7) // 8),
+                             "what": "matrix bits + log-densities out + centre planes"},
+            "k_mstep_onehot": {"ms": onehot_ms / max(onehot_n, 1), "bytes": x_bytes + n_loc * 4 + K * D * 4,
+                               "what": "matrix bits + row lists + column counts out"}}
+        for kk, v in kernels.items():
+            v["achieved_GBs"] = v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else None
+            v["frac"] = v["achieved_GBs"] / peak if v["ms"] > 0 else None
+        dom = max(kernels, key=lambda kk: kernels[kk]["ms"])
         biter = b_iter_bytes(N, D, K, nnz)
+        tr = traffic.get(dom, {}).get("dram_bytes_per_launch") if world == 1 else None
         line = {"metric": "NEM EM iterations/sec", "value": value, "unit": "EM iterations/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit ops + f64 epilogue", "data": "synthetic",
                 "config": workload_config(a), "gpu_launches": launches, "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": float(st_mean[dom]),
-                             "stage_ms": {n: float(v) for n, v in zip(names, st_mean)},
+                "mstep_mode": "incremental" if a.incremental else "full recount every iteration",
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBs"], "peak": peak,
+                             "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": tr, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": kernels[dom]["bytes"], "kernel_ms": kernels[dom]["ms"],
+                             "kernels": kernels, "stage_ms": {n: float(v) for n, v in zip(names, st_mean)},
                              "iteration": {"B_iter_bytes": biter, "achieved_GBs": biter / (ms_total / a.steps / 1000.0) / 1e9,
                                            "frac": biter / (ms_total / a.steps / 1000.0) / 1e9 / (peak * world)}},
                 "check": {"label_accuracy_vs_generator": acc, "gs_levels": graph.n_levels, "nnz": nnz,
                           "last_maxdiff": statuses[-1][0], "status": statuses[-1][1]}}
+    # ---- the product default (incremental M-step: only rows that changed class are recounted), same steps
+    if not a.incremental:
+        be_i = CudaBackend(sp.bits, D, N, K, False, engine.EPI_LOGSPACE, graph)
+        em_i = ShardedEM(be_i, N, K, rank, world, group)
+        em_i.start(beta)
+        for _ in range(a.warmup):
+            em_i.iterate(beta)
+        barrier()
+        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+        s0.record(st)
+        for _ in range(a.steps):
+            em_i.iterate(beta)
+        s1.record(st)
+        barrier()
+        ms_i = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([ms_i], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            ms_i = float(t.item())
+        same = bool(torch.equal(be_i.T[em_i.cur], be.T[em.cur]))
+        if rank == 0:
+            line["value_incremental"] = {"value": a.steps / (ms_i / 1000.0), "unit": "EM iterations/s", "ms_per_step": ms_i / a.steps,
+                                         "posteriors_identical_to_full_recount": same}
+        del be_i, em_i
     # ---- end to end through the host-buffer C ABI (rank 0's shard when N > 1: every rank would do the same)
     if not a.no_e2e and world == 1:
         host_bits = torch.empty(sp.bits.shape, dtype=torch.int32, pin_memory=True)

@@ -100,6 +100,10 @@ int  nemb200_plan_create(nemb200_plan** plan, int64_t N_local, int64_t N_total, 
                          int32_t K, int32_t free_disp, uint32_t flags);
 void nemb200_plan_destroy(nemb200_plan* plan);
 
+/* Measurement aid: while enabled, every k_mstep_onehot launch is bracketed by CUDA events on its stream.  Each call
+ * returns (and clears) the time and count accumulated so far, then sets the mode.  Synchronises on the recorded events. */
+int nemb200_plan_timing(nemb200_plan* plan, int32_t enable, float* onehot_ms_total, int32_t* onehot_launches);
+
 /* partition.py:65-85 + nem_exe.c:1023-1040: initial pk/mu/eps for (K, D), written into the plan's parameter block. */
 int nemb200_init_params(nemb200_plan* plan, void* stream);
 
@@ -109,6 +113,9 @@ int nemb200_init_params(nemb200_plan* plan, void* stream);
  * fsum = double[K][Dpad] fuzzy column sums, nk_cnt = int64-free int32[K], nk_fz = double[K]. */
 int nemb200_mstep_accumulate(nemb200_plan* plan, const uint32_t* bits, const float* T, void* stream);
 int nemb200_stats_ptrs(nemb200_plan* plan, int32_t** cnt, double** fsum, int32_t** nk_cnt, double** nk_fz, int64_t* Dpad);
+/* The same statistics as two contiguous blocks (cnt followed by nk_cnt; fsum followed by nk_fz), so that one int32 and
+ * one fp64 all-reduce cover them. */
+int nemb200_stats_blocks(nemb200_plan* plan, int32_t** iblock, int64_t* ilen, double** dblock, int64_t* dlen);
 
 /* M-step, part 2 (nem_mod.c:1317-1474 median, :1020-1076 / :1131-1170 dispersion, :455-459 proportions): parameters
  * from (all-reduced) statistics.  Sets the plan's status word to NEMB200_STS_EMPTYCLASS when a class is empty. */

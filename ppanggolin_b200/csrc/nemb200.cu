@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "nemb200_kernels.cuh"
@@ -71,6 +72,9 @@ struct nemb200_plan {
   double* Lword = nullptr;  // [K][Ws] (skd)
   double* fin_partial = nullptr;  // [K][nchunk][2]
   int* fin_tickets = nullptr;     // [K]
+  // optional CUDA-event timing of k_mstep_onehot (bench.py's roofline): pairs recorded per launch, read back on demand
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> onehot_events;
   uint32_t* flags2 = nullptr;     // [0] max |T_new - T_old| as float bits, [1] status (P.status points here)
   int fin_chunks = 0;
   float* eps_init = nullptr;
@@ -118,9 +122,12 @@ extern "C" int nemb200_plan_create(nemb200_plan** out, int64_t N_local, int64_t 
   A(P.L, pl->free_disp ? (size_t)K * pl->Dpad : (size_t)K) A(P.B, K)
   A(P.has_half, 1) A(pl->flags2, 2)
   P.status = (int*)(pl->flags2 + 1);
-  A(pl->cnt, (size_t)K * pl->Dpad) A(pl->fsum, (size_t)K * pl->Dpad)
+  // statistics that a multi-GPU driver all-reduces: one contiguous int32 block and one contiguous fp64 block
+  A(pl->cnt, (size_t)K * pl->Dpad + K) A(pl->fsum, (size_t)K * pl->Dpad + K)
+  pl->nk_cnt = pl->cnt + (size_t)K * pl->Dpad;
+  pl->nk_fz = pl->fsum + (size_t)K * pl->Dpad;
   A(pl->cnt_local, (size_t)K * pl->Dpad)
-  A(pl->nk_cnt, K) A(pl->nk_fz, K) A(pl->hist, 2 * K + 1) A(pl->offsets, 2 * K + 2) A(pl->cursor, 2 * K + 1)
+  A(pl->hist, 2 * K + 1) A(pl->offsets, 2 * K + 2) A(pl->cursor, 2 * K + 1)
   A(pl->prev, N_local) A(pl->ent, N_local) A(pl->perm, 2 * N_local)
   A(pl->Lword, (size_t)K * pl->Ws) A(pl->eps_init, K) A(P.eps_k, K)
   pl->fin_chunks = (pl->Dpad + kFinCols - 1) / kFinCols;
@@ -135,6 +142,7 @@ extern "C" int nemb200_plan_create(nemb200_plan** out, int64_t N_local, int64_t 
 
 extern "C" void nemb200_plan_destroy(nemb200_plan* pl) {
   if (!pl) return;
+  for (auto& pr : pl->onehot_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (void* p : pl->allocs) cudaFree(p);
   delete pl;
 }
@@ -220,8 +228,17 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
     const long long slots = (long long)num_sms() * std::max(per_sm, 1);
     const long long slices = std::min<long long>(std::max<long long>(slots / ntiles, 1), 65535);  // longer slices are walked in kMaxRun pieces
     dim3 grid(ntiles, (unsigned)slices);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (pl->timing) {
+      CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      CK(cudaEventRecord(e0, st));
+    }
     k_mstep_onehot<<<grid, kMsTpb, 0, st>>>((const uint2*)bits, W2, tile_w, K, pl->offsets, pl->perm, pl->cnt_local, pl->Dpad);
     CK(cudaGetLastError());
+    if (pl->timing) {
+      CK(cudaEventRecord(e1, st));
+      pl->onehot_events.emplace_back(e0, e1);
+    }
     rc = DISPATCH_KB(K, launch_fuzzy, pl, bits, T, st);
     if (rc) return rc;
   }
@@ -238,6 +255,33 @@ extern "C" int nemb200_stats_ptrs(nemb200_plan* pl, int32_t** cnt, double** fsum
   if (nk_cnt) *nk_cnt = pl->nk_cnt;
   if (nk_fz) *nk_fz = pl->nk_fz;
   if (Dpad) *Dpad = pl->Dpad;
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_plan_timing(nemb200_plan* pl, int32_t enable, float* onehot_ms_total, int32_t* onehot_launches) {
+  if (!pl) return fail(NEMB200_ERR_ARG, "plan_timing: null plan");
+  float tot = 0.0f;
+  int n = 0;
+  for (auto& pr : pl->onehot_events) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { tot += ms; n++; }
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  pl->onehot_events.clear();
+  if (onehot_ms_total) *onehot_ms_total = tot;
+  if (onehot_launches) *onehot_launches = n;
+  pl->timing = enable != 0;
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_stats_blocks(nemb200_plan* pl, int32_t** iblock, int64_t* ilen, double** dblock, int64_t* dlen) {
+  if (!pl) return fail(NEMB200_ERR_ARG, "stats_blocks: null plan");
+  const int64_t n = (int64_t)pl->K * pl->Dpad + pl->K;
+  if (iblock) *iblock = pl->cnt;
+  if (dblock) *dblock = pl->fsum;
+  if (ilen) *ilen = n;
+  if (dlen) *dlen = n;
   return NEMB200_OK;
 }
 

@@ -51,10 +51,12 @@ SIGNATURES = {
     "nemb200_gs_schedule": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp]),
     "nemb200_plan_create": (ctypes.c_int, [ctypes.POINTER(_vp), _i64, _i64, _i64, _i64, _i32, _i32, _u32]),
     "nemb200_plan_destroy": (None, [_vp]),
+    "nemb200_plan_timing": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_f32), ctypes.POINTER(_i32)]),
     "nemb200_init_params": (ctypes.c_int, [_vp, _vp]),
     "nemb200_mstep_accumulate": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "nemb200_stats_ptrs": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
                                           ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
+    "nemb200_stats_blocks": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i64), ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
     "nemb200_mstep_finalize": (ctypes.c_int, [_vp, _vp]),
     "nemb200_density": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "nemb200_sweep": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp]),
@@ -313,6 +315,29 @@ class Plan:
             cnt, fsum, nkc, nkf = self._stat_ptrs
             self._views = (view(cnt, (K, Dp), "<i4"), view(fsum, (K, Dp), "<f8"), view(nkc, (K,), "<i4"), view(nkf, (K,), "<f8"))
         return self._views
+
+    def timing(self, enable: bool):
+        """(total ms, launches) of k_mstep_onehot recorded since the last call; then switch event timing on/off."""
+        ms, n = _f32(0.0), _i32(0)
+        _check(lib().nemb200_plan_timing(self._h, int(enable), ctypes.byref(ms), ctypes.byref(n)), "plan_timing")
+        return float(ms.value), int(n.value)
+
+    def stats_blocks(self):
+        """(int32 block, fp64 block): flat torch views covering all M-step statistics, for two in-place all-reduces."""
+        if getattr(self, "_blocks", None) is None:
+            torch = _torch()
+            ib, db, il, dl = _vp(), _vp(), _i64(), _i64()
+            _check(lib().nemb200_stats_blocks(self._h, ctypes.byref(ib), ctypes.byref(il), ctypes.byref(db), ctypes.byref(dl)), "stats_blocks")
+            dev = torch.cuda.current_device()
+
+            def view(ptr, n, typestr):
+                class _A:
+                    pass
+                a = _A()
+                a.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+                return torch.as_tensor(a, device=f"cuda:{dev}")
+            self._blocks = (view(ib.value, int(il.value), "<i4"), view(db.value, int(dl.value), "<f8"))
+        return self._blocks
 
     def init_params(self):
         _check(lib().nemb200_init_params(self._h, _stream()), "init_params")

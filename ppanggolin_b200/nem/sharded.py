@@ -56,7 +56,7 @@ class CudaBackend:
         self.plan.mstep_accumulate(self.bits, T_local); self.launches += 5
 
     def stats(self):
-        return self.plan.stats_tensors()
+        return self.plan.stats_blocks()   # two contiguous blocks: int32 counts + class sizes, fp64 fuzzy sums + sizes
 
     def finalize(self):
         self.plan.mstep_finalize(); self.launches += 1
