@@ -86,6 +86,19 @@ int nemb200_nem_device(const uint32_t* bits, int64_t N, int64_t D, int64_t row_s
                        float* T_out, float* mu_out, float* eps_out, float* pk_out, nemb200_result* result,
                        void* stream);
 
+/* A batch of independent instances (the K-selection sweep of partition.py:482-514: same matrix, K = 2..20, beta 0,
+ * 10 iterations; or the chunk samples of partition.py:837-846), device-resident operands, arrays of length n_inst.
+ * Every instance gets its own stream; iterations are enqueued in lock-step so that the small kernels of different
+ * instances overlap on the GPU, and there is one flag read per instance and iteration.  Array arguments that are not
+ * needed (graph arrays when every beta is 0, output arrays) may be NULL. */
+int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* bits, const int64_t* N, const int64_t* D,
+                             const int64_t* row_stride_words, const int32_t* const* rowptr, const int32_t* const* col,
+                             const float* const* w, const int32_t* const* sched_level_ptr,
+                             const int32_t* const* sched_rows, const int32_t* n_levels, const int32_t* K,
+                             const float* beta, const int32_t* free_disp, const int32_t* itermax, float cv_th,
+                             uint32_t flags, float* const* T_out, float* const* mu_out, float* const* eps_out,
+                             float* const* pk_out, nemb200_result* results);
+
 /* Host helper: level schedule of the in-place sweep.  level(i) = 1 + max level(j) over neighbours j < i, so rows of one
  * level can be updated concurrently and still read exactly the values the sequential sweep 0..N-1 would (neighbours
  * j < i already updated, j >= i not yet; nem_alg.c:2441-2476).  level_ptr_out: N+1 ints (only n_levels+1 used),

@@ -519,75 +519,112 @@ struct RunBuffers {
   ~RunBuffers() { for (void* p : owned) cudaFree(p); }
 };
 
-static int run_em(nemb200_plan* pl, const uint32_t* bits, const int32_t* rowptr, const int32_t* col, const float* w,
-                  const int32_t* lvl_ptr, const int32_t* lvl_rows, int n_levels, float beta, int itermax, float cv_th,
-                  float* T_out, nemb200_result* res, cudaStream_t st) {
-  const long long N = pl->N_local;
-  const int K = pl->K;
+// One EM run as a small state machine, so that a single instance and a batch of independent instances (K sweep,
+// chunk samples: partition.py:482-514, :837-846) share the same code: begin() and enqueue_iteration() only enqueue
+// work on the instance's stream; poll() does the iteration's single 8-byte read-back.
+struct EmRun {
+  nemb200_plan* pl = nullptr;
+  const uint32_t* bits = nullptr;
+  const int32_t *rowptr = nullptr, *col = nullptr, *lvl_ptr = nullptr, *lvl_rows = nullptr;
+  const float* w = nullptr;
+  int n_levels = 1;
+  float beta = 0.0f, cv_th = 0.01f;
+  int itermax = 100;
+  cudaStream_t st = nullptr;
   RunBuffers rb;
-  auto alloc = [&](void** p, size_t bytes) -> int {
-    CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
-    rb.owned.push_back(*p);
-    return 0;
-  };
-  int rc;
-  if ((rc = alloc((void**)&rb.logf, (size_t)N * K * sizeof(double)))) return rc;
-  if ((rc = alloc((void**)&rb.Ta, (size_t)N * K * sizeof(float)))) return rc;
-  if ((rc = alloc((void**)&rb.Tb, (size_t)N * K * sizeof(float)))) return rc;
-  if ((rc = alloc((void**)&rb.flags, 4 * sizeof(uint32_t)))) return rc;
-  cudaEvent_t ev0, ev1;
-  CK(cudaEventCreate(&ev0));
-  CK(cudaEventCreate(&ev1));
-  CK(cudaEventRecord(ev0, st));
-
-  // --- nem_alg.c:2023-2065 with Needinit = 1
-  if ((rc = nemb200_init_params(pl, st))) return rc;
-  CK(cudaMemsetAsync(rb.Ta, 0, (size_t)N * K * sizeof(float), st));  // ClassifM is calloc'ed (nem_exe.c:533-536)
-  if ((rc = nemb200_density(pl, bits, rb.logf, st))) return rc;
-  if ((rc = nemb200_sweep(pl, N, rb.logf, rb.Ta, rb.Tb, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, 0.0f, rb.flags, st))) return rc;
-  float* cur = rb.Tb;
-  float* other = rb.Ta;
-  if (beta != 0.0f) {
-    if ((rc = nemb200_sweep(pl, N, rb.logf, cur, other, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, beta, rb.flags, st))) return rc;
-    std::swap(cur, other);
-  }
-  // with beta == 0 the second sweep of the reference recomputes the same posteriors: skipped
-
-  // --- nem_alg.c:1829-1894
+  float *cur = nullptr, *other = nullptr;
   int iter = 0, converged = 0, status = NEMB200_STS_OK;
-  for (iter = 1; iter <= itermax && !converged && status == NEMB200_STS_OK; iter++) {
+  bool active = true;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double crit[5] = {0, 0, 0, 0, 0};
+  float ms = 0.0f;
+  ~EmRun() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
+
+  int begin() {  // nem_alg.c:2023-2065 with Needinit = 1
+    const long long N = pl->N_local;
+    const int K = pl->K;
+    auto alloc = [&](void** p, size_t bytes) -> int {
+      CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+      rb.owned.push_back(*p);
+      return 0;
+    };
+    int rc;
+    if ((rc = alloc((void**)&rb.logf, (size_t)N * K * sizeof(double)))) return rc;
+    if ((rc = alloc((void**)&rb.Ta, (size_t)N * K * sizeof(float)))) return rc;
+    if ((rc = alloc((void**)&rb.Tb, (size_t)N * K * sizeof(float)))) return rc;
+    if ((rc = alloc((void**)&rb.flags, 4 * sizeof(uint32_t)))) return rc;
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, st));
+    if ((rc = nemb200_init_params(pl, st))) return rc;
+    CK(cudaMemsetAsync(rb.Ta, 0, (size_t)N * K * sizeof(float), st));  // ClassifM is calloc'ed (nem_exe.c:533-536)
+    if ((rc = nemb200_density(pl, bits, rb.logf, st))) return rc;
+    if ((rc = nemb200_sweep(pl, N, rb.logf, rb.Ta, rb.Tb, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, 0.0f, rb.flags, st))) return rc;
+    cur = rb.Tb;
+    other = rb.Ta;
+    if (beta != 0.0f) {
+      if ((rc = nemb200_sweep(pl, N, rb.logf, cur, other, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, beta, rb.flags, st))) return rc;
+      std::swap(cur, other);
+    }
+    // with beta == 0 the second sweep of the reference recomputes the same posteriors: skipped
+    active = itermax >= 1;
+    return 0;
+  }
+  int enqueue_iteration() {  // nem_alg.c:1844-1863
+    int rc;
+    iter++;
     if ((rc = nemb200_mstep_accumulate(pl, bits, cur, st))) return rc;
     if ((rc = nemb200_mstep_finalize(pl, st))) return rc;
     if ((rc = nemb200_density(pl, bits, rb.logf, st))) return rc;
-    if ((rc = nemb200_sweep(pl, N, rb.logf, cur, other, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, beta, nullptr, st))) return rc;
+    return nemb200_sweep(pl, pl->N_local, rb.logf, cur, other, rowptr, col, w, lvl_ptr, lvl_rows, n_levels, beta, nullptr, st);
+  }
+  int poll() {  // nem_alg.c:1868-1892
     float maxdif = 0.0f;
     int32_t sts = 0;
-    if ((rc = nemb200_read_flags(pl, &maxdif, &sts, st))) return rc;   // the one device->host read of the iteration
+    int rc = nemb200_read_flags(pl, &maxdif, &sts, st);  // the one device->host read of the iteration
+    if (rc) return rc;
     status = sts;
-    if (status != NEMB200_STS_OK) break;  // empty class: the reference stops before the E-step (nem_alg.c:1873-1892)
+    if (status != NEMB200_STS_OK) { active = false; return 0; }  // empty class: the reference stops (nem_alg.c:1873-1892)
     std::swap(cur, other);
     converged = (maxdif < cv_th);  // nem_alg.c:2160-2173
+    if (converged || iter >= itermax) active = false;
+    return 0;
   }
-  if (status == NEMB200_STS_OK) iter = iter - 1;
-  // --- nem_alg.c:1906
-  double crit[5] = {0, 0, 0, 0, 0};
-  if (status == NEMB200_STS_OK) {
-    if ((rc = nemb200_criteria(pl, N, rb.logf, cur, rowptr, col, w, beta, crit, st))) return rc;
-    if (std::isinf(crit[0]) && crit[0] < 0) status = NEMB200_STS_INFINITE;  // nem_alg.c:2482-2487
+  int finish(float* T_out, nemb200_result* res) {  // nem_alg.c:1906
+    int rc;
+    if (status == NEMB200_STS_OK) {
+      if ((rc = nemb200_criteria(pl, pl->N_local, rb.logf, cur, rowptr, col, w, beta, crit, st))) return rc;
+      if (std::isinf(crit[0]) && crit[0] < 0) status = NEMB200_STS_INFINITE;  // nem_alg.c:2482-2487
+    }
+    CK(cudaEventRecord(ev1, st));
+    CK(cudaEventSynchronize(ev1));
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    if (T_out) CK(cudaMemcpyAsync(T_out, cur, (size_t)pl->N_local * pl->K * sizeof(float), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    if (res) {
+      for (int q = 0; q < 5; q++) res->crit[q] = crit[q];
+      res->n_iter = iter; res->converged = converged; res->status = status; res->n_levels = n_levels; res->elapsed_ms = ms;
+    }
+    return NEMB200_OK;
   }
-  CK(cudaEventRecord(ev1, st));
-  CK(cudaEventSynchronize(ev1));
-  float ms = 0.0f;
-  CK(cudaEventElapsedTime(&ms, ev0, ev1));
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
-  if (T_out) CK(cudaMemcpyAsync(T_out, cur, (size_t)N * K * sizeof(float), cudaMemcpyDefault, st));
-  CK(cudaStreamSynchronize(st));
-  if (res) {
-    for (int q = 0; q < 5; q++) res->crit[q] = crit[q];
-    res->n_iter = iter; res->converged = converged; res->status = status; res->n_levels = n_levels; res->elapsed_ms = ms;
+};
+
+static int run_em(nemb200_plan* pl, const uint32_t* bits, const int32_t* rowptr, const int32_t* col, const float* w,
+                  const int32_t* lvl_ptr, const int32_t* lvl_rows, int n_levels, float beta, int itermax, float cv_th,
+                  float* T_out, nemb200_result* res, cudaStream_t st) {
+  EmRun r;
+  r.pl = pl; r.bits = bits; r.rowptr = rowptr; r.col = col; r.w = w; r.lvl_ptr = lvl_ptr; r.lvl_rows = lvl_rows;
+  r.n_levels = n_levels; r.beta = beta; r.itermax = itermax; r.cv_th = cv_th; r.st = st;
+  int rc = r.begin();
+  if (rc) return rc;
+  while (r.active) {
+    if ((rc = r.enqueue_iteration())) return rc;
+    if ((rc = r.poll())) return rc;
   }
-  return NEMB200_OK;
+  return r.finish(T_out, res);
 }
 
 static int copy_params_out(nemb200_plan* pl, float* mu, float* eps, float* pk, cudaStream_t st) {
@@ -618,6 +655,60 @@ extern "C" int nemb200_nem_device(const uint32_t* bits, int64_t N, int64_t D, in
   rc = run_em(pl, bits, rowptr, col, w, sched_level_ptr, sched_rows, n_levels, beta, itermax, cv_th, T_out, result, st);
   if (rc == 0) rc = copy_params_out(pl, mu_out, eps_out, pk_out, st);
   nemb200_plan_destroy(pl);
+  return rc;
+}
+
+extern "C" int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* bits, const int64_t* N, const int64_t* D,
+                                        const int64_t* row_stride_words, const int32_t* const* rowptr,
+                                        const int32_t* const* col, const float* const* w,
+                                        const int32_t* const* sched_level_ptr, const int32_t* const* sched_rows,
+                                        const int32_t* n_levels, const int32_t* K, const float* beta,
+                                        const int32_t* free_disp, const int32_t* itermax, float cv_th, uint32_t flags,
+                                        float* const* T_out, float* const* mu_out, float* const* eps_out,
+                                        float* const* pk_out, nemb200_result* results) {
+  if (n_inst < 1 || !bits || !N || !D || !row_stride_words || !K || !beta || !free_disp || !itermax || !results)
+    return fail(NEMB200_ERR_ARG, "nem_device_batch: null argument");
+  std::vector<EmRun> runs(n_inst);
+  std::vector<nemb200_plan*> plans(n_inst, nullptr);
+  std::vector<cudaStream_t> streams(n_inst, nullptr);
+  int rc = 0;
+  auto cleanup = [&]() {
+    for (auto s : streams) if (s) { cudaStreamSynchronize(s); }
+    runs.clear();                                   // frees the per-run device buffers
+    for (auto p : plans) nemb200_plan_destroy(p);
+    for (auto s : streams) if (s) cudaStreamDestroy(s);
+  };
+  for (int i = 0; i < n_inst && rc == 0; i++) {
+    const bool graph = beta[i] != 0.0f;
+    if (!bits[i] || N[i] < 1) { rc = fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d has no matrix", i); break; }
+    if (graph && (!rowptr || !col || !w || !rowptr[i] || !col[i] || !w[i])) { rc = fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d needs its neighbour graph", i); break; }
+    if (cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking) != cudaSuccess) { rc = fail(NEMB200_ERR_CUDA, "nem_device_batch: stream"); break; }
+    rc = nemb200_plan_create(&plans[i], N[i], N[i], D[i], row_stride_words[i], K[i], free_disp[i], flags);
+    if (rc) break;
+    EmRun& r = runs[i];
+    r.pl = plans[i]; r.bits = bits[i];
+    r.rowptr = graph ? rowptr[i] : nullptr; r.col = graph ? col[i] : nullptr; r.w = graph ? w[i] : nullptr;
+    r.lvl_ptr = (graph && sched_level_ptr) ? sched_level_ptr[i] : nullptr;
+    r.lvl_rows = (graph && sched_rows) ? sched_rows[i] : nullptr;
+    r.n_levels = (graph && n_levels) ? n_levels[i] : 1;
+    r.beta = beta[i]; r.itermax = itermax[i]; r.cv_th = cv_th; r.st = streams[i];
+    rc = r.begin();
+  }
+  // lock-step: enqueue one iteration of every live instance (their kernels overlap on the GPU), then read the flags
+  bool any = rc == 0;
+  while (any && rc == 0) {
+    any = false;
+    for (int i = 0; i < n_inst && rc == 0; i++)
+      if (runs[i].active) rc = runs[i].enqueue_iteration();
+    for (int i = 0; i < n_inst && rc == 0; i++)
+      if (runs[i].active) { rc = runs[i].poll(); any = any || runs[i].active; }
+  }
+  for (int i = 0; i < n_inst && rc == 0; i++) {
+    rc = runs[i].finish(T_out ? T_out[i] : nullptr, &results[i]);
+    if (rc == 0) rc = copy_params_out(plans[i], mu_out ? mu_out[i] : nullptr, eps_out ? eps_out[i] : nullptr,
+                                      pk_out ? pk_out[i] : nullptr, streams[i]);
+  }
+  cleanup();
   return rc;
 }
 

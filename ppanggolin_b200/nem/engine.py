@@ -48,6 +48,7 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, ctypes.POINTER(_Result)]),
     "nemb200_nem_device": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _i32,
                                           _f32, _u32, _vp, _vp, _vp, _vp, ctypes.POINTER(_Result), _vp]),
+    "nemb200_nem_device_batch": (ctypes.c_int, [_i32] + [_vp] * 14 + [_f32, _u32] + [_vp] * 5),
     "nemb200_gs_schedule": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp]),
     "nemb200_plan_create": (ctypes.c_int, [ctypes.POINTER(_vp), _i64, _i64, _i64, _i64, _i32, _i32, _u32]),
     "nemb200_plan_destroy": (None, [_vp]),
@@ -256,6 +257,56 @@ def nem_run_device(inp: DeviceInput, K: int, beta: float, free_dispersion: bool 
     s = stats.tolist()
     return NemRun(T, mu.cpu().numpy(), eps.cpu().numpy(), pk.cpu().numpy(), s[:5], int(s[5]), bool(s[6]), int(s[7]),
                   int(s[8]), float(s[9]))
+
+
+def nem_run_batch(instances, cv_th: float = 0.01, flags: int = EPI_REF):
+    """Independent NEM instances in one call (``nemb200_nem_device_batch``): the K-selection sweep or chunk samples.
+
+    ``instances``: list of ``(DeviceInput, K, beta, free_dispersion, itermax)``.  Returns a list of :class:`NemRun`."""
+    torch = _require_cuda()
+    n = len(instances)
+    if n == 0:
+        return []
+    dev = instances[0][0].bits.device
+    outs = []
+    P = ctypes.c_void_p * n
+    bits, rp, cl, ww, sp, sr = P(), P(), P(), P(), P(), P()
+    Tp, mup, epsp, pkp = P(), P(), P(), P()
+    Ns, Ds, Ws = (ctypes.c_int64 * n)(), (ctypes.c_int64 * n)(), (ctypes.c_int64 * n)()
+    nl, Ks, fds, its = (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)()
+    betas = (ctypes.c_float * n)()
+    res = (_Result * n)()
+    for i, (inp, K, beta, fd, itermax) in enumerate(instances):
+        if not (1 <= K <= MAX_K):
+            raise NemB200Error(f"K={K} outside 1..{MAX_K}")
+        beta32 = float(np.float32(beta))
+        g = beta32 != 0.0
+        if g and inp.rowptr is None:
+            raise NemB200Error("beta != 0 needs the neighbour graph")
+        N, W = inp.bits.shape
+        T = torch.empty((N, K), dtype=torch.float32, device=dev)
+        mu = torch.empty((K, inp.D), dtype=torch.float32, device=dev)
+        eps = torch.empty((K, inp.D), dtype=torch.float32, device=dev)
+        pk = torch.empty((K,), dtype=torch.float32, device=dev)
+        outs.append((T, mu, eps, pk))
+        bits[i], Ns[i], Ds[i], Ws[i] = _ptr(inp.bits), N, inp.D, W
+        rp[i], cl[i], ww[i] = (_ptr(inp.rowptr), _ptr(inp.col), _ptr(inp.w)) if g else (0, 0, 0)
+        sp[i], sr[i], nl[i] = (_ptr(inp.sched_ptr), _ptr(inp.sched_rows), inp.n_levels) if g else (0, 0, 1)
+        Ks[i], betas[i], fds[i], its[i] = K, beta32, int(bool(fd)), itermax
+        Tp[i], mup[i], epsp[i], pkp[i] = _ptr(T), _ptr(mu), _ptr(eps), _ptr(pk)
+    torch.cuda.current_stream().synchronize()   # the instances run on their own streams: inputs must be complete
+    addr = lambda a: ctypes.cast(a, ctypes.c_void_p)
+    with torch.cuda.device(dev):
+        rc = lib().nemb200_nem_device_batch(n, addr(bits), addr(Ns), addr(Ds), addr(Ws), addr(rp), addr(cl), addr(ww), addr(sp),
+                                            addr(sr), addr(nl), addr(Ks), addr(betas), addr(fds), addr(its), cv_th, flags,
+                                            addr(Tp), addr(mup), addr(epsp), addr(pkp), addr(res))
+    _check(rc, "nemb200_nem_device_batch")
+    runs = []
+    for i, (T, mu, eps, pk) in enumerate(outs):
+        r = res[i]
+        runs.append(NemRun(T, mu.cpu().numpy(), eps.cpu().numpy(), pk.cpu().numpy(), list(r.crit), r.n_iter, bool(r.converged),
+                           r.status, r.n_levels, r.elapsed_ms))
+    return runs
 
 
 def labels_device(T):

@@ -209,16 +209,50 @@ def evaluate_nb_partitions(
         select_organisms = set(organisms)
 
     _, nb_fam = write_nem_input_files(newtmpdir, select_organisms, sm_degree)
-    all_log_likelihood = []
-    for k in range(krange[0] - 1, krange[1] + 1):
-        all_log_likelihood.append(nem_single((newtmpdir, len(select_organisms), 0, free_dispersion, k, seed,
-                                              "param_file", True, 10, True)))
+    # the K candidates are independent NEM instances over the same matrix (beta 0, 10 iterations, partition.py:482-496):
+    # one batched call instead of the reference's fork pool; under torch.distributed the candidates are split over ranks
+    ks = list(range(krange[0] - 1, krange[1] + 1))
+    all_log_likelihood = run_k_candidates(newtmpdir, len(select_organisms), ks, free_dispersion)
     chosen_k, all_bics, all_icls, all_lls = select_k(all_log_likelihood, len(select_organisms), nb_fam,
                                                      free_dispersion, icl_margin)
     if len(all_bics) > 0 and draw_icl:
         _draw_icl(output, all_bics, all_icls, all_lls, chosen_k)
     export.release(newtmpdir)
     return chosen_k
+
+
+def run_k_candidates(nem_dir_path: Path, nb_org: int, ks: List[int], free_dispersion: bool):
+    """[(K, M, entropy) | ({}, None, None)] for every K in ``ks`` -- what ``nem_single`` returns with
+    ``just_log_likelihood=True`` (partition.py:271-272), computed as one batch on the GPU."""
+    logger = logging.getLogger("PPanGGOLiN")
+    inp = export.lookup(nem_dir_path)
+    if inp is None:
+        raise FileNotFoundError(f"no exported NEM instance registered for {nem_dir_path}")
+    if inp.device is None:
+        inp.device = engine.DeviceInput.from_numpy(inp.bits, inp.D, inp.rowptr, inp.col, inp.w)
+    rank, world = 0, 1
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        dist = None
+    mine = ks[rank::world]
+    runs = engine.nem_run_batch([(inp.device, k, 0.0, free_dispersion, 10) for k in mine], flags=_epilogue_flags(nb_org))
+    results = []
+    for k, run in zip(mine, runs):
+        if not run.ok:
+            logger.warning("A NEM run failed while estimating the optimal number of partitions "
+                           "(testing a candidate K), and this candidate was skipped. Final partitioning can still succeed.")
+            results.append(({}, None, None))
+            continue
+        _, entropy = engine.labels_device(run.T)
+        results.append((k, _g(run.crit[3], "%g"), entropy))
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, results)
+        results = [r for part in gathered for r in part]
+    return results
 
 
 def select_k(all_log_likelihood, nb_org: int, nb_fam: int, free_dispersion: bool, icl_margin: float):

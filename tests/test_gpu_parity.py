@@ -226,3 +226,44 @@ def test_partition_api_matches_reference(eng, name, tmp_path):
     for k, v in g["params"].items():
         assert pan.parameters["partition"][k] == v, k
     assert pan.status["partitioned"] == "Computed"
+
+
+def test_batch_equals_individual_runs(eng):
+    """nemb200_nem_device_batch (K candidates over one matrix + a neighbour-graph instance) == one call per instance."""
+    sp = synth_pangenome(3000, 300, seed=21)
+    inp = eng.DeviceInput.from_numpy(sp.bits, sp.D, sp.rowptr, sp.col, sp.w)
+    sp2 = synth_pangenome(1200, 90, seed=22)
+    inp2 = eng.DeviceInput.from_numpy(sp2.bits, sp2.D, sp2.rowptr, sp2.col, sp2.w)
+    inst = [(inp, k, 0.0, False, 10) for k in (2, 3, 5, 9, 14, 20)] + [(inp, 4, 0.0, True, 10), (inp2, 3, sp2.beta_eff(2.5), False, 100)]
+    batch = eng.nem_run_batch(inst)
+    for (i, k, beta, fd, itermax), b in zip(inst, batch):
+        a = eng.nem_run_device(i, k, beta, fd, itermax)
+        assert (a.status, a.n_iter, a.converged) == (b.status, b.n_iter, b.converged)
+        assert np.array_equal(a.T.cpu().numpy(), b.T.cpu().numpy())
+        assert np.array_equal(a.mu, b.mu) and np.array_equal(a.eps, b.eps) and np.array_equal(a.pk, b.pk)
+        assert a.crit[3] == pytest.approx(b.crit[3], rel=1e-12)
+
+
+def test_k_sweep_matches_reference_goldens(eng):
+    """The K-selection ingredients (M, entropy -> ICL) of the batched sweep against the reference's runs of the same
+    matrix (tests/golden/nem_sweep_K*.npz), and the K the reference's rule would choose from them."""
+    from ppanggolin_b200.nem import partition as part
+    names = [n for n in NEM_CASES if n.startswith("sweep_K")]
+    gs = {load_nem(n)["K"]: load_nem(n) for n in names}
+    g0 = next(iter(gs.values()))
+    inp = eng.DeviceInput.from_numpy(g0["bits"], g0["D"], g0["rowptr"], g0["col"], g0["w"])
+    ks = sorted(gs)
+    runs = eng.nem_run_batch([(inp, k, 0.0, False, 10) for k in ks])
+    ours, ref = [], []
+    N = g0["bits"].shape[0]
+    for k, run in zip(ks, runs):
+        _, ent = eng.labels_device(run.T)
+        ours.append((k, g6(run.crit[3]), ent))
+        _, _, rent = refnem.oracle_labels(gs[k]["T3"].astype(np.float32))
+        ref.append((k, gs[k]["crit"][3], rent))
+        assert abs(run.crit[3] - gs[k]["crit"][3]) <= REL_M * abs(gs[k]["crit"][3])
+    k_ours, _, icl_o, _ = part.select_k(ours, g0["D"], N, False, 0.05)
+    k_ref, _, icl_r, _ = part.select_k(ref, g0["D"], N, False, 0.05)
+    assert k_ours == k_ref
+    for k in ks:
+        assert abs(icl_o[k] - icl_r[k]) <= REL_M * abs(icl_r[k])
