@@ -65,6 +65,9 @@ typedef struct nemb200_result {
 int         nemb200_abi_version(void);
 const char* nemb200_last_error(void);
 int         nemb200_device_count(void);
+/* Plans and whole-run calls take their device memory from a per-process cache of freed blocks (cudaMalloc/cudaFree are
+ * too slow for thousands of chunk instances); this returns the cache to the driver. */
+int         nemb200_release_cached_memory(void);
 
 /* ---- whole-run entry points (replace nem(), nem_exe.h:23-38) ------------------------------------------------- */
 

@@ -52,6 +52,77 @@ static int num_sms() {
   return g_num_sms;
 }
 
+// Device memory: every plan / run takes ONE block from a small per-process cache of freed blocks (cudaMalloc and
+// cudaFree cost 0.1-1 ms each and cudaFree synchronises the device; a chunked partition() issues thousands of
+// instances).  nemb200_release_cached_memory() returns the cache to the driver.
+#include <mutex>
+extern "C" int nemb200_release_cached_memory(void);
+namespace {
+struct CachedBlock { void* p; size_t bytes; int dev; };
+std::mutex g_cache_mu;
+std::vector<CachedBlock> g_cache;
+size_t g_cache_bytes = 0;
+constexpr size_t kCacheLimit = (size_t)8 << 30;
+
+int cached_malloc(void** out, size_t bytes) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  bytes = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_cache.size(); i++)
+      if (g_cache[i].dev == dev && g_cache[i].bytes >= bytes && g_cache[i].bytes <= 2 * bytes + (1 << 20) &&
+          (best < 0 || g_cache[i].bytes < g_cache[best].bytes))
+        best = i;
+    if (best >= 0) {
+      *out = g_cache[best].p;
+      g_cache_bytes -= g_cache[best].bytes;
+      g_cache.erase(g_cache.begin() + best);
+      return 0;
+    }
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give the cache back and retry once
+    cudaGetLastError();
+    nemb200_release_cached_memory();
+    e = cudaMalloc(out, bytes);
+  }
+  if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? NEMB200_ERR_NOMEM : NEMB200_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  return 0;
+}
+size_t block_size_of(size_t bytes) { return std::max<size_t>((bytes + 255) & ~(size_t)255, 256); }
+void cached_free(void* p, size_t bytes) {
+  if (!p) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bytes = block_size_of(bytes);
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  if (g_cache_bytes + bytes > kCacheLimit) { cudaFree(p); return; }
+  g_cache.push_back({p, bytes, dev});
+  g_cache_bytes += bytes;
+}
+// bump allocator over one block; in counting mode it only measures
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0;
+  bool counting = true;
+  template <typename T> T* take(size_t n) {
+    const size_t a = (off + 255) & ~(size_t)255;
+    off = a + std::max<size_t>(n, 1) * sizeof(T);
+    return counting ? nullptr : reinterpret_cast<T*>(base + a);
+  }
+};
+}  // namespace
+
+extern "C" int nemb200_release_cached_memory(void) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto& b : g_cache) cudaFree(b.p);
+  g_cache.clear();
+  g_cache_bytes = 0;
+  return NEMB200_OK;
+}
+
 struct nemb200_plan {
   long long N_local = 0, N_total = 0;
   int D = 0, Ws = 0, Dpad = 0, K = 0, free_disp = 0;
@@ -81,17 +152,45 @@ struct nemb200_plan {
   double* crit_partial = nullptr;
   double* crit4 = nullptr;
   int crit_blocks = 0;
-  std::vector<void*> allocs;
+  float* crit_terms = nullptr;    // [N_local][K][2]  per-(row, class) D and G terms (reference-order accumulation)
+  double* crit_rows = nullptr;    // [N_local][2]     per-row log f_i and log z_i
+  // run buffers of the whole-run drivers (nem_host / nem_device / batch); not used by the stepwise interface
+  bool with_run_buffers = false;
+  double* run_logf = nullptr;
+  float *run_Ta = nullptr, *run_Tb = nullptr;
+  void* block = nullptr;          // the one device allocation everything above is carved from
+  size_t block_bytes = 0;
 };
 
-template <typename T>
-static int dalloc(nemb200_plan* pl, T** p, size_t n) {
-  void* q = nullptr;
-  CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
-  pl->allocs.push_back(q);
-  *p = (T*)q;
-  return 0;
+// lays every buffer of a plan out in `ar` (counting pass, then the real one)
+static void plan_layout(nemb200_plan* pl, Arena& ar) {
+  Params& P = pl->P;
+  const int K = pl->K;
+  const size_t N = (size_t)pl->N_local, D = (size_t)pl->D, Ws = (size_t)pl->Ws, Dpad = (size_t)pl->Dpad;
+  P.pk = ar.take<float>(K); P.logpk32 = ar.take<float>(K); P.logpk64 = ar.take<double>(K);
+  P.mu = ar.take<float>(K * D); P.eps = ar.take<float>(K * D); P.eps_k = ar.take<float>(K);
+  P.m1 = ar.take<uint32_t>(K * Ws); P.valid = ar.take<uint32_t>(K * Ws);
+  P.L = ar.take<double>(pl->free_disp ? K * Dpad : (size_t)K); P.B = ar.take<double>(K);
+  P.has_half = ar.take<int>(1);
+  pl->flags2 = ar.take<uint32_t>(2);
+  P.status = (int*)(pl->flags2 + 1);
+  // statistics that a multi-GPU driver all-reduces: one contiguous int32 block and one contiguous fp64 block
+  pl->cnt = ar.take<int>(K * Dpad + K); pl->fsum = ar.take<double>(K * Dpad + K);
+  pl->nk_cnt = pl->cnt + K * Dpad; pl->nk_fz = pl->fsum + K * Dpad;
+  pl->cnt_local = ar.take<int>(K * Dpad);
+  pl->hist = ar.take<int>(2 * K + 1); pl->offsets = ar.take<int>(2 * K + 2); pl->cursor = ar.take<int>(2 * K + 1);
+  pl->prev = ar.take<int>(N); pl->ent = ar.take<int2>(N); pl->perm = ar.take<int>(2 * N);
+  pl->Lword = ar.take<double>(K * Ws); pl->eps_init = ar.take<float>(K);
+  pl->fin_partial = ar.take<double>((size_t)K * pl->fin_chunks * 2); pl->fin_tickets = ar.take<int>(K);
+  pl->crit_partial = ar.take<double>((size_t)pl->crit_blocks * 4); pl->crit4 = ar.take<double>(8);
+  pl->crit_terms = ar.take<float>((size_t)pl->N_total * K * 2); pl->crit_rows = ar.take<double>((size_t)pl->N_total * 2);  // the sweep and the criteria run over all rows, also on a shard's plan
+  if (pl->with_run_buffers) {
+    pl->run_logf = ar.take<double>(N * K); pl->run_Ta = ar.take<float>(N * K); pl->run_Tb = ar.take<float>(N * K);
+  }
 }
+
+static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int64_t D, int64_t row_stride_words,
+                      int32_t K, int32_t free_disp, uint32_t flags, bool with_run_buffers);
 
 extern "C" int nemb200_abi_version(void) { return NEMB200_ABI_VERSION; }
 extern "C" const char* nemb200_last_error(void) { return g_err.c_str(); }
@@ -103,6 +202,11 @@ extern "C" int nemb200_device_count(void) {
 
 extern "C" int nemb200_plan_create(nemb200_plan** out, int64_t N_local, int64_t N_total, int64_t D,
                                    int64_t row_stride_words, int32_t K, int32_t free_disp, uint32_t flags) {
+  return plan_build(out, N_local, N_total, D, row_stride_words, K, free_disp, flags, false);
+}
+
+static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int64_t D, int64_t row_stride_words,
+                      int32_t K, int32_t free_disp, uint32_t flags, bool with_run_buffers) {
   if (!out || N_local < 0 || N_total < 1 || D < 1 || K < 1 || K > NEMB200_MAX_K || row_stride_words % 4 != 0 ||
       row_stride_words * 32 < D || N_total > 0x7fffffffLL)
     return fail(NEMB200_ERR_ARG, "plan_create: bad shape N_local=%lld N_total=%lld D=%lld stride=%lld K=%d",
@@ -112,30 +216,23 @@ extern "C" int nemb200_plan_create(nemb200_plan** out, int64_t N_local, int64_t 
   nemb200_plan* pl = new nemb200_plan();
   pl->N_local = N_local; pl->N_total = N_total; pl->D = (int)D; pl->Ws = (int)row_stride_words;
   pl->Dpad = pl->Ws * 32; pl->K = K; pl->free_disp = free_disp ? 1 : 0; pl->flags = flags;
+  pl->with_run_buffers = with_run_buffers;
   Params& P = pl->P;
   P.K = K; P.D = pl->D; P.Ws = pl->Ws; P.Dpad = pl->Dpad; P.free_disp = pl->free_disp;
-  int rc = 0;
-#define A(ptr, n) if ((rc = dalloc(pl, &(ptr), (size_t)(n))) != 0) { nemb200_plan_destroy(pl); return rc; }
-  A(P.pk, K) A(P.logpk32, K) A(P.logpk64, K)
-  A(P.mu, (size_t)K * pl->D) A(P.eps, (size_t)K * pl->D)
-  A(P.m1, (size_t)K * pl->Ws) A(P.valid, (size_t)K * pl->Ws)
-  A(P.L, pl->free_disp ? (size_t)K * pl->Dpad : (size_t)K) A(P.B, K)
-  A(P.has_half, 1) A(pl->flags2, 2)
-  P.status = (int*)(pl->flags2 + 1);
-  // statistics that a multi-GPU driver all-reduces: one contiguous int32 block and one contiguous fp64 block
-  A(pl->cnt, (size_t)K * pl->Dpad + K) A(pl->fsum, (size_t)K * pl->Dpad + K)
-  pl->nk_cnt = pl->cnt + (size_t)K * pl->Dpad;
-  pl->nk_fz = pl->fsum + (size_t)K * pl->Dpad;
-  A(pl->cnt_local, (size_t)K * pl->Dpad)
-  A(pl->hist, 2 * K + 1) A(pl->offsets, 2 * K + 2) A(pl->cursor, 2 * K + 1)
-  A(pl->prev, N_local) A(pl->ent, N_local) A(pl->perm, 2 * N_local)
-  A(pl->Lword, (size_t)K * pl->Ws) A(pl->eps_init, K) A(P.eps_k, K)
   pl->fin_chunks = (pl->Dpad + kFinCols - 1) / kFinCols;
-  A(pl->fin_partial, (size_t)K * pl->fin_chunks * 2) A(pl->fin_tickets, K)
-  if (cudaMemset(pl->fin_tickets, 0, K * sizeof(int)) != cudaSuccess) { nemb200_plan_destroy(pl); return fail(NEMB200_ERR_CUDA, "plan_create: memset"); }
   pl->crit_blocks = num_sms() * 4;
-  A(pl->crit_partial, (size_t)pl->crit_blocks * 4) A(pl->crit4, 4)
-#undef A
+  Arena count;
+  plan_layout(pl, count);
+  pl->block_bytes = count.off + 256;
+  int rc = cached_malloc(&pl->block, pl->block_bytes);
+  if (rc) { delete pl; return rc; }
+  Arena real;
+  real.base = (char*)pl->block; real.counting = false;
+  plan_layout(pl, real);
+  if (cudaMemset(pl->fin_tickets, 0, K * sizeof(int)) != cudaSuccess) {
+    nemb200_plan_destroy(pl);
+    return fail(NEMB200_ERR_CUDA, "plan_create: memset");
+  }
   *out = pl;
   return NEMB200_OK;
 }
@@ -143,7 +240,7 @@ extern "C" int nemb200_plan_create(nemb200_plan** out, int64_t N_local, int64_t 
 extern "C" void nemb200_plan_destroy(nemb200_plan* pl) {
   if (!pl) return;
   for (auto& pr : pl->onehot_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-  for (void* p : pl->allocs) cudaFree(p);
+  cached_free(pl->block, pl->block_bytes);
   delete pl;
 }
 
@@ -421,19 +518,37 @@ extern "C" int nemb200_criteria(nemb200_plan* pl, int64_t N, const double* logf,
   a.N = N; a.K = pl->K; a.logf = logf; a.pk = pl->P.pk; a.logpk32 = pl->P.logpk32; a.logpk64 = pl->P.logpk64; a.T = T;
   a.rowptr = rowptr; a.col = col; a.w = w; a.beta = beta; a.logspace = (pl->flags & NEMB200_EPI_LOGSPACE) ? 1 : 0;
   a.partial = pl->crit_partial;
+  a.terms = pl->crit_terms; a.rows = pl->crit_rows;
+  if (N > pl->N_total) return fail(NEMB200_ERR_ARG, "criteria: N exceeds the plan's total row count");
   k_criteria<<<pl->crit_blocks, 256, 0, st>>>(a);
   CK(cudaGetLastError());
-  k_crit_reduce<<<1, 32, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4);
-  CK(cudaGetLastError());
   double h[4];
+  if (a.logspace) {
+    k_crit_reduce<<<1, 32, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4);
+    CK(cudaGetLastError());
+  } else {
+    const size_t smem = (size_t)kSeqRows * pl->K * 2 * sizeof(float) + (size_t)kSeqRows * 2 * sizeof(double);
+    k_crit_seq<<<1, 32, smem, st>>>(pl->crit_terms, pl->crit_rows, N, pl->K, pl->crit4);
+    CK(cudaGetLastError());
+  }
   CK(cudaMemcpyAsync(h, pl->crit4, sizeof h, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const double cD = h[0], cG = h[1], cL = h[2], cZ = h[3];
-  crit_out[0] = cD + 0.5 * (double)beta * cG;  // U  (nem_alg.c:2834)
-  crit_out[1] = cD;
-  crit_out[2] = cL;
-  crit_out[3] = cD + (double)beta * cG + cZ;    // M  (nem_alg.c:2835)
-  crit_out[4] = cZ;
+  if (a.logspace) {
+    const double cD = h[0], cG = h[1], cL = h[2], cZ = h[3];
+    crit_out[0] = cD + 0.5 * (double)beta * cG;  // U  (nem_alg.c:2834)
+    crit_out[1] = cD;
+    crit_out[2] = cL;
+    crit_out[3] = cD + (double)beta * cG + cZ;    // M  (nem_alg.c:2835)
+    crit_out[4] = cZ;
+  } else {
+    // float32 fields combined with the reference's expression types (nem_alg.c:2834-2835)
+    const float cD = (float)h[0], cG = (float)h[1], cL = (float)h[2], cZ = (float)h[3];
+    const float cU = (float)((double)cD + 0.5 * (double)beta * (double)cG);
+    volatile float t1 = beta * cG;
+    volatile float t2 = cD + t1;
+    const float cM = t2 + cZ;
+    crit_out[0] = cU; crit_out[1] = cD; crit_out[2] = cL; crit_out[3] = cM; crit_out[4] = cZ;
+  }
   return NEMB200_OK;
 }
 
@@ -510,13 +625,11 @@ extern "C" int nemb200_gs_schedule(int64_t N, const int32_t* rowptr, const int32
 // ------------------------------------------------------------------------------------------------------------------
 // whole-run drivers
 // ------------------------------------------------------------------------------------------------------------------
-struct RunBuffers {
+struct RunBuffers {   // views into the plan's block (plan_build(..., with_run_buffers = true))
   double* logf = nullptr;
   float* Ta = nullptr;
   float* Tb = nullptr;
   uint32_t* flags = nullptr;  // [0] maxdiff bits
-  std::vector<void*> owned;
-  ~RunBuffers() { for (void* p : owned) cudaFree(p); }
 };
 
 // One EM run as a small state machine, so that a single instance and a batch of independent instances (K sweep,
@@ -546,16 +659,9 @@ struct EmRun {
   int begin() {  // nem_alg.c:2023-2065 with Needinit = 1
     const long long N = pl->N_local;
     const int K = pl->K;
-    auto alloc = [&](void** p, size_t bytes) -> int {
-      CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
-      rb.owned.push_back(*p);
-      return 0;
-    };
     int rc;
-    if ((rc = alloc((void**)&rb.logf, (size_t)N * K * sizeof(double)))) return rc;
-    if ((rc = alloc((void**)&rb.Ta, (size_t)N * K * sizeof(float)))) return rc;
-    if ((rc = alloc((void**)&rb.Tb, (size_t)N * K * sizeof(float)))) return rc;
-    if ((rc = alloc((void**)&rb.flags, 4 * sizeof(uint32_t)))) return rc;
+    if (!pl->with_run_buffers) return fail(NEMB200_ERR_ARG, "EmRun: plan built without run buffers");
+    rb.logf = pl->run_logf; rb.Ta = pl->run_Ta; rb.Tb = pl->run_Tb; rb.flags = pl->flags2;
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(cudaEventRecord(ev0, st));
@@ -649,7 +755,7 @@ extern "C" int nemb200_nem_device(const uint32_t* bits, int64_t N, int64_t D, in
   if (!bits || N < 1) return fail(NEMB200_ERR_ARG, "nem_device: null matrix");
   if (beta != 0.0f && (!rowptr || !col || !w)) return fail(NEMB200_ERR_ARG, "nem_device: beta != 0 needs the neighbour graph");
   nemb200_plan* pl = nullptr;
-  int rc = nemb200_plan_create(&pl, N, N, D, row_stride_words, K, free_disp, flags);
+  int rc = plan_build(&pl, N, N, D, row_stride_words, K, free_disp, flags, true);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
   rc = run_em(pl, bits, rowptr, col, w, sched_level_ptr, sched_rows, n_levels, beta, itermax, cv_th, T_out, result, st);
@@ -683,7 +789,7 @@ extern "C" int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* b
     if (!bits[i] || N[i] < 1) { rc = fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d has no matrix", i); break; }
     if (graph && (!rowptr || !col || !w || !rowptr[i] || !col[i] || !w[i])) { rc = fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d needs its neighbour graph", i); break; }
     if (cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking) != cudaSuccess) { rc = fail(NEMB200_ERR_CUDA, "nem_device_batch: stream"); break; }
-    rc = nemb200_plan_create(&plans[i], N[i], N[i], D[i], row_stride_words[i], K[i], free_disp[i], flags);
+    rc = plan_build(&plans[i], N[i], N[i], D[i], row_stride_words[i], K[i], free_disp[i], flags, true);
     if (rc) break;
     EmRun& r = runs[i];
     r.pl = plans[i]; r.bits = bits[i];
@@ -722,10 +828,14 @@ extern "C" int nemb200_nem_host(const uint32_t* bits, int64_t N, int64_t D, int6
   cudaStream_t st = nullptr;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   struct Guard {
-    std::vector<void*> p; cudaStream_t s;
-    ~Guard() { for (void* q : p) cudaFree(q); cudaStreamDestroy(s); }
+    std::vector<std::pair<void*, size_t>> p; cudaStream_t s;
+    ~Guard() { cudaStreamSynchronize(s); for (auto& q : p) cached_free(q.first, q.second); cudaStreamDestroy(s); }
   } g{{}, st};
-  auto dmal = [&](void** p, size_t bytes) -> int { CK(cudaMalloc(p, std::max<size_t>(bytes, 16))); g.p.push_back(*p); return 0; };
+  auto dmal = [&](void** p, size_t bytes) -> int {
+    int r = cached_malloc(p, bytes);
+    if (r == 0) g.p.emplace_back(*p, bytes);
+    return r;
+  };
   uint32_t* d_bits = nullptr; int32_t *d_rowptr = nullptr, *d_col = nullptr, *d_lp = nullptr, *d_lr = nullptr; float* d_w = nullptr;
   float* d_T = nullptr;
   int rc;
@@ -752,7 +862,7 @@ extern "C" int nemb200_nem_host(const uint32_t* bits, int64_t N, int64_t D, int6
   }
   if ((rc = dmal((void**)&d_T, (size_t)N * K * sizeof(float)))) return rc;
   nemb200_plan* pl = nullptr;
-  rc = nemb200_plan_create(&pl, N, N, D, row_stride_words, K, free_disp, flags);
+  rc = plan_build(&pl, N, N, D, row_stride_words, K, free_disp, flags, true);
   if (rc) return rc;
   rc = run_em(pl, d_bits, d_rowptr, d_col, d_w, d_lp, d_lr, n_levels, beta, itermax, cv_th, d_T, result, st);
   if (rc == 0 && T_out) {

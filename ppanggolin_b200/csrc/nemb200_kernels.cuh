@@ -840,6 +840,8 @@ struct CritArgs {
   float beta;
   int logspace;
   double* partial;  // [gridDim.x][4]  D, G, L, Z
+  float* terms;     // reference arithmetic: [N][K][2] per-(row, class) D and G terms ...
+  double* rows;     // ... and [N][2] per-row log f_i, log z_i, accumulated in the reference's order by k_crit_seq
 };
 
 __global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
@@ -907,6 +909,13 @@ __global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
       rowZ = -log(zi);
     }
     accD += rowD; accG += rowG; accL += rowL; accZ += rowZ;
+    if (!a.logspace) {
+      if (lane < K) {
+        a.terms[((size_t)i * K + lane) * 2 + 0] = (float)dik;   // dik / gik already hold float32 values
+        a.terms[((size_t)i * K + lane) * 2 + 1] = (float)gik;
+      }
+      if (lane == 0) { a.rows[(size_t)i * 2 + 0] = rowL; a.rows[(size_t)i * 2 + 1] = -rowZ; }
+    }
   }
   if (lane == 0) { s_part[wid][0] = accD; s_part[wid][1] = accG; s_part[wid][2] = accL; s_part[wid][3] = accZ; }
   __syncthreads();
@@ -915,6 +924,35 @@ __global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
     for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += s_part[q][threadIdx.x];
     a.partial[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
   }
+}
+
+// The reference accumulates D, G, L and Z in float32, sequentially over rows then classes (nem_alg.c:2788-2828).  At
+// N = 20 000 that rounding alone moves M by 2e-5 relative (measured with the oracle), more than the parity bar, so the
+// four sums are re-accumulated in exactly that order: one warp, one lane per chain, tiles staged in shared memory.
+constexpr int kSeqRows = 128;
+__global__ void __launch_bounds__(32)
+k_crit_seq(const float* __restrict__ terms, const double* __restrict__ rows, long long N, int K, double* __restrict__ out4) {
+  extern __shared__ float s_seq[];                       // [kSeqRows*K*2] floats, then [kSeqRows*2] doubles
+  double* s_rows = reinterpret_cast<double*>(s_seq + (size_t)kSeqRows * K * 2);
+  const int lane = threadIdx.x;
+  float acc = 0.0f;                                      // lane 0: D, 1: G, 2: L, 3: Z
+  for (long long r0 = 0; r0 < N; r0 += kSeqRows) {
+    const int nr = (int)min((long long)kSeqRows, N - r0);
+    __syncwarp();
+    for (int t = lane; t < nr * K * 2; t += 32) s_seq[t] = terms[(size_t)r0 * K * 2 + t];
+    for (int t = lane; t < nr * 2; t += 32) s_rows[t] = rows[(size_t)r0 * 2 + t];
+    __syncwarp();
+    if (lane < 2) {
+      const int n = nr * K;
+#pragma unroll 8
+      for (int t = 0; t < n; t++) acc = __fadd_rn(acc, s_seq[2 * t + lane]);
+    } else if (lane == 2) {
+      for (int r = 0; r < nr; r++) acc = (float)((double)acc + s_rows[2 * r]);        // L = L + log(fi)
+    } else if (lane == 3) {
+      for (int r = 0; r < nr; r++) acc = (float)((double)acc - s_rows[2 * r + 1]);    // Z = Z - log(zi)
+    }
+  }
+  if (lane < 4) out4[lane] = (double)acc;
 }
 
 __global__ void k_crit_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ out4) {

@@ -44,6 +44,7 @@ SIGNATURES = {
     "nemb200_abi_version": (ctypes.c_int, []),
     "nemb200_last_error": (ctypes.c_char_p, []),
     "nemb200_device_count": (ctypes.c_int, []),
+    "nemb200_release_cached_memory": (ctypes.c_int, []),
     "nemb200_nem_host": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _f32, _u32,
                                         _vp, _vp, _vp, _vp, ctypes.POINTER(_Result)]),
     "nemb200_nem_device": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _i32,
