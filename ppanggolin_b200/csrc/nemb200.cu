@@ -283,7 +283,12 @@ static int launch_classify(nemb200_plan* pl, const float* T, cudaStream_t st) {
 }
 template <int KB>
 static int launch_fuzzy(nemb200_plan* pl, const uint32_t* bits, const float* T, cudaStream_t st) {
-  dim3 grid((pl->Dpad + 255) / 256, 64);
+  const int col_tiles = (pl->Dpad + 255) / 256;
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mstep_fuzzy<KB>, 256, 0));
+  const long long slots = (long long)num_sms() * std::max(per_sm, 1);
+  const long long slices = std::min<long long>(std::max<long long>(slots / col_tiles, 1), 65535);  // one resident wave
+  dim3 grid(col_tiles, (unsigned)slices);
   k_mstep_fuzzy<KB><<<grid, 256, 0, st>>>(bits, pl->Ws, pl->K, pl->D, pl->offsets, pl->perm, T, pl->fsum, pl->Dpad);
   CK(cudaGetLastError());
   return 0;
@@ -510,10 +515,8 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
   return NEMB200_OK;
 }
 
-extern "C" int nemb200_criteria(nemb200_plan* pl, int64_t N, const double* logf, const float* T, const int32_t* rowptr,
-                                const int32_t* col, const float* w, float beta, double crit_out[5], void* stream_) {
-  if (!pl || !logf || !T || !crit_out) return fail(NEMB200_ERR_ARG, "criteria: null argument");
-  cudaStream_t st = (cudaStream_t)stream_;
+static int criteria_enqueue(nemb200_plan* pl, int64_t N, const double* logf, const float* T, const int32_t* rowptr,
+                            const int32_t* col, const float* w, float beta, cudaStream_t st) {
   CritArgs a;
   a.N = N; a.K = pl->K; a.logf = logf; a.pk = pl->P.pk; a.logpk32 = pl->P.logpk32; a.logpk64 = pl->P.logpk64; a.T = T;
   a.rowptr = rowptr; a.col = col; a.w = w; a.beta = beta; a.logspace = (pl->flags & NEMB200_EPI_LOGSPACE) ? 1 : 0;
@@ -522,18 +525,22 @@ extern "C" int nemb200_criteria(nemb200_plan* pl, int64_t N, const double* logf,
   if (N > pl->N_total) return fail(NEMB200_ERR_ARG, "criteria: N exceeds the plan's total row count");
   k_criteria<<<pl->crit_blocks, 256, 0, st>>>(a);
   CK(cudaGetLastError());
-  double h[4];
   if (a.logspace) {
     k_crit_reduce<<<1, 32, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4);
     CK(cudaGetLastError());
   } else {
     const size_t smem = (size_t)kSeqRows * pl->K * 2 * sizeof(float) + (size_t)kSeqRows * 2 * sizeof(double);
-    k_crit_seq<<<1, 32, smem, st>>>(pl->crit_terms, pl->crit_rows, N, pl->K, pl->crit4);
+    k_crit_seq<<<1, kSeqTpb, smem, st>>>(pl->crit_terms, pl->crit_rows, N, pl->K, pl->crit4);
     CK(cudaGetLastError());
   }
+  return 0;
+}
+
+static int criteria_collect(nemb200_plan* pl, float beta, double crit_out[5], cudaStream_t st) {
+  double h[4];
   CK(cudaMemcpyAsync(h, pl->crit4, sizeof h, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (a.logspace) {
+  if (pl->flags & NEMB200_EPI_LOGSPACE) {
     const double cD = h[0], cG = h[1], cL = h[2], cZ = h[3];
     crit_out[0] = cD + 0.5 * (double)beta * cG;  // U  (nem_alg.c:2834)
     crit_out[1] = cD;
@@ -550,6 +557,15 @@ extern "C" int nemb200_criteria(nemb200_plan* pl, int64_t N, const double* logf,
     crit_out[0] = cU; crit_out[1] = cD; crit_out[2] = cL; crit_out[3] = cM; crit_out[4] = cZ;
   }
   return NEMB200_OK;
+}
+
+extern "C" int nemb200_criteria(nemb200_plan* pl, int64_t N, const double* logf, const float* T, const int32_t* rowptr,
+                                const int32_t* col, const float* w, float beta, double crit_out[5], void* stream_) {
+  if (!pl || !logf || !T || !crit_out) return fail(NEMB200_ERR_ARG, "criteria: null argument");
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rc = criteria_enqueue(pl, N, logf, T, rowptr, col, w, beta, st);
+  if (rc) return rc;
+  return criteria_collect(pl, beta, crit_out, st);
 }
 
 extern "C" int nemb200_get_params(nemb200_plan* pl, float* mu, float* eps, float* pk, int32_t* status, void* stream_) {
@@ -699,10 +715,14 @@ struct EmRun {
     if (converged || iter >= itermax) active = false;
     return 0;
   }
-  int finish(float* T_out, nemb200_result* res) {  // nem_alg.c:1906
+  int finish_enqueue() {  // nem_alg.c:1906, asynchronous part
+    if (status == NEMB200_STS_OK) return criteria_enqueue(pl, pl->N_local, rb.logf, cur, rowptr, col, w, beta, st);
+    return 0;
+  }
+  int finish(float* T_out, nemb200_result* res) {
     int rc;
     if (status == NEMB200_STS_OK) {
-      if ((rc = nemb200_criteria(pl, pl->N_local, rb.logf, cur, rowptr, col, w, beta, crit, st))) return rc;
+      if ((rc = criteria_collect(pl, beta, crit, st))) return rc;
       if (std::isinf(crit[0]) && crit[0] < 0) status = NEMB200_STS_INFINITE;  // nem_alg.c:2482-2487
     }
     CK(cudaEventRecord(ev1, st));
@@ -730,6 +750,7 @@ static int run_em(nemb200_plan* pl, const uint32_t* bits, const int32_t* rowptr,
     if ((rc = r.enqueue_iteration())) return rc;
     if ((rc = r.poll())) return rc;
   }
+  if ((rc = r.finish_enqueue())) return rc;
   return r.finish(T_out, res);
 }
 
@@ -809,6 +830,7 @@ extern "C" int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* b
     for (int i = 0; i < n_inst && rc == 0; i++)
       if (runs[i].active) { rc = runs[i].poll(); any = any || runs[i].active; }
   }
+  for (int i = 0; i < n_inst && rc == 0; i++) rc = runs[i].finish_enqueue();   // all criteria kernels in flight together
   for (int i = 0; i < n_inst && rc == 0; i++) {
     rc = runs[i].finish(T_out ? T_out[i] : nullptr, &results[i]);
     if (rc == 0) rc = copy_params_out(plans[i], mu_out ? mu_out[i] : nullptr, eps_out ? eps_out[i] : nullptr,

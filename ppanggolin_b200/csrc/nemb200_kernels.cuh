@@ -405,12 +405,14 @@ k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ pr
   for (int t = threadIdx.x; t < KB; t += blockDim.x) { s_fz[t] = 0.0; s_nk[t] = 0; }
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float t[KB];
+#pragma unroll
+  for (int k = 0; k < KB; k++) t[k] = 0.0f;
+  bool fuzzy = false;
   if (i < N) {
-    float t[KB];
     int ones = 0, zeros = 0, arg = 0;
 #pragma unroll
     for (int k = 0; k < KB; k++) {
-      t[k] = 0.0f;
       if (k < K) {
         t[k] = T[(size_t)i * K + k];
         if (t[k] == 1.0f) { ones++; arg = k; }
@@ -419,12 +421,7 @@ k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ pr
     }
     int key;
     if (ones == 1 && zeros == K - 1) { key = arg; atomicAdd(&s_nk[key], 1); }
-    else {
-      key = K;
-#pragma unroll
-      for (int k = 0; k < KB; k++)
-        if (k < K && t[k] != 0.0f) atomicAdd(&s_fz[k], (double)t[k]);
-    }
+    else { key = K; fuzzy = true; }
     const int old = prev[i];
     int e0 = -1, e1 = -1;
     if (key == K) e1 = 2 * K;                   // fuzzy: always recomputed
@@ -437,12 +434,24 @@ k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ pr
     if (e0 >= 0) atomicAdd(&s_hist[e0], 1);
     if (e1 >= 0) atomicAdd(&s_hist[e1], 1);
   }
+  // class sizes of the fuzzy rows: warp reduction first (in the K sweep nearly every row is fuzzy and per-thread
+  // shared-memory fp64 atomics serialise), one shared atomic per warp and class
+  if (__any_sync(0xffffffffu, fuzzy)) {
+#pragma unroll
+    for (int k = 0; k < KB; k++) {
+      if (k < K) {
+        double v = fuzzy ? (double)t[k] : 0.0;
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&s_fz[k], v);
+      }
+    }
+  }
   __syncthreads();
-  for (int t = threadIdx.x; t < 2 * K + 1; t += blockDim.x)
-    if (s_hist[t]) atomicAdd(&hist[t], s_hist[t]);
-  for (int t = threadIdx.x; t < K; t += blockDim.x) {
-    if (s_nk[t]) atomicAdd(&nk_cnt[t], s_nk[t]);
-    if (s_fz[t] != 0.0) atomicAdd(&nk_fz[t], s_fz[t]);
+  for (int t2 = threadIdx.x; t2 < 2 * K + 1; t2 += blockDim.x)
+    if (s_hist[t2]) atomicAdd(&hist[t2], s_hist[t2]);
+  for (int t2 = threadIdx.x; t2 < K; t2 += blockDim.x) {
+    if (s_nk[t2]) atomicAdd(&nk_cnt[t2], s_nk[t2]);
+    if (s_fz[t2] != 0.0) atomicAdd(&nk_fz[t2], s_fz[t2]);
   }
 }
 
@@ -616,9 +625,11 @@ k_mstep_onehot(const uint2* __restrict__ bits2, int W2, int tile_w, int K, const
   }
 }
 
-// Fuzzy rows: one thread per genome column, fp64 accumulators per class; blockIdx.y owns an equal share of the fuzzy
-// list.  The share's row ids and posteriors are staged in shared memory first, so the matrix loads of consecutive rows
-// are independent (unrolled) instead of a chain of dependent loads per row.
+// Fuzzy rows: fsum[k][d] += T[i][k] for every set bit (i, d) of a fuzzy row.  One thread per genome column with fp64
+// accumulators per class; blockIdx.y owns an equal share of the fuzzy list (the host sizes the grid to the resident CTA
+// slots: in the K-selection sweep at K = 20 nearly every row is fuzzy and this kernel is the M-step).  The share's row
+// ids and posteriors (converted to fp64 once) are staged in shared memory, so the matrix loads of consecutive rows are
+// independent; a warp's 32 lanes look at the same matrix word, so all-zero words are skipped with a uniform branch.
 constexpr int kFzRows = 64;
 
 template <int KB>
@@ -626,37 +637,47 @@ __global__ void __launch_bounds__(256)
 k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int* __restrict__ offsets,
               const int* __restrict__ perm, const float* __restrict__ T, double* __restrict__ fsum /*[K][Dpad]*/,
               int Dpad) {
+  constexpr int KP = (KB + 1) & ~1;   // even: the staged posteriors are read as double2
   __shared__ int s_row[kFzRows];
-  __shared__ float s_t[kFzRows][KB];
+  __shared__ __align__(16) double s_t[kFzRows][KP];
   const int f0 = offsets[2 * K], f1 = offsets[2 * K + 1];   // the fuzzy bucket
   const int nf = f1 - f0;
-  const long long S = gridDim.y;
+  const long long S = min((long long)gridDim.y, max(1LL, ((long long)nf + kFzRows - 1) / kFzRows));
+  if (blockIdx.y >= S) return;
   const int lo = f0 + (int)((long long)nf * blockIdx.y / S), hi = f0 + (int)((long long)nf * (blockIdx.y + 1) / S);
   if (lo >= hi) return;
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   const int word = d >> 5, bit = d & 31;
   const bool in_range = word < Ws;
+  const uint32_t* colp = bits + (in_range ? word : 0);
   double acc[KB];
 #pragma unroll
   for (int k = 0; k < KB; k++) acc[k] = 0.0;
   for (int base = lo; base < hi; base += kFzRows) {
     const int n = min(kFzRows, hi - base);
     __syncthreads();
-    for (int t = threadIdx.x; t < n * K; t += blockDim.x) {
-      const int r = t / K, k = t - r * K;
+    for (int t = threadIdx.x; t < n * KP; t += blockDim.x) {
+      const int r = t / KP, k = t - r * KP;
       const int row = perm[base + r];
       if (k == 0) s_row[r] = row;
-      s_t[r][k] = T[(size_t)row * K + k];
+      s_t[r][k] = k < K ? (double)T[(size_t)row * K + k] : 0.0;
     }
     __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
     for (int r = 0; r < n; r++) {
-      uint32_t x = 0;
-      if (in_range) x = __ldg(bits + (size_t)s_row[r] * Ws + word);
-      if ((x >> bit) & 1u) {
+      const uint32_t x = in_range ? __ldg(colp + (size_t)s_row[r] * Ws) : 0u;
+      if (x != 0u) {                       // warp-uniform: the 32 lanes of a warp share the word
+        if ((x >> bit) & 1u) {
+          const double2* tr = reinterpret_cast<const double2*>(&s_t[r][0]);
 #pragma unroll
-        for (int k = 0; k < KB; k++)
-          if (k < K) acc[k] += (double)s_t[r][k];
+          for (int k2 = 0; k2 < KP / 2; k2++) {
+            if (2 * k2 < K) {
+              const double2 v = tr[k2];
+              acc[2 * k2] += v.x;
+              if (2 * k2 + 1 < KB) acc[2 * k2 + 1] += v.y;
+            }
+          }
+        }
       }
     }
   }
@@ -928,31 +949,67 @@ __global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
 
 // The reference accumulates D, G, L and Z in float32, sequentially over rows then classes (nem_alg.c:2788-2828).  At
 // N = 20 000 that rounding alone moves M by 2e-5 relative (measured with the oracle), more than the parity bar, so the
-// four sums are re-accumulated in exactly that order: one warp, one lane per chain, tiles staged in shared memory.
+// four sums are re-accumulated in exactly that order.  Adding 0.0f is the identity, and most (row, class) terms are
+// exactly zero (one-hot posteriors), so each tile is first compacted in order by the whole CTA (ballot + prefix), then
+// four threads in four different warps run the four dependent chains concurrently.
 constexpr int kSeqRows = 128;
-__global__ void __launch_bounds__(32)
+constexpr int kSeqTpb = 256;
+__global__ void __launch_bounds__(kSeqTpb)
 k_crit_seq(const float* __restrict__ terms, const double* __restrict__ rows, long long N, int K, double* __restrict__ out4) {
-  extern __shared__ float s_seq[];                       // [kSeqRows*K*2] floats, then [kSeqRows*2] doubles
+  extern __shared__ float s_seq[];                       // sD[kSeqRows*K], sG[kSeqRows*K], then [kSeqRows*2] doubles
+  float* sD = s_seq;
+  float* sG = s_seq + (size_t)kSeqRows * K;
   double* s_rows = reinterpret_cast<double*>(s_seq + (size_t)kSeqRows * K * 2);
-  const int lane = threadIdx.x;
-  float acc = 0.0f;                                      // lane 0: D, 1: G, 2: L, 3: Z
+  __shared__ int s_wcnt[kSeqTpb / 32];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float2* terms2 = reinterpret_cast<const float2*>(terms);
+  float acc = 0.0f;                                      // thread 0: D, 32: G, 64: L, 96: Z
   for (long long r0 = 0; r0 < N; r0 += kSeqRows) {
     const int nr = (int)min((long long)kSeqRows, N - r0);
-    __syncwarp();
-    for (int t = lane; t < nr * K * 2; t += 32) s_seq[t] = terms[(size_t)r0 * K * 2 + t];
-    for (int t = lane; t < nr * 2; t += 32) s_rows[t] = rows[(size_t)r0 * 2 + t];
-    __syncwarp();
-    if (lane < 2) {
-      const int n = nr * K;
-#pragma unroll 8
-      for (int t = 0; t < n; t++) acc = __fadd_rn(acc, s_seq[2 * t + lane]);
-    } else if (lane == 2) {
+    const int n = nr * K;
+    __syncthreads();
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += kSeqTpb) {           // ordered compaction of the non-zero (D, G) terms
+      const int t = c0 + tid;
+      float2 v = make_float2(0.0f, 0.0f);
+      if (t < n) v = terms2[(size_t)r0 * K + t];
+      const bool nz = (v.x != 0.0f) || (v.y != 0.0f);
+      const unsigned m = __ballot_sync(0xffffffffu, nz);
+      if (lane == 0) s_wcnt[wid] = __popc(m);
+      __syncthreads();
+      int off = s_total;
+      for (int q = 0; q < wid; q++) off += s_wcnt[q];
+      if (nz) { const int pos = off + __popc(m & ((1u << lane) - 1u)); sD[pos] = v.x; sG[pos] = v.y; }
+      __syncthreads();
+      if (tid == 0) { int tot = s_total; for (int q = 0; q < kSeqTpb / 32; q++) tot += s_wcnt[q]; s_total = tot; }
+      __syncthreads();
+    }
+    for (int t = tid; t < nr * 2; t += kSeqTpb) s_rows[t] = rows[(size_t)r0 * 2 + t];
+    __syncthreads();
+    const int cnt = s_total;
+    if (tid == 0 || tid == 32) {
+      const float* src = tid == 0 ? sD : sG;
+      int t = 0;
+      for (; t + 8 <= cnt; t += 8) {                     // loads first (independent), then the dependent chain of adds
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = src[t + q];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc = __fadd_rn(acc, v[q]);
+      }
+      for (; t < cnt; t++) acc = __fadd_rn(acc, src[t]);
+    } else if (tid == 64) {
       for (int r = 0; r < nr; r++) acc = (float)((double)acc + s_rows[2 * r]);        // L = L + log(fi)
-    } else if (lane == 3) {
+    } else if (tid == 96) {
       for (int r = 0; r < nr; r++) acc = (float)((double)acc - s_rows[2 * r + 1]);    // Z = Z - log(zi)
     }
   }
-  if (lane < 4) out4[lane] = (double)acc;
+  if (tid == 0) out4[0] = (double)acc;
+  if (tid == 32) out4[1] = (double)acc;
+  if (tid == 64) out4[2] = (double)acc;
+  if (tid == 96) out4[3] = (double)acc;
 }
 
 __global__ void k_crit_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ out4) {

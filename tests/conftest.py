@@ -10,6 +10,9 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the native pieces are built in-tree (git-ignored); rebuild when missing or older than their sources
+    import __graft_entry__ as entry
+    entry.build()
 
 
 @pytest.fixture(autouse=True)

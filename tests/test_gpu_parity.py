@@ -267,3 +267,70 @@ def test_k_sweep_matches_reference_goldens(eng):
     assert k_ours == k_ref
     for k in ks:
         assert abs(icl_o[k] - icl_r[k]) <= REL_M * abs(icl_r[k])
+
+
+def _popcount_rows(bits):
+    """Row popcounts of an int32 bit matrix on the GPU (byte lookup table)."""
+    import torch
+    table = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int32, device=bits.device)
+    out = torch.zeros(bits.shape[0], dtype=torch.int64, device=bits.device)
+    step = 8192
+    for r0 in range(0, bits.shape[0], step):
+        b = bits[r0:r0 + step].contiguous().view(torch.uint8).to(torch.int64)
+        out[r0:r0 + step] = table[b].sum(1)
+    return out
+
+
+def test_full_size_properties(eng):
+    """BASELINE.json configs[4] at full size (200 000 families x 50 000 genomes): no oracle finishes this shape, so the
+    kernels are checked through size-independent identities of the domain.
+
+    * density: hamming(x, mu) = popcount(x) for a zero centre and D - popcount(x) for an all-ones centre, so with the
+      initial parameters log f_ik is a closed form of the row popcount (integer-exact popcounts);
+    * M-step: sum_d cnt[k][d] = sum of the popcounts of the one-hot rows of class k (a checksum of checksums), and the
+      class sizes add up to N;
+    * incremental M-step == full recount after further iterations (bit-exact posteriors);
+    * the partition recovers the generator's classes."""
+    import torch
+    from ppanggolin_b200.nem.sharded import CudaBackend, ShardedEM
+    from ppanggolin_b200.synthetic import synth_pangenome_large
+    N, D, K = 200_000, 50_000, 3
+    sp = synth_pangenome_large(N, D, seed=5, device="cuda")
+    pop = _popcount_rows(sp.bits)
+    assert int(pop.min()) >= 1 and int(pop.max()) <= D
+    graph = eng.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), D, sp.rowptr, sp.col, sp.w)
+    beta = float(np.float32(sp.beta_eff(2.5)))
+    outs = []
+    for flags in (eng.EPI_LOGSPACE | eng.FULL_RECOUNT, eng.EPI_LOGSPACE):
+        be = CudaBackend(sp.bits, D, N, K, False, flags, graph)
+        em = ShardedEM(be, N, K)
+        be.init_params()
+        # --- density identity with the initial parameters: class 0 has mu = 1, eps = .25; classes 1, 2 mu = 0, eps = .5 / .25
+        be.density(be.logf_full)
+        pk0, mu0, eps0 = npref.init_params(K, 8)
+        e = eps0[:, 0].astype(np.float32)
+        L = np.log(((np.float32(1) - e) / e).astype(np.float64)); l1 = np.log((np.float32(1) - e).astype(np.float64))
+        popd = pop.to(torch.float64)
+        want = torch.stack([D * l1[0] - (D - popd) * L[0], D * l1[1] - popd * L[1], D * l1[2] - popd * L[2]], 1)
+        assert torch.allclose(be.logf_full, want, rtol=1e-13, atol=1e-7)
+        # --- EM
+        em.start(beta)
+        for _ in range(4):
+            md, status = em.iterate(beta)
+            assert status == 0
+        T = be.T[em.cur]
+        # --- M-step checksum on the current posteriors
+        be.accumulate(T)
+        cnt, fsum, nkc, nkf = be.plan.stats_tensors()
+        onehot = ((T == 1.0).sum(1) == 1) & ((T == 0.0).sum(1) == K - 1)
+        cls = T.argmax(1)
+        for k in range(K):
+            sel = onehot & (cls == k)
+            assert int(cnt[k].sum()) == int(pop[sel].sum())
+            assert int(nkc[k]) == int(sel.sum())
+        assert float(nkc.sum() + nkf.sum()) == pytest.approx(N, rel=1e-9)
+        outs.append(T.clone())
+        lab, _ = eng.labels_device(T)
+        assert float((lab.cpu() == torch.from_numpy(sp.true_class.astype(np.int32))).float().mean()) > 0.98
+        be.plan.close()
+    assert torch.equal(outs[0], outs[1])
