@@ -182,6 +182,22 @@ class DeviceInput:
         return int(self.bits.shape[0])
 
     @staticmethod
+    def from_tensor(bits_t, D: int, rowptr=None, col=None, w=None) -> "DeviceInput":
+        """Matrix already resident on the device (export_arrays.PangenomeArrays.instance); CSR as numpy arrays."""
+        torch = _require_cuda()
+        di = DeviceInput(bits_t.contiguous(), D)
+        if rowptr is not None and len(col) > 0:
+            dev = bits_t.device
+            lp, rows, nl = gs_schedule(rowptr, col)
+            di.rowptr = torch.from_numpy(np.ascontiguousarray(rowptr, np.int32)).to(dev)
+            di.col = torch.from_numpy(np.ascontiguousarray(col, np.int32)).to(dev)
+            di.w = torch.from_numpy(np.ascontiguousarray(w, np.float32)).to(dev)
+            di.sched_ptr = torch.from_numpy(lp).to(dev)
+            di.sched_rows = torch.from_numpy(rows).to(dev)
+            di.n_levels = nl
+        return di
+
+    @staticmethod
     def from_numpy(bits: np.ndarray, D: int, rowptr=None, col=None, w=None, device="cuda") -> "DeviceInput":
         torch = _require_cuda()
         b = torch.from_numpy(np.ascontiguousarray(bits).view(np.int32)).to(device)

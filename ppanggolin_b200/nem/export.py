@@ -30,10 +30,17 @@ class NemInput:
     edges_weight: float              # total_edges_weight / 2
     nei_text: Optional[list] = None  # per-row (indices, weight strings) as written to .nei, kept for keep_tmp_files
     device: Optional[object] = None  # engine.DeviceInput once uploaded
+    bits_tensor: Optional[object] = None  # (N, Ws) int32 torch tensor when the instance was derived on the device
+    fam_rows: Optional[object] = None     # torch int64 (N,): global family index of each row (array exporter only)
 
     @property
     def N(self) -> int:
-        return int(self.bits.shape[0])
+        return len(self.fam_names)
+
+    def host_bits(self) -> np.ndarray:
+        if self.bits is None:
+            self.bits = self.bits_tensor.cpu().numpy().view(np.uint32)
+        return self.bits
 
 
 _REGISTRY: Dict[str, NemInput] = {}
@@ -131,7 +138,7 @@ def write_text_files(tmpdir: Path, inp: NemInput) -> None:
     from ..synthetic import unpack_rows
     tmpdir = Path(tmpdir)
     tmpdir.mkdir(parents=True, exist_ok=True)
-    X = unpack_rows(inp.bits, inp.D)
+    X = unpack_rows(inp.host_bits(), inp.D)
     with open(tmpdir / "column_org_file", "w") as f:
         f.write(" ".join(f'"{n}"' for n in inp.org_names) + "\n")
     with open(tmpdir / "nem_file.str", "w") as f:

@@ -73,6 +73,12 @@ def _epilogue_flags(nb_org: int) -> int:
     return engine.EPI_REF if nb_org <= REF_EPILOGUE_MAX_ORGS else engine.EPI_LOGSPACE
 
 
+def _device_input(inp):
+    if inp.bits_tensor is not None and inp.bits_tensor.is_cuda:
+        return engine.DeviceInput.from_tensor(inp.bits_tensor, inp.D, inp.rowptr, inp.col, inp.w)
+    return engine.DeviceInput.from_numpy(inp.host_bits(), inp.D, inp.rowptr, inp.col, inp.w)
+
+
 def _g(x: float, spec: str) -> float:
     """Value after the C printf/parse round trip the reference performs through the .mf file."""
     return float(spec % x)
@@ -103,7 +109,7 @@ def run_partitioning(
     if inp is None:
         raise FileNotFoundError(f"no exported NEM instance registered for {nem_dir_path}: call write_nem_input_files first")
     if inp.device is None:
-        inp.device = engine.DeviceInput.from_numpy(inp.bits, inp.D, inp.rowptr, inp.col, inp.w)
+        inp.device = _device_input(inp)
     run = engine.nem_run_device(inp.device, kval, beta, free_dispersion, itermax=itermax, cv_th=0.01,
                                 flags=_epilogue_flags(nb_org))
     if not run.ok:
@@ -176,10 +182,41 @@ def nem_samples(pack: tuple):
     return partition_nem(*pack)
 
 
+_ARRAYS = {"pan": None, "arrays": None}
+
+
+def _arrays_for(pangenome):
+    """Array form of ``pangenome`` (export_arrays.PangenomeArrays), built once per partition() call; None when the
+    fast exporter is switched off (PPANGGOLIN_B200_FAST_EXPORT=0) or no CUDA device is present."""
+    if os.environ.get("PPANGGOLIN_B200_FAST_EXPORT", "1") == "0":
+        return None
+    if _ARRAYS["pan"] is pangenome:
+        return _ARRAYS["arrays"]
+    return None
+
+
+def prepare_arrays(pangenome, device=None):
+    """Read the pangenome objects once into tensors; every later write_nem_input_files(...) for this pangenome derives
+    its instance from them.  Called by partition(); callers that drive write_nem_input_files themselves (rarefaction)
+    may call it too."""
+    if os.environ.get("PPANGGOLIN_B200_FAST_EXPORT", "1") == "0":
+        return None
+    from .export_arrays import PangenomeArrays
+    if device is None:
+        import torch
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    _ARRAYS["pan"], _ARRAYS["arrays"] = pangenome, PangenomeArrays.from_pangenome(pangenome, device)
+    return _ARRAYS["arrays"]
+
+
 def write_nem_input_files(tmpdir: Path, organisms: set, sm_degree: int = 10, keep_tmp_files: bool = False) -> Tuple[float, int]:
     """partition.py:344-436.  Exports the sub-pangenome of ``organisms`` (global ``pan``) and registers it under
     ``tmpdir``; returns (total edge weight / 2, number of families) exactly like the reference."""
-    inp = export.export_from_pangenome(pan, organisms, sm_degree, keep_text=keep_tmp_files)
+    arrays = _arrays_for(pan)
+    if arrays is not None and not keep_tmp_files:
+        inp = arrays.instance(organisms, sm_degree)          # tensor ops on the cached array form of the pangenome
+    else:
+        inp = export.export_from_pangenome(pan, organisms, sm_degree, keep_text=keep_tmp_files)
     export.register(tmpdir, inp)
     if keep_tmp_files:
         export.write_text_files(Path(tmpdir), inp)
@@ -229,7 +266,7 @@ def run_k_candidates(nem_dir_path: Path, nb_org: int, ks: List[int], free_disper
     if inp is None:
         raise FileNotFoundError(f"no exported NEM instance registered for {nem_dir_path}")
     if inp.device is None:
-        inp.device = engine.DeviceInput.from_numpy(inp.bits, inp.D, inp.rowptr, inp.col, inp.w)
+        inp.device = _device_input(inp)
     rank, world = 0, 1
     try:
         import torch.distributed as dist
@@ -334,6 +371,8 @@ def partition(
     check_pangenome_former_partition(pangenome, force)
     check_pangenome_info(pangenome, need_annotations=True, need_families=True, need_graph=True, disable_bar=disable_bar)
     organisms = set(pangenome.organisms)
+    if not keep_tmp_files:
+        prepare_arrays(pangenome)   # one traversal of the objects; every sample / chunk below is derived from tensors
 
     if keep_tmp_files:
         tmp_dir = tempfile.mkdtemp(dir=tmpdir)
@@ -381,7 +420,13 @@ def partition(
     start_partitioning = time.time()
     logger.info("Partitioning...")
     pansize = len(families)
-    if chunk_size < len(organisms):
+    arrays = _arrays_for(pangenome)
+    if chunk_size < len(organisms) and arrays is not None:
+        partitioning_results = [_partition_chunked_arrays(arrays, organisms, chunk_size, kval, beta, sm_degree,
+                                                          free_dispersion, pansize), []]
+        logger.info(f"Did {len(samples)} partitioning with chunks of size {chunk_size} among "
+                    f"{len(organisms)} genomes in {round(time.time() - start_partitioning, 2)} seconds.")
+    elif chunk_size < len(organisms):
         validated = set()
 
         def validate_family(res):  # partition.py:784-802
@@ -401,14 +446,7 @@ def partition(
         condition = len(organisms) / chunk_size
         while len(validated) < pansize:
             prev = len(samples)
-            while not all(val >= condition for val in org_nb_sample.values()):
-                shuffled_orgs = list(organisms)
-                random.shuffle(shuffled_orgs)
-                while len(shuffled_orgs) > chunk_size:       # strict '>': the tail of every shuffle is dropped
-                    samples.append(set(shuffled_orgs[:chunk_size]))
-                    for org in samples[-1]:
-                        org_nb_sample[org] += 1
-                    shuffled_orgs = shuffled_orgs[chunk_size:]
+            _draw_samples(organisms, chunk_size, org_nb_sample, condition)
             logger.info("Launching NEM")
             for i, _ in enumerate(samples[prev:], start=prev):
                 validate_family(nem_samples((i, kval, beta, sm_degree, free_dispersion, seed, init, tmp_path, keep_tmp_files)))
@@ -436,10 +474,77 @@ def partition(
 
     pangenome.status["partitioned"] = "Computed"
     export.release(tmp_path)
+    _ARRAYS["pan"], _ARRAYS["arrays"] = None, None
     if not keep_tmp_files:
         tmp_dir.cleanup()
     else:
         copytree(tmp_path, output / "NEM_files/")
+
+
+def _draw_samples(organisms, chunk_size, org_nb_sample, condition):
+    """partition.py:810-818: shuffle the genomes and cut chunks until every genome was drawn `condition` times.
+    The strict '>' drops the tail of every shuffle (SURVEY.md Appendix A #10)."""
+    while not all(val >= condition for val in org_nb_sample.values()):
+        shuffled_orgs = list(organisms)
+        random.shuffle(shuffled_orgs)
+        while len(shuffled_orgs) > chunk_size:
+            samples.append(set(shuffled_orgs[:chunk_size]))
+            for org in samples[-1]:
+                org_nb_sample[org] += 1
+            shuffled_orgs = shuffled_orgs[chunk_size:]
+
+
+CHUNK_BATCH = 16   # chunk instances per batched GPU call
+
+
+def _partition_chunked_arrays(arrays, organisms, chunk_size, kval, beta, sm_degree, free_dispersion, pansize):
+    """The chunked mode of partition.py:781-864 on tensors: every chunk instance is derived from the cached arrays,
+    instances run in batches on the GPU, and ``validate_family`` (partition.py:784-802) is applied to the whole result of
+    a chunk at once (a family occurs at most once per chunk, so the element-wise form is the same rule)."""
+    import torch
+    logger = logging.getLogger("PPanGGOLiN")
+    dev = arrays.device
+    F = len(arrays.fam_names)
+    n_org = len(organisms)
+    votes = torch.zeros((F, 4), dtype=torch.long, device=dev)          # columns: P, S, C, U
+    validated = torch.zeros(F, dtype=torch.bool, device=dev)
+    org_nb_sample = Counter()
+    for org in organisms:
+        org_nb_sample[org] = 0
+    condition = n_org / chunk_size
+    while int(validated.sum().item()) < pansize:
+        prev = len(samples)
+        _draw_samples(organisms, chunk_size, org_nb_sample, condition)
+        logger.info("Launching NEM")
+        new = list(range(prev, len(samples)))
+        for b0 in range(0, len(new), CHUNK_BATCH):
+            insts = [arrays.instance(samples[i], sm_degree) for i in new[b0:b0 + CHUNK_BATCH]]
+            jobs = [(_device_input(inp), kval, beta * (inp.N / inp.edges_weight), free_dispersion, 100) for inp in insts]
+            runs = engine.nem_run_batch(jobs, flags=_epilogue_flags(chunk_size))
+            for inp, run in zip(insts, runs):
+                if not run.ok:
+                    logger.warning("A NEM run failed for this dataset/chunk and was skipped. In chunked mode, other chunks "
+                                   "can still complete and final partitioning may still succeed.")
+                    continue
+                lab, _ = engine.labels_device(run.T)
+                lab = lab.to(torch.long)
+                code = torch.where(lab == 0, 0, torch.where(lab == kval - 1, 2, 1))    # first letter: P / S (S1.., S_) / C
+                rows = inp.fam_rows
+                votes.index_put_((rows, code), torch.ones_like(code), accumulate=True)
+                v = votes[rows]
+                s = v.sum(1)
+                mx = v.max(1).values
+                cond = ((s > n_org / chunk_size) & (mx.to(torch.float64) >= s.to(torch.float64) * 0.5)) | (s > n_org)
+                newly = cond & ~validated[rows]
+                undecided = newly & (mx.to(torch.float64) < s.to(torch.float64) * 0.5)
+                if bool(undecided.any()):
+                    votes[rows[undecided], 3] = n_org
+                validated[rows[newly]] = True
+        condition += 1
+        logger.debug(f"There are {int(validated.sum().item())} validated families out of {pansize} families.")
+    best = votes.argmax(1).cpu().numpy()                                  # ties -> first of P, S, C, U like max(dict)
+    letters = np.array(["P", "S", "C", "U"])
+    return dict(zip(arrays.fam_names, letters[best].tolist()))
 
 
 def launch(args: argparse.Namespace):
