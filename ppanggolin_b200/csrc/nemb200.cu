@@ -895,3 +895,5 @@ extern "C" int nemb200_nem_host(const uint32_t* bits, int64_t N, int64_t D, int6
   nemb200_plan_destroy(pl);
   return rc;
 }
+
+#include "nem_shim.inc"

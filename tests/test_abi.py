@@ -70,3 +70,20 @@ def test_bad_arguments_are_rejected():
     assert engine.lib().nemb200_plan_create(ctypes.byref(h), 10, 10, 100, 3, 3, 0, 0) == -1      # stride not multiple of 4
     assert engine.lib().nemb200_plan_create(ctypes.byref(h), 10, 10, 100, 4, 33, 0, 0) == -1     # K > 32
     assert engine.lib().nemb200_plan_create(ctypes.byref(h), 10, 10, 200, 4, 3, 0, 0) == -1      # stride too short for D
+
+
+def test_reference_nem_symbol_is_exported_with_reference_error_codes(tmp_path):
+    """include/nem_stats_b200.h: `int nem(...)` with the signature of NEM/nem_exe.h:23-38 (what nem_stats.pyx binds)."""
+    import ctypes as C
+    L = C.CDLL(str(engine.LIB_PATH))
+    assert hasattr(L, "nem")
+    L.nem.restype = C.c_int
+    L.nem.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_float, C.c_char_p, C.c_float, C.c_char_p, C.c_int, C.c_int,
+                      C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    base = str(tmp_path / "nem_file").encode()
+    args = lambda **kw: [kw.get("f", base), kw.get("k", 3), kw.get("algo", b"nem"), 1.0, b"clas", 0.01, b"fuzzy", 100, 1, b"bern",
+                         b"pk", kw.get("disp", b"sk_"), kw.get("init", 2), base + b"_init_3.m", base + b"_3", 42]
+    assert L.nem(*args(algo=b"gem")) == 2          # EXIT_E_ARGS: only what PPanGGOLiN passes is supported
+    assert L.nem(*args(init=1)) == 2
+    assert L.nem(*args()) == 3                     # EXIT_E_FILE: no input files
+    assert b"can't open" in (tmp_path / "nem_file_3.stderr").read_bytes()

@@ -334,3 +334,55 @@ def test_full_size_properties(eng):
         assert float((lab.cpu() == torch.from_numpy(sp.true_class.astype(np.int32))).float().mean()) > 0.98
         be.plan.close()
     assert torch.equal(outs[0], outs[1])
+
+
+def _our_nem(dirpath, K, beta, fd, itermax=100):
+    """nem(...) of libnemb200.so called exactly like partition.py:126-150 calls nem_stats.nem."""
+    import ctypes as C
+    from ppanggolin_b200.nem import engine
+    L = C.CDLL(str(engine.LIB_PATH))
+    L.nem.restype = C.c_int
+    L.nem.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_float, C.c_char_p, C.c_float, C.c_char_p, C.c_int, C.c_int,
+                      C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    p = dirpath.as_posix().encode("ascii")
+    return L.nem(p + b"/nem_file", K, b"nem", beta, b"clas", 0.01, b"fuzzy", itermax, True, b"bern", b"pk",
+                 b"skd" if fd else b"sk_", 2, p + b"/nem_file_init_" + str(K).encode() + b".m", p + b"/nem_file_" + str(K).encode(), 42)
+
+
+@pytest.mark.parametrize("name", ["appendixB", "sk_graph", "skd_graph", "sweep_K5", "emptyclass"])
+def test_file_based_nem_entry_point(eng, name, tmp_path):
+    """The reference's own FFI symbol on the B200 path: same input files, same output files (.uf/.mf/.stderr), parsed by the
+    same code that parses the reference's, compared with the reference's golden results."""
+    g = load_nem(name)
+    X = unpack_rows(g["bits"], g["D"])
+    N = X.shape[0]
+    w_text = [repr(round(float(v), 4)) for v in g["w"]]
+    refnem.write_nem_files(tmp_path, X, refnem.csr_to_nei_lists(N, g["rowptr"], g["col"], w_text))
+    refnem.write_init_file(tmp_path, g["K"], g["D"])
+    rc = _our_nem(tmp_path, g["K"], g["beta"], bool(g["fd"]), g["itermax"])
+    out = refnem.parse_ref_outputs(tmp_path, g["K"], g["D"])
+    if not g["ok"]:
+        assert rc == 1 and out is None          # EXIT_W_RESULT, no .uf: partition.py:233-265 then returns ({}, None, None)
+        return
+    assert rc == 0 and out is not None
+    assert out["n_iter"] in (g["n_iter"] - 1, g["n_iter"], g["n_iter"] + 1)
+    assert abs(out["crit"][3] - g["crit"][3]) <= REL_M * abs(g["crit"][3]) + 1e-6 * abs(g["crit"][3])   # %g keeps 6 digits
+    lab, _, _ = refnem.oracle_labels(out["T3"].astype(np.float32))
+    ref_lab, _, _ = refnem.oracle_labels(g["T3"].astype(np.float32))
+    assert (lab == ref_lab).mean() >= (0.995 if _is_sweep(g["beta"], g["itermax"]) else 0.999)
+    assert np.array_equal(out["mu"], g["mu"].astype(np.float64)) or (out["mu"] != g["mu"]).mean() < 0.002
+    assert np.allclose(out["pk"], g["pk"], atol=2e-3) and np.allclose(out["eps"], g["eps"], rtol=1e-4, atol=1e-6)
+    # same file layout as the reference's .mf: header, blank, criteria line, ..., K parameter lines
+    mf = (tmp_path / f"nem_file_{g['K']}.mf").read_text().splitlines()
+    assert mf[0].startswith("Criteria U=NEM") and mf[1] == "" and len(mf[2].split()) == 6 and mf[4] == "Beta (fixed)"
+    assert mf[6].startswith(f"Mu ({g['D']}), Pk, and disp ({g['D']}) of the {g['K']} classes") and len(mf) == 8 + g["K"]
+    if refnem.have_ref():   # byte-level comparison of the layout with the reference's own writer
+        ref_dir = tmp_path / "ref"
+        refnem.write_nem_files(ref_dir, X, refnem.csr_to_nei_lists(N, g["rowptr"], g["col"], w_text))
+        refnem.write_init_file(ref_dir, g["K"], g["D"])
+        assert refnem.ref_nem_call(ref_dir, g["K"], g["beta"], bool(g["fd"]), g["itermax"]) == 0
+        rmf = (ref_dir / f"nem_file_{g['K']}.mf").read_text().splitlines()
+        assert len(rmf) == len(mf) and rmf[0] == mf[0] and rmf[4] == mf[4] and rmf[5] == mf[5] and rmf[6] == mf[6]
+        ruf = (ref_dir / f"nem_file_{g['K']}.uf").read_text().splitlines()
+        uf = (tmp_path / f"nem_file_{g['K']}.uf").read_text().splitlines()
+        assert len(ruf) == len(uf) and np.mean([a == b for a, b in zip(ruf, uf)]) >= 0.99
