@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=400)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="N>1: exchange through NCCL collectives instead of the kernels' NVLink peer-memory path")
     ap.add_argument("--incremental", action="store_true", help="time the incremental M-step (product default) as the headline")
     return ap.parse_args()
 
@@ -230,7 +231,8 @@ def run_ours(a):
     graph = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), D, sp.rowptr, sp.col, sp.w, device=dev)
     nnz = int(len(sp.col))
     mflags = engine.EPI_LOGSPACE | (0 if a.incremental else engine.FULL_RECOUNT)
-    be = CudaBackend(sp.bits, D, N, K, False, mflags, graph)
+    pg = group if (world > 1 and not a.nccl) else None
+    be = CudaBackend(sp.bits, D, N, K, False, mflags, graph, peer_group=pg, row_offset=lo)
     em = ShardedEM(be, N, K, rank, world, group)
     em.start(beta)
 
@@ -279,6 +281,8 @@ def run_ours(a):
     lab, _ = engine.labels_device(be.T[em.cur])
     truth = torch.from_numpy(sp.true_class.astype(np.int32)).to(dev)
     acc = float((lab == truth).float().mean().item())
+    Tf = be.T[em.cur]
+    t_checksum = float((Tf.double() * torch.arange(1, K + 1, device=dev, dtype=torch.float64)).sum().item())
 
     line = None
     if rank == 0:
@@ -308,6 +312,7 @@ def run_ours(a):
                 "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit ops + f64 epilogue", "data": "synthetic",
                 "config": workload_config(a), "gpu_launches": launches, "clocks": clocks,
                 "mstep_mode": "incremental" if a.incremental else "full recount every iteration",
+                "exchange": ("none (1 GPU)" if world == 1 else ("NCCL all-reduce + all-gather" if a.nccl else "NVLink peer memory, fused into k_mstep_finalize / k_density_sk")),
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBs"], "peak": peak,
                              "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": tr, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": kernels[dom]["bytes"], "kernel_ms": kernels[dom]["ms"],
@@ -315,10 +320,10 @@ def run_ours(a):
                              "iteration": {"B_iter_bytes": biter, "achieved_GBs": biter / (ms_total / a.steps / 1000.0) / 1e9,
                                            "frac": biter / (ms_total / a.steps / 1000.0) / 1e9 / (peak * world)}},
                 "check": {"label_accuracy_vs_generator": acc, "gs_levels": graph.n_levels, "nnz": nnz,
-                          "last_maxdiff": statuses[-1][0], "status": statuses[-1][1]}}
+                          "last_maxdiff": statuses[-1][0], "status": statuses[-1][1], "posterior_checksum": t_checksum}}
     # ---- the product default (incremental M-step: only rows that changed class are recounted), same steps
     if not a.incremental:
-        be_i = CudaBackend(sp.bits, D, N, K, False, engine.EPI_LOGSPACE, graph)
+        be_i = CudaBackend(sp.bits, D, N, K, False, engine.EPI_LOGSPACE, graph, peer_group=pg, row_offset=lo)
         em_i = ShardedEM(be_i, N, K, rank, world, group)
         em_i.start(beta)
         for _ in range(a.warmup):
@@ -369,7 +374,7 @@ def run_ours(a):
         t0 = time.perf_counter()
         dbits = host_bits.to(dev, non_blocking=True)
         g2 = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), D, sp.rowptr, sp.col, sp.w, device=dev)
-        be2 = CudaBackend(dbits, D, N, K, False, engine.EPI_LOGSPACE, g2)
+        be2 = CudaBackend(dbits, D, N, K, False, engine.EPI_LOGSPACE, g2, peer_group=pg, row_offset=lo)
         out = ShardedEM(be2, N, K, rank, world, group).run(beta, 100, 0.01)
         if rank == 0:
             _ = out.T.cpu()

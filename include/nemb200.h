@@ -48,6 +48,8 @@ enum {
   NEMB200_EPI_LOGSPACE = 1 << 0, /* log-sum-exp epilogue: valid for any number of genomes */
   NEMB200_JACOBI       = 1 << 1, /* parallel posterior update instead of the reference's in-place Gauss-Seidel
                                     sweep (nem_alg.c:2459-2464); off by default                                  */
+  NEMB200_PEER_EXCHANGE = 1 << 3, /* plan owns a full-length log-density buffer and signal words that other ranks of a
+                                    row-sharded run map through CUDA IPC (nemb200_peer_*)                        */
   NEMB200_FULL_RECOUNT = 1 << 2  /* M-step: recount every one-hot row at every iteration instead of updating the integer
                                     column counts with the rows that changed class (same result bit for bit; this is
                                     the mode the benchmark times as its headline)                                */
@@ -140,6 +142,23 @@ int nemb200_mstep_finalize(nemb200_plan* plan, void* stream);
 /* E-step, part 1 (nem_mod.c:618-689 + nem_alg.c:2319-2374): log f_k(x_i) for this rank's rows -> logf (N_local x K
  * doubles, device; -inf encodes the reference's null density). */
 int nemb200_density(nemb200_plan* plan, const uint32_t* bits, double* logf, void* stream);
+
+/* ---- row-sharded runs: the two exchange steps of an iteration over NVLink peer memory, fused into the kernels ------
+ * One process per GPU; every rank creates its plan with NEMB200_PEER_EXCHANGE, exports (CUDA IPC handle of the plan's
+ * block + 4 offsets), the driver all-gathers those 96 bytes per rank out of band (torch.distributed), and every rank
+ * attaches.  From then on
+ *   - nemb200_density_peers stores the shard's log-densities into the log-density buffer of EVERY rank (peer stores)
+ *     and publishes an epoch; nemb200_peer_wait_densities blocks the stream until all ranks have published it: together
+ *     they are the all-gather that precedes the replicated Gauss-Seidel sweep;
+ *   - nemb200_mstep_finalize publishes / waits for the statistics epoch and reads every rank's statistic blocks (peer
+ *     loads), adding them in rank order: the all-reduce of the M-step, identical parameters on every rank.
+ * world <= 8 (one NVSwitch box).  The reference has no counterpart (one process per NEM instance, partition.py:505). */
+int nemb200_peer_export(nemb200_plan* plan, unsigned char handle_out[64], int64_t offsets_out[4]);
+int nemb200_peer_attach(nemb200_plan* plan, int32_t world, int32_t rank, const unsigned char* handles /*world*64*/,
+                        const int64_t* offsets /*world*4*/);
+int nemb200_peer_logf(nemb200_plan* plan, double** logf_full);
+int nemb200_density_peers(nemb200_plan* plan, const uint32_t* bits, int64_t row_offset, void* stream);
+int nemb200_peer_wait_densities(nemb200_plan* plan, void* stream);
 
 /* E-step, part 2 (nem_alg.c:2412-2489, :2630-2701): posterior sweep over rows [0, N) of logf/T (full-length arrays),
  * reading T_old and writing T_new; maxdiff_bits receives max |T_new - T_old| as float bits (atomicMax).

@@ -147,6 +147,18 @@ struct nemb200_plan {
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> onehot_events;
   uint32_t* flags2 = nullptr;     // [0] max |T_new - T_old| as float bits, [1] status (P.status points here)
+  // row-sharded exchange over NVLink peer memory (nemb200_peer_*)
+  double* logf_full = nullptr;    // [N_total][K] log-densities of ALL rows: every rank's density kernel stores into it
+  int* sig = nullptr;             // [2][kMaxPeers] epochs completed by each rank: phase 0 = M-step statistics, 1 = densities
+  int* peer_err = nullptr;        // [1] set when a peer wait timed out
+  int** sig_ptrs = nullptr;       // [kMaxPeers] device array: the ranks' sig arrays
+  int world = 1, rank = 0;
+  bool attached = false;
+  void* peer_base[kMaxPeers] = {nullptr};
+  double* peer_logf[kMaxPeers] = {nullptr};
+  const int* peer_iblock[kMaxPeers] = {nullptr};
+  const double* peer_dblock[kMaxPeers] = {nullptr};
+  int epoch_stats = 0, epoch_dens = 0;
   int fin_chunks = 0;
   float* eps_init = nullptr;
   double* crit_partial = nullptr;
@@ -183,6 +195,8 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   pl->Lword = ar.take<double>(K * Ws); pl->eps_init = ar.take<float>(K);
   pl->fin_partial = ar.take<double>((size_t)K * pl->fin_chunks * 2); pl->fin_tickets = ar.take<int>(K);
   pl->crit_partial = ar.take<double>((size_t)pl->crit_blocks * 4); pl->crit4 = ar.take<double>(8);
+  pl->sig = ar.take<int>(2 * kMaxPeers); pl->peer_err = ar.take<int>(1); pl->sig_ptrs = ar.take<int*>(kMaxPeers);
+  if (pl->flags & NEMB200_PEER_EXCHANGE) pl->logf_full = ar.take<double>((size_t)pl->N_total * K);
   pl->crit_terms = ar.take<float>((size_t)pl->N_total * K * 2); pl->crit_rows = ar.take<double>((size_t)pl->N_total * 2);  // the sweep and the criteria run over all rows, also on a shard's plan
   if (pl->with_run_buffers) {
     pl->run_logf = ar.take<double>(N * K); pl->run_Ta = ar.take<float>(N * K); pl->run_Tb = ar.take<float>(N * K);
@@ -229,7 +243,8 @@ static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int6
   Arena real;
   real.base = (char*)pl->block; real.counting = false;
   plan_layout(pl, real);
-  if (cudaMemset(pl->fin_tickets, 0, K * sizeof(int)) != cudaSuccess) {
+  if (cudaMemset(pl->sig, 0, 2 * kMaxPeers * sizeof(int)) != cudaSuccess || cudaMemset(pl->peer_err, 0, sizeof(int)) != cudaSuccess ||
+      cudaMemset(pl->fin_tickets, 0, K * sizeof(int)) != cudaSuccess) {
     nemb200_plan_destroy(pl);
     return fail(NEMB200_ERR_CUDA, "plan_create: memset");
   }
@@ -240,6 +255,11 @@ static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int6
 extern "C" void nemb200_plan_destroy(nemb200_plan* pl) {
   if (!pl) return;
   for (auto& pr : pl->onehot_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  if (pl->attached) {
+    cudaDeviceSynchronize();
+    for (int r = 0; r < pl->world; r++)
+      if (r != pl->rank && pl->peer_base[r]) cudaIpcCloseMemHandle(pl->peer_base[r]);
+  }
   cached_free(pl->block, pl->block_bytes);
   delete pl;
 }
@@ -391,8 +411,20 @@ extern "C" int nemb200_mstep_finalize(nemb200_plan* pl, void* stream_) {
   if (!pl) return fail(NEMB200_ERR_ARG, "mstep_finalize: null plan");
   cudaStream_t st = (cudaStream_t)stream_;
   CK(cudaMemsetAsync(pl->P.has_half, 0, sizeof(int), st));
-  k_mstep_finalize<<<dim3(pl->fin_chunks, pl->K), 256, 0, st>>>(pl->P, pl->cnt, pl->fsum, pl->nk_cnt, pl->nk_fz, pl->N_total,
-                                                             pl->fin_partial, pl->fin_tickets);
+  PeerStats ps;
+  ps.n = 1; ps.iblock[0] = pl->cnt; ps.dblock[0] = pl->fsum;
+  if (pl->attached) {
+    // the all-reduce of the M-step statistics, fused into this kernel: publish "my statistics of this iteration are
+    // complete", wait for every rank's, then read and add all ranks' blocks in rank order (peer loads over NVLink)
+    const int epoch = ++pl->epoch_stats;
+    k_peer_signal<<<1, 32, 0, st>>>(pl->sig_ptrs, pl->world, 0, pl->rank, epoch);
+    CK(cudaGetLastError());
+    k_peer_wait<<<1, 32, 0, st>>>(pl->sig, pl->world, 0, epoch, pl->peer_err);
+    CK(cudaGetLastError());
+    ps.n = pl->world;
+    for (int r = 0; r < pl->world; r++) { ps.iblock[r] = pl->peer_iblock[r]; ps.dblock[r] = pl->peer_dblock[r]; }
+  }
+  k_mstep_finalize<<<dim3(pl->fin_chunks, pl->K), 256, 0, st>>>(pl->P, ps, pl->N_total, pl->fin_partial, pl->fin_tickets);
   CK(cudaGetLastError());
   if (pl->free_disp) {
     const int n = pl->K * pl->Ws;
@@ -409,7 +441,7 @@ static int group_lanes(int units) {  // lanes cooperating on one row: smallest p
 }
 
 template <int KB, int KX>
-static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
+static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, const PeerOut& out, cudaStream_t st) {
   constexpr int RB = KB <= 4 ? 4 : (KB <= 8 ? 2 : 1);  // rows per lane group: bounded by registers (2 * RB * KB + 4 * RB)
   const int W4 = pl->Ws / 4;
   const int G = group_lanes(W4);
@@ -426,11 +458,11 @@ static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* log
   if (blocks < 1) blocks = 1;
   kern<<<(unsigned)blocks, kDensTpb, in_smem ? smem : 0, st>>>((const uint4*)bits, pl->N_local, W4, pl->K, G,
                                                           (const uint4*)pl->P.m1, (const uint4*)pl->P.valid, pl->P.L,
-                                                          pl->P.B, pl->P.has_half, logf, in_smem);
+                                                          pl->P.B, pl->P.has_half, out, in_smem);
   CK(cudaGetLastError());
   return 0;
 }
-static int dispatch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
+static int dispatch_density_sk(nemb200_plan* pl, const uint32_t* bits, const PeerOut& logf, cudaStream_t st) {
   switch (pl->K) {  // exact-K kernels for the common small K (no per-class predicates), buckets above
     case 1: case 2: return launch_density_sk<2, 0>(pl, bits, logf, st);
     case 3: return launch_density_sk<3, 3>(pl, bits, logf, st);
@@ -447,7 +479,7 @@ static int dispatch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* l
   return launch_density_sk<32, 0>(pl, bits, logf, st);
 }
 template <int KB>
-static int launch_density_skd(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
+static int launch_density_skd(nemb200_plan* pl, const uint32_t* bits, const PeerOut& logf, cudaStream_t st) {
   const int G = group_lanes(pl->Ws);
   const long long rows_per_block = (long long)(256 / 32) * (32 / G);
   long long blocks = (pl->N_local + rows_per_block - 1) / rows_per_block;
@@ -460,12 +492,94 @@ static int launch_density_skd(nemb200_plan* pl, const uint32_t* bits, double* lo
   return 0;
 }
 
+static int density_to(nemb200_plan* pl, const uint32_t* bits, const PeerOut& out, cudaStream_t st) {
+  if (pl->free_disp) return DISPATCH_KB(pl->K, launch_density_skd, pl, bits, out, st);
+  return dispatch_density_sk(pl, bits, out, st);
+}
+
 extern "C" int nemb200_density(nemb200_plan* pl, const uint32_t* bits, double* logf, void* stream_) {
   if (!pl || (pl->N_local > 0 && (!bits || !logf))) return fail(NEMB200_ERR_ARG, "density: null argument");
   if (pl->N_local == 0) return NEMB200_OK;
+  PeerOut out;
+  out.n = 1; out.ptr[0] = logf; out.row_off = 0;
+  return density_to(pl, bits, out, (cudaStream_t)stream_);
+}
+
+// ---- row-sharded exchange over peer memory -------------------------------------------------------------------------
+extern "C" int nemb200_peer_export(nemb200_plan* pl, unsigned char handle_out[64], int64_t offsets_out[4]) {
+  if (!pl || !handle_out || !offsets_out) return fail(NEMB200_ERR_ARG, "peer_export: null argument");
+  if (!pl->logf_full) return fail(NEMB200_ERR_ARG, "peer_export: plan was not created with NEMB200_PEER_EXCHANGE");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  CK(cudaIpcGetMemHandle(&hd, pl->block));
+  memcpy(handle_out, &hd, 64);
+  const char* base = (const char*)pl->block;
+  offsets_out[0] = (const char*)pl->cnt - base;
+  offsets_out[1] = (const char*)pl->fsum - base;
+  offsets_out[2] = (const char*)pl->logf_full - base;
+  offsets_out[3] = (const char*)pl->sig - base;
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_peer_attach(nemb200_plan* pl, int32_t world, int32_t rank, const unsigned char* handles,
+                                   const int64_t* offsets) {
+  if (!pl || !handles || !offsets || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(NEMB200_ERR_ARG, "peer_attach: bad argument (world <= %d)", kMaxPeers);
+  if (!pl->logf_full) return fail(NEMB200_ERR_ARG, "peer_attach: plan was not created with NEMB200_PEER_EXCHANGE");
+  int* sig_host[kMaxPeers] = {nullptr};
+  for (int r = 0; r < world; r++) {
+    char* base;
+    if (r == rank) base = (char*)pl->block;
+    else {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, handles + (size_t)r * 64, 64);
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+      pl->peer_base[r] = p;
+      base = (char*)p;
+    }
+    pl->peer_iblock[r] = (const int*)(base + offsets[r * 4 + 0]);
+    pl->peer_dblock[r] = (const double*)(base + offsets[r * 4 + 1]);
+    pl->peer_logf[r] = (double*)(base + offsets[r * 4 + 2]);
+    sig_host[r] = (int*)(base + offsets[r * 4 + 3]);
+  }
+  CK(cudaMemcpy(pl->sig_ptrs, sig_host, sizeof sig_host, cudaMemcpyHostToDevice));
+  pl->world = world; pl->rank = rank; pl->attached = true;
+  return NEMB200_OK;
+}
+
+extern "C" int nemb200_peer_logf(nemb200_plan* pl, double** logf_full) {
+  if (!pl || !logf_full) return fail(NEMB200_ERR_ARG, "peer_logf: null argument");
+  *logf_full = pl->logf_full;
+  return NEMB200_OK;
+}
+
+/* E-step part 1 for a shard: densities of this rank's rows, stored into the logf buffer of every rank at row_offset
+ * (the all-gather, fused into the kernel's epilogue), then this rank's "densities complete" epoch is published. */
+extern "C" int nemb200_density_peers(nemb200_plan* pl, const uint32_t* bits, int64_t row_offset, void* stream_) {
+  if (!pl || !pl->attached) return fail(NEMB200_ERR_ARG, "density_peers: plan is not attached to its peers");
   cudaStream_t st = (cudaStream_t)stream_;
-  if (pl->free_disp) return DISPATCH_KB(pl->K, launch_density_skd, pl, bits, logf, st);
-  return dispatch_density_sk(pl, bits, logf, st);
+  if (pl->N_local > 0) {
+    if (!bits) return fail(NEMB200_ERR_ARG, "density_peers: null matrix");
+    PeerOut out;
+    out.n = pl->world; out.row_off = row_offset;
+    out.ptr[0] = pl->peer_logf[pl->rank];            // own buffer first
+    int q = 1;
+    for (int r = 0; r < pl->world; r++) if (r != pl->rank) out.ptr[q++] = pl->peer_logf[r];
+    int rc = density_to(pl, bits, out, st);
+    if (rc) return rc;
+  }
+  k_peer_signal<<<1, 32, 0, st>>>(pl->sig_ptrs, pl->world, 1, pl->rank, ++pl->epoch_dens);
+  CK(cudaGetLastError());
+  return NEMB200_OK;
+}
+
+/* Blocks the stream until every rank has published the current densities epoch (call before the sweep). */
+extern "C" int nemb200_peer_wait_densities(nemb200_plan* pl, void* stream_) {
+  if (!pl || !pl->attached) return fail(NEMB200_ERR_ARG, "peer_wait_densities: plan is not attached to its peers");
+  k_peer_wait<<<1, 32, 0, (cudaStream_t)stream_>>>(pl->sig, pl->world, 1, pl->epoch_dens, pl->peer_err);
+  CK(cudaGetLastError());
+  return NEMB200_OK;
 }
 
 extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, const float* T_old, float* T_new,
@@ -588,8 +702,11 @@ extern "C" int nemb200_read_flags(nemb200_plan* pl, float* maxdiff, int32_t* sta
   if (!pl) return fail(NEMB200_ERR_ARG, "read_flags: null plan");
   cudaStream_t st = (cudaStream_t)stream_;
   uint32_t h[2] = {0, 0};
+  int perr = 0;
   CK(cudaMemcpyAsync(h, pl->flags2, sizeof h, cudaMemcpyDeviceToHost, st));
+  if (pl->attached) CK(cudaMemcpyAsync(&perr, pl->peer_err, sizeof perr, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (perr != 0) return fail(NEMB200_ERR_CUDA, "peer exchange: a wait for another rank timed out");
   if (maxdiff) memcpy(maxdiff, &h[0], sizeof(float));
   if (status) *status = (int32_t)h[1];
   return NEMB200_OK;

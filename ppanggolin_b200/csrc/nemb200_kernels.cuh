@@ -58,6 +58,48 @@ struct Params {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+// Row-sharded multi-GPU exchange over NVLink peer memory (no collective library on the data path):
+//  * the density kernels store every log-density row straight into the logf buffer of EVERY rank (peer stores), which
+//    is the all-gather the replicated Gauss-Seidel sweep needs, fused into the producing kernel;
+//  * k_mstep_finalize reads the column statistics of every rank (peer loads) and adds them in rank order, which is the
+//    all-reduce of the M-step, fused into the consuming kernel (same order on every rank -> identical parameters);
+//  * k_peer_signal / k_peer_wait are the two tiny flag barriers per iteration that order those accesses.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+struct PeerOut {            // where a density kernel writes: n buffers (own + peers), rows shifted by row_off
+  double* ptr[kMaxPeers];
+  int n;
+  long long row_off;
+};
+struct PeerStats {          // where k_mstep_finalize reads: the statistic blocks of the n ranks
+  const int* iblock[kMaxPeers];     // cnt[K][Dpad] followed by nk_cnt[K]
+  const double* dblock[kMaxPeers];  // fsum[K][Dpad] followed by nk_fz[K]
+  int n;
+};
+
+// every rank owns sig[2][kMaxPeers] ints: sig[phase][r] = last epoch rank r has completed for that phase
+__global__ void k_peer_signal(int* const* peer_sig /*[n] device pointers to the ranks' sig arrays*/, int n, int phase, int rank,
+                              int epoch) {
+  if (threadIdx.x < n && blockIdx.x == 0) {
+    __threadfence_system();
+    volatile int* dst = peer_sig[threadIdx.x] + phase * kMaxPeers + rank;
+    *dst = epoch;
+    __threadfence_system();
+  }
+}
+__global__ void k_peer_wait(const int* sig /*own sig array*/, int n, int phase, int epoch, int* error) {
+  if (threadIdx.x < n && blockIdx.x == 0) {
+    const volatile int* src = sig + phase * kMaxPeers + threadIdx.x;
+    long long spins = 0;
+    while (*src < epoch) {
+      __nanosleep(200);
+      if (++spins > (1LL << 24)) { atomicExch(error, 2); break; }   // ~several seconds: never hang the GPU
+    }
+    __threadfence_system();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // E-step part 1: log densities.  A group of G lanes walks RB rows at once so that each class's centre words are
 // fetched from shared memory once per RB matrix words.
 // ------------------------------------------------------------------------------------------------------------------
@@ -77,7 +119,7 @@ __device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint
 template <int KB, int KX, int RB, bool HALF, typename PlanePtr>
 __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, long long N, int W4, int Krt, int G,
                                                 PlanePtr m1, PlanePtr valid, const double* __restrict__ L,
-                                                const double* __restrict__ B, double* __restrict__ logf) {
+                                                const double* __restrict__ B, const PeerOut& out) {
   const int K = KX > 0 ? KX : Krt;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
@@ -154,7 +196,9 @@ __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, 
           if (r0 + r < N) {
             // e_k <= 1e-20: L = +inf; a mismatch gives the reference's null density (nem_mod.c:663-665, :684-685)
             const double v = (h[r][k] == 0) ? Bk : (Bk - (double)h[r][k] * Lk);
-            logf[(r0 + r) * K + k] = v;
+            const size_t o = (size_t)(out.row_off + r0 + r) * K + k;
+            out.ptr[0][o] = v;
+            for (int q = 1; q < out.n; q++) out.ptr[q][o] = v;      // peer stores over NVLink (row-sharded runs)
           }
         }
       }
@@ -168,7 +212,7 @@ template <int KB, int KX, int RB>
 __global__ void __launch_bounds__(kDensTpb)
 k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
              const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
-             const int* __restrict__ has_half, double* __restrict__ logf, int planes_in_smem) {
+             const int* __restrict__ has_half, PeerOut out, int planes_in_smem) {
   extern __shared__ uint4 smem4[];
   const bool half = (*has_half != 0);   // any centre at 0.5 (exact median tie): needs the `valid` plane
   if (planes_in_smem) {
@@ -180,11 +224,11 @@ k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, 
     __syncthreads();
     const uint4* sm1 = smem4;            // shared-memory pointers: LDS, not generic loads
     const uint4* sval = smem4 + n;
-    if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, sm1, sval, L, B, logf);
-    else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, sm1, sval, L, B, logf);
+    if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, sm1, sval, L, B, out);
+    else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, sm1, sval, L, B, out);
   } else {
-    if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, m1g, validg, L, B, logf);
-    else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, m1g, validg, L, B, logf);
+    if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, m1g, validg, L, B, out);
+    else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, m1g, validg, L, B, out);
   }
 }
 
@@ -194,7 +238,7 @@ template <int KB>
 __global__ void __launch_bounds__(256)
 k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int Dpad, int G,
               const uint32_t* __restrict__ m1, const uint32_t* __restrict__ valid, const double* __restrict__ Lkd,
-              const double* __restrict__ Lword, const double* __restrict__ B, double* __restrict__ logf) {
+              const double* __restrict__ Lword, const double* __restrict__ B, PeerOut out) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
   const int grp = lane / G;
@@ -244,7 +288,11 @@ k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int
     }
 #pragma unroll
     for (int k = 0; k < KB; k++)
-      if (k < K && (k & (G - 1)) == sub && row < N) logf[row * K + k] = B[k] - s[k];
+      if (k < K && (k & (G - 1)) == sub && row < N) {
+        const size_t o = (size_t)(out.row_off + row) * K + k;
+        const double v = B[k] - s[k];
+        for (int q = 0; q < out.n; q++) out.ptr[q][o] = v;
+      }
   }
 }
 
@@ -696,15 +744,18 @@ k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int
 constexpr int kFinCols = 1024;
 
 __global__ void __launch_bounds__(256)
-k_mstep_finalize(Params P, const int* __restrict__ cnt, const double* __restrict__ fsum, const int* __restrict__ nk_cnt,
-                 const double* __restrict__ nk_fz, long long N_total, double* __restrict__ partial /*[K][nchunk][2]*/,
+k_mstep_finalize(Params P, PeerStats ps, long long N_total, double* __restrict__ partial /*[K][nchunk][2]*/,
                  int* __restrict__ tickets /*[K]*/) {
   __shared__ double s_red[8][2];
   __shared__ int s_last;
   const int k = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
   const int D = P.D, Dpad = P.Dpad, Ws = P.Ws;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const double nk = (double)nk_cnt[k] + nk_fz[k];
+  const size_t KD = (size_t)P.K * Dpad;
+  long long nk_i = 0;
+  double nk_f = 0.0;
+  for (int q = 0; q < ps.n; q++) { nk_i += ps.iblock[q][KD + k]; nk_f += ps.dblock[q][KD + k]; }   // rank order: same on every rank
+  const double nk = (double)nk_i + nk_f;
   if (!(nk > kEps)) {  // empty class: nem_mod.c:1399-1403 -> STS_W_EMPTYCLASS, parameters kept
     if (threadIdx.x == 0 && chunk == 0) atomicMax(P.status, 1);
     return;
@@ -717,7 +768,10 @@ k_mstep_finalize(Params P, const int* __restrict__ cnt, const double* __restrict
     float m = 0.0f;
     double iner = 0.0;
     if (d < D) {
-      const double s1 = (double)cnt[(size_t)k * Dpad + d] + fsum[(size_t)k * Dpad + d];
+      long long c_i = 0;
+      double c_f = 0.0;
+      for (int q = 0; q < ps.n; q++) { c_i += ps.iblock[q][(size_t)k * Dpad + d]; c_f += ps.dblock[q][(size_t)k * Dpad + d]; }
+      const double s1 = (double)c_i + c_f;
       const double s0 = nk - s1;
       if (s1 > s0) { m = 1.0f; iner = s0; }
       else if (s1 < s0) { m = 0.0f; iner = s1; }

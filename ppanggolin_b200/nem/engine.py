@@ -22,6 +22,7 @@ EPI_REF = 0
 EPI_LOGSPACE = 1
 JACOBI = 2
 FULL_RECOUNT = 4
+PEER_EXCHANGE = 8
 MAX_K = 32
 
 STS_OK, STS_EMPTYCLASS, STS_INFINITE = 0, 1, 2
@@ -61,6 +62,11 @@ SIGNATURES = {
     "nemb200_stats_blocks": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i64), ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
     "nemb200_mstep_finalize": (ctypes.c_int, [_vp, _vp]),
     "nemb200_density": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "nemb200_peer_export": (ctypes.c_int, [_vp, _vp, _vp]),
+    "nemb200_peer_attach": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    "nemb200_peer_logf": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "nemb200_density_peers": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
+    "nemb200_peer_wait_densities": (ctypes.c_int, [_vp, _vp]),
     "nemb200_sweep": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp]),
     "nemb200_read_flags": (ctypes.c_int, [_vp, ctypes.POINTER(_f32), ctypes.POINTER(_i32), _vp]),
     "nemb200_criteria": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f32, ctypes.POINTER(ctypes.c_double * 5), _vp]),
@@ -389,6 +395,37 @@ class Plan:
         ms, n = _f32(0.0), _i32(0)
         _check(lib().nemb200_plan_timing(self._h, int(enable), ctypes.byref(ms), ctypes.byref(n)), "plan_timing")
         return float(ms.value), int(n.value)
+
+    # ---- row-sharded exchange over NVLink peer memory ----------------------------------------------------------
+    def peer_export(self):
+        """(64-byte CUDA IPC handle of the plan's block, 4 offsets) to be all-gathered by the driver."""
+        h = (ctypes.c_ubyte * 64)()
+        offs = (ctypes.c_int64 * 4)()
+        _check(lib().nemb200_peer_export(self._h, ctypes.cast(h, _vp), ctypes.cast(offs, _vp)), "peer_export")
+        return bytes(h), list(offs)
+
+    def peer_attach(self, world: int, rank: int, handles, offsets):
+        hb = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        ob = (ctypes.c_int64 * (4 * world))(*[v for o in offsets for v in o])
+        _check(lib().nemb200_peer_attach(self._h, world, rank, ctypes.cast(hb, _vp), ctypes.cast(ob, _vp)), "peer_attach")
+
+    def peer_logf(self):
+        """Torch view of the plan-owned full-length log-density buffer (N_total, K) float64."""
+        torch = _torch()
+        p = _vp()
+        _check(lib().nemb200_peer_logf(self._h, ctypes.byref(p)), "peer_logf")
+
+        class _A:
+            pass
+        a = _A()
+        a.__cuda_array_interface__ = {"shape": (self.N_total, self.K), "typestr": "<f8", "data": (p.value, False), "version": 3}
+        return torch.as_tensor(a, device=f"cuda:{torch.cuda.current_device()}")
+
+    def density_peers(self, bits, row_offset: int):
+        _check(lib().nemb200_density_peers(self._h, _ptr(bits), row_offset, _stream()), "density_peers")
+
+    def peer_wait_densities(self):
+        _check(lib().nemb200_peer_wait_densities(self._h, _stream()), "peer_wait_densities")
 
     def stats_blocks(self):
         """(int32 block, fp64 block): flat torch views covering all M-step statistics, for two in-place all-reduces."""

@@ -35,17 +35,34 @@ def shard_rows(N: int, world: int, rank: int):
 class CudaBackend:
     """Kernels through libnemb200.so (engine.Plan)."""
 
-    def __init__(self, bits_local, D: int, N_total: int, K: int, free_dispersion: bool, flags: int, graph):
+    def __init__(self, bits_local, D: int, N_total: int, K: int, free_dispersion: bool, flags: int, graph, peer_group=None,
+                 row_offset: int = 0):
+        """``peer_group``: a torch.distributed group -> the two exchange steps of an iteration go over NVLink peer memory
+        inside the kernels (nemb200_peer_*) instead of NCCL collectives; None -> single GPU, or NCCL in ShardedEM."""
         import torch
         from . import engine
         self.torch, self.engine = torch, engine
         self.bits = bits_local
         self.N_local = int(bits_local.shape[0])
         self.N, self.K, self.D = N_total, K, D
+        self.row_offset = row_offset
+        self.peer = peer_group is not None
+        if self.peer:
+            flags |= engine.PEER_EXCHANGE
         self.plan = engine.Plan(self.N_local, N_total, D, int(bits_local.shape[1]), K, free_dispersion, flags)
         self.graph = graph  # engine.DeviceInput carrying the full CSR + schedule (replicated), or None
         dev = bits_local.device
-        self.logf_full = torch.empty((N_total, K), dtype=torch.float64, device=dev)
+        if self.peer:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(peer_group), dist.get_rank(peer_group)
+            mine = self.plan.peer_export()
+            allx = [None] * world
+            dist.all_gather_object(allx, mine, group=peer_group)
+            self.plan.peer_attach(world, rank, [h for h, _ in allx], [o for _, o in allx])
+            dist.barrier(group=peer_group)
+            self.logf_full = self.plan.peer_logf()
+        else:
+            self.logf_full = torch.empty((N_total, K), dtype=torch.float64, device=dev)
         self.T = [torch.zeros((N_total, K), dtype=torch.float32, device=dev) for _ in range(2)]
         self.launches = 0
 
@@ -62,9 +79,14 @@ class CudaBackend:
         self.plan.mstep_finalize(); self.launches += 1
 
     def density(self, logf_local):
-        self.plan.density(self.bits, logf_local); self.launches += 1
+        if self.peer:   # stores into every rank's buffer and publishes the epoch: the all-gather, fused
+            self.plan.density_peers(self.bits, self.row_offset); self.launches += 2
+        else:
+            self.plan.density(self.bits, logf_local); self.launches += 1
 
     def sweep(self, T_old, T_new, beta_now):
+        if self.peer:
+            self.plan.peer_wait_densities(); self.launches += 1
         self.plan.sweep(self.N, self.logf_full, T_old, T_new, self.graph, beta_now, None); self.launches += 1
 
     def read_flags(self):
@@ -94,14 +116,14 @@ class ShardedEM:
 
     # -- exchange steps ------------------------------------------------------------------------------------------
     def _allreduce_stats(self):
-        if self.world == 1:
+        if self.world == 1 or getattr(self.b, "peer", False):   # peer mode: fused into nemb200_mstep_finalize
             return
         import torch.distributed as dist
         for t in self.b.stats():
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def _allgather_logf(self):
-        if self.world == 1:
+        if self.world == 1 or getattr(self.b, "peer", False):   # peer mode: fused into the density kernel
             return
         import torch
         import torch.distributed as dist
