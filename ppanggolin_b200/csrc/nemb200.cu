@@ -561,13 +561,31 @@ extern "C" int nemb200_density_peers(nemb200_plan* pl, const uint32_t* bits, int
   cudaStream_t st = (cudaStream_t)stream_;
   if (pl->N_local > 0) {
     if (!bits) return fail(NEMB200_ERR_ARG, "density_peers: null matrix");
-    PeerOut out;
-    out.n = pl->world; out.row_off = row_offset;
-    out.ptr[0] = pl->peer_logf[pl->rank];            // own buffer first
-    int q = 1;
-    for (int r = 0; r < pl->world; r++) if (r != pl->rank) out.ptr[q++] = pl->peer_logf[r];
-    int rc = density_to(pl, bits, out, st);
+    // densities into this rank's own buffer at full streaming speed, then one wide push of the shard to every peer
+    PeerOut own;
+    own.n = 1; own.row_off = row_offset; own.ptr[0] = pl->logf_full;
+    int rc = density_to(pl, bits, own, st);
     if (rc) return rc;
+    if (pl->world > 1) {
+      PeerOut out;
+      out.n = pl->world; out.ptr[0] = pl->logf_full;
+      int q = 1;
+      for (int r = 0; r < pl->world; r++) if (r != pl->rank) out.ptr[q++] = pl->peer_logf[r];
+      long long first = row_offset * pl->K, count = pl->N_local * (long long)pl->K;   // the shard, in doubles
+      if (first & 1) {                                  // 16-byte stores need an even start: leading double on its own
+        PeerOut one = out;
+        one.row_off = first;
+        k_peer_broadcast<<<dim3(1, pl->world - 1), 32, 0, st>>>(pl->logf_full, one, 1);
+        CK(cudaGetLastError());
+        first += 1; count -= 1;
+      }
+      if (count > 0) {
+        out.row_off = first;
+        dim3 grid(std::max(1, std::min(32, (int)((count / 2 + 255) / 256))), pl->world - 1);
+        k_peer_broadcast<<<grid, 256, 0, st>>>(pl->logf_full, out, count);
+        CK(cudaGetLastError());
+      }
+    }
   }
   k_peer_signal<<<1, 32, 0, st>>>(pl->sig_ptrs, pl->world, 1, pl->rank, ++pl->epoch_dens);
   CK(cudaGetLastError());

@@ -77,6 +77,20 @@ struct PeerStats {          // where k_mstep_finalize reads: the statistic block
   int n;
 };
 
+// push this rank's freshly computed shard of log-densities (contiguous rows of its own buffer) into the same rows of
+// every peer's buffer: 16-byte coalesced peer stores, one peer per blockIdx.y
+__global__ void __launch_bounds__(256)
+k_peer_broadcast(const double* __restrict__ own, PeerOut out /*ptr[1..n-1] = peers*/, long long n_doubles /*shard size*/) {
+  const int peer = blockIdx.y + 1;
+  if (peer >= out.n) return;
+  const long long off = out.row_off;                  // in doubles, even (K * row_off rounded by the caller)
+  const double2* src = reinterpret_cast<const double2*>(own + off);
+  double2* dst = reinterpret_cast<double2*>(out.ptr[peer] + off);
+  const long long n2 = n_doubles / 2;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (long long)gridDim.x * blockDim.x) dst[t] = src[t];
+  if ((n_doubles & 1) && blockIdx.x == 0 && threadIdx.x == 0) out.ptr[peer][off + n_doubles - 1] = own[off + n_doubles - 1];
+}
+
 // every rank owns sig[2][kMaxPeers] ints: sig[phase][r] = last epoch rank r has completed for that phase
 __global__ void k_peer_signal(int* const* peer_sig /*[n] device pointers to the ranks' sig arrays*/, int n, int phase, int rank,
                               int epoch) {
@@ -768,9 +782,17 @@ k_mstep_finalize(Params P, PeerStats ps, long long N_total, double* __restrict__
     float m = 0.0f;
     double iner = 0.0;
     if (d < D) {
+      int ci[kMaxPeers];
+      double cf[kMaxPeers];
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; q++) {          // all peer loads in flight together, then added in rank order
+        ci[q] = 0; cf[q] = 0.0;
+        if (q < ps.n) { ci[q] = ps.iblock[q][(size_t)k * Dpad + d]; cf[q] = ps.dblock[q][(size_t)k * Dpad + d]; }
+      }
       long long c_i = 0;
       double c_f = 0.0;
-      for (int q = 0; q < ps.n; q++) { c_i += ps.iblock[q][(size_t)k * Dpad + d]; c_f += ps.dblock[q][(size_t)k * Dpad + d]; }
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; q++) { c_i += ci[q]; c_f += cf[q]; }
       const double s1 = (double)c_i + c_f;
       const double s0 = nk - s1;
       if (s1 > s0) { m = 1.0f; iner = s0; }
