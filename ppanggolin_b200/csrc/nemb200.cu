@@ -164,8 +164,10 @@ struct nemb200_plan {
   double* crit_partial = nullptr;
   double* crit4 = nullptr;
   int crit_blocks = 0;
-  float* crit_terms = nullptr;    // [N_local][K][2]  per-(row, class) D and G terms (reference-order accumulation)
-  double* crit_rows = nullptr;    // [N_local][2]     per-row log f_i and log z_i
+  float* crit_terms = nullptr;    // per-warp regions of compacted (d_ik, g_ik) terms (reference-order accumulation)
+  int* crit_counts = nullptr;     // [crit_blocks * 8] terms per region
+  int* crit_offsets = nullptr;    // [crit_blocks * 8 + 1]
+  float* crit_dense = nullptr;    // the regions' terms, contiguous and in order
   // run buffers of the whole-run drivers (nem_host / nem_device / batch); not used by the stepwise interface
   bool with_run_buffers = false;
   double* run_logf = nullptr;
@@ -197,7 +199,11 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   pl->crit_partial = ar.take<double>((size_t)pl->crit_blocks * 4); pl->crit4 = ar.take<double>(8);
   pl->sig = ar.take<int>(2 * kMaxPeers); pl->peer_err = ar.take<int>(1); pl->sig_ptrs = ar.take<int*>(kMaxPeers);
   if (pl->flags & NEMB200_PEER_EXCHANGE) pl->logf_full = ar.take<double>((size_t)pl->N_total * K);
-  pl->crit_terms = ar.take<float>((size_t)pl->N_total * K * 2); pl->crit_rows = ar.take<double>((size_t)pl->N_total * 2);  // the sweep and the criteria run over all rows, also on a shard's plan
+  // the sweep and the criteria run over all rows, also on a shard's plan; one region of ceil(N/warps) rows per warp
+  pl->crit_terms = ar.take<float>(((size_t)pl->N_total + (size_t)pl->crit_blocks * 8) * K * 2);
+  pl->crit_counts = ar.take<int>((size_t)pl->crit_blocks * 8);
+  pl->crit_offsets = ar.take<int>((size_t)pl->crit_blocks * 8 + 1);
+  pl->crit_dense = ar.take<float>(((size_t)pl->N_total * K + 64) * 2);
   if (pl->with_run_buffers) {
     pl->run_logf = ar.take<double>(N * K); pl->run_Ta = ar.take<float>(N * K); pl->run_Tb = ar.take<float>(N * K);
   }
@@ -653,16 +659,29 @@ static int criteria_enqueue(nemb200_plan* pl, int64_t N, const double* logf, con
   a.N = N; a.K = pl->K; a.logf = logf; a.pk = pl->P.pk; a.logpk32 = pl->P.logpk32; a.logpk64 = pl->P.logpk64; a.T = T;
   a.rowptr = rowptr; a.col = col; a.w = w; a.beta = beta; a.logspace = (pl->flags & NEMB200_EPI_LOGSPACE) ? 1 : 0;
   a.partial = pl->crit_partial;
-  a.terms = pl->crit_terms; a.rows = pl->crit_rows;
   if (N > pl->N_total) return fail(NEMB200_ERR_ARG, "criteria: N exceeds the plan's total row count");
-  k_criteria<<<pl->crit_blocks, 256, 0, st>>>(a);
+  const int n_warps = pl->crit_blocks * 8;
+  a.rows_per_warp = (N + n_warps - 1) / n_warps;
+  a.terms = a.logspace ? nullptr : (float2*)pl->crit_terms;
+  a.counts = a.logspace ? nullptr : pl->crit_counts;
+  const int GS = pl->K <= 4 ? 4 : (pl->K <= 8 ? 8 : (pl->K <= 16 ? 16 : 32));
+  if (GS == 4) k_criteria<4><<<pl->crit_blocks, 256, 0, st>>>(a);
+  else if (GS == 8) k_criteria<8><<<pl->crit_blocks, 256, 0, st>>>(a);
+  else if (GS == 16) k_criteria<16><<<pl->crit_blocks, 256, 0, st>>>(a);
+  else k_criteria<32><<<pl->crit_blocks, 256, 0, st>>>(a);
   CK(cudaGetLastError());
   if (a.logspace) {
-    k_crit_reduce<<<1, 32, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4);
+    k_crit_reduce<<<1, 32, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4, 0);
     CK(cudaGetLastError());
   } else {
-    const size_t smem = (size_t)kSeqRows * pl->K * 2 * sizeof(float) + (size_t)kSeqRows * 2 * sizeof(double);
-    k_crit_seq<<<1, kSeqTpb, smem, st>>>(pl->crit_terms, pl->crit_rows, N, pl->K, pl->crit4);
+    k_crit_reduce<<<1, 32, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4, 2);       // L, Z: fp64 sums
+    CK(cudaGetLastError());
+    k_crit_offsets<<<1, 32, 0, st>>>(pl->crit_counts, n_warps, pl->crit_offsets);
+    CK(cudaGetLastError());
+    k_crit_compact<<<(n_warps + 7) / 8, 256, 0, st>>>((const float2*)pl->crit_terms, pl->crit_counts, pl->crit_offsets, n_warps,
+                                                    a.rows_per_warp, pl->K, (float2*)pl->crit_dense);
+    CK(cudaGetLastError());
+    k_crit_chain<<<1, 64, 0, st>>>((const float2*)pl->crit_dense, pl->crit_offsets, n_warps, pl->crit4);  // D, G
     CK(cudaGetLastError());
   }
   return 0;

@@ -921,7 +921,15 @@ __global__ void k_init_params(Params P, float base_prop, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Criteria (nem_alg.c:2764-2843).  One warp per row, lane k = class k; per-block partial sums, reduced by k_crit_reduce.
+// Criteria (nem_alg.c:2764-2843), once per run.
+//
+// k_criteria<GS>: every warp owns a contiguous range of rows and walks it 32/GS rows at a time (a group of GS lanes per
+// row, lane = class).  L = sum log f_i and Z = -sum log z_i are summed in fp64 (per-block partials -> k_crit_reduce).
+// D and G are the two criteria PPanGGOLiN's "log-likelihood" M is made of, and the reference accumulates them in
+// float32, sequentially over rows then classes (nem_alg.c:2813-2823): at N = 20 000 that rounding alone moves M by
+// 2e-5 relative (measured with the oracle), more than the parity bar.  In reference-arithmetic mode each warp therefore
+// also writes its non-zero (d_ik, g_ik) terms, in (row, class) order, into its own region (adding 0.0f is the identity, so
+// the zero terms -- all but about one per row -- can be dropped), and k_crit_chain re-adds the regions in order.
 // ------------------------------------------------------------------------------------------------------------------
 struct CritArgs {
   long long N;
@@ -936,27 +944,37 @@ struct CritArgs {
   const float* w;
   float beta;
   int logspace;
-  double* partial;  // [gridDim.x][4]  D, G, L, Z
-  float* terms;     // reference arithmetic: [N][K][2] per-(row, class) D and G terms ...
-  double* rows;     // ... and [N][2] per-row log f_i, log z_i, accumulated in the reference's order by k_crit_seq
+  double* partial;   // [gridDim.x][4]  D, G, L, Z
+  float2* terms;     // reference arithmetic: per-warp regions of compacted (d_ik, g_ik), region w at w * rows_per_warp * K
+  int* counts;       // [total warps] terms in each region
+  long long rows_per_warp;
 };
 
+template <int GS>
 __global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
   __shared__ double s_part[8][4];
+  constexpr int RPW = 32 / GS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = lane & (GS - 1), grp = lane / GS;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int K = a.K;
-  const int k = lane < K ? lane : K - 1;
+  const int k = sub < K ? sub : K - 1;
+  const long long row_lo = warp_global * a.rows_per_warp;
+  const long long row_hi = min(a.N, row_lo + a.rows_per_warp);
+  float2* region = a.terms ? a.terms + (size_t)row_lo * K : nullptr;
+  int cnt = 0;
   double accD = 0, accG = 0, accL = 0, accZ = 0;
-  for (long long i = warp_global; i < a.N; i += nwarps) {
-    const float cik = a.T[(size_t)i * K + k];
+  for (long long i0 = row_lo; i0 < row_hi; i0 += RPW) {
+    const long long i = i0 + grp;
+    const bool valid = i < row_hi;
+    const long long ii = valid ? i : row_lo;
+    const float cik = a.T[(size_t)ii * K + k];
     float pik = 0.0f;
-    if (a.rowptr != nullptr) {
-      const int n0 = a.rowptr[i], n1 = a.rowptr[i + 1];
+    if (valid && a.rowptr != nullptr) {
+      const int n0 = a.rowptr[ii], n1 = a.rowptr[ii + 1];
       for (int n = n0; n < n1; n++) pik = __fadd_rn(pik, __fmul_rn(a.w[n], a.T[(size_t)a.col[n] * K + k]));
     }
-    const double lf = a.logf[(size_t)i * K + k];
+    const double lf = a.logf[(size_t)ii * K + k];
     double dik = 0.0, gik = 0.0, term_l, zterm;
     if (!a.logspace) {
       const float lf32 = (lf == -INFINITY) ? -FLT_MAX : (float)lf;
@@ -978,41 +996,49 @@ __global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
       term_l = av;
       zterm = exp((double)a.beta * (double)pik);
     }
-    if (lane >= K) { dik = 0; gik = 0; zterm = 0; term_l = a.logspace ? -INFINITY : 0.0; }
+    if (sub >= K || !valid) { dik = 0; gik = 0; zterm = 0; term_l = a.logspace ? -INFINITY : 0.0; }
     double rowD = 0, rowG = 0, rowL, rowZ;
     if (!a.logspace) {
       double fi = 0.0;
       float zi = 0.0f;
       for (int kk = 0; kk < K; kk++) {
-        fi = fi + __shfl_sync(0xffffffffu, term_l, kk);
-        zi = (float)((double)zi + __shfl_sync(0xffffffffu, zterm, kk));
-        rowD += __shfl_sync(0xffffffffu, dik, kk);
-        rowG += __shfl_sync(0xffffffffu, gik, kk);
+        fi = fi + __shfl_sync(0xffffffffu, term_l, kk, GS);
+        zi = (float)((double)zi + __shfl_sync(0xffffffffu, zterm, kk, GS));
+        rowD += __shfl_sync(0xffffffffu, dik, kk, GS);
+        rowG += __shfl_sync(0xffffffffu, gik, kk, GS);
       }
       rowL = log(fi);
       rowZ = -log((double)zi);
+      if (region != nullptr) {      // ordered compaction of the non-zero terms: lanes are in (row, class) order
+        const bool nz = valid && sub < K && (dik != 0.0 || gik != 0.0);
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (nz) region[cnt + __popc(m & ((1u << lane) - 1u))] = make_float2((float)dik, (float)gik);
+        cnt += __popc(m);
+      }
     } else {
       double m = term_l;
-      for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-      double s = 0.0, zi = 0.0;
-      const double e = (lane < K && m > -INFINITY) ? exp(term_l - m) : 0.0;
+#pragma unroll
+      for (int off = GS >> 1; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off, GS));
+      double sum = 0.0, zi = 0.0;
+      const double e = (sub < K && valid && m > -INFINITY) ? exp(term_l - m) : 0.0;
       for (int kk = 0; kk < K; kk++) {
-        s += __shfl_sync(0xffffffffu, e, kk);
-        zi += __shfl_sync(0xffffffffu, zterm, kk);
-        rowD += __shfl_sync(0xffffffffu, dik, kk);
-        rowG += __shfl_sync(0xffffffffu, gik, kk);
+        sum += __shfl_sync(0xffffffffu, e, kk, GS);
+        zi += __shfl_sync(0xffffffffu, zterm, kk, GS);
+        rowD += __shfl_sync(0xffffffffu, dik, kk, GS);
+        rowG += __shfl_sync(0xffffffffu, gik, kk, GS);
       }
-      rowL = (m > -INFINITY) ? m + log(s) : -INFINITY;
+      rowL = (m > -INFINITY) ? m + log(sum) : -INFINITY;
       rowZ = -log(zi);
     }
-    accD += rowD; accG += rowG; accL += rowL; accZ += rowZ;
-    if (!a.logspace) {
-      if (lane < K) {
-        a.terms[((size_t)i * K + lane) * 2 + 0] = (float)dik;   // dik / gik already hold float32 values
-        a.terms[((size_t)i * K + lane) * 2 + 1] = (float)gik;
-      }
-      if (lane == 0) { a.rows[(size_t)i * 2 + 0] = rowL; a.rows[(size_t)i * 2 + 1] = -rowZ; }
-    }
+    if (valid && sub == 0) { accD += rowD; accG += rowG; accL += rowL; accZ += rowZ; }
+  }
+  if (a.counts != nullptr && lane == 0) a.counts[warp_global] = cnt;
+  // the group leaders' partial sums -> warp -> block (fixed order)
+  for (int off = 16; off > 0; off >>= 1) {
+    accD += __shfl_xor_sync(0xffffffffu, accD, off);
+    accG += __shfl_xor_sync(0xffffffffu, accG, off);
+    accL += __shfl_xor_sync(0xffffffffu, accL, off);
+    accZ += __shfl_xor_sync(0xffffffffu, accZ, off);
   }
   if (lane == 0) { s_part[wid][0] = accD; s_part[wid][1] = accG; s_part[wid][2] = accL; s_part[wid][3] = accZ; }
   __syncthreads();
@@ -1023,73 +1049,61 @@ __global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
   }
 }
 
-// The reference accumulates D, G, L and Z in float32, sequentially over rows then classes (nem_alg.c:2788-2828).  At
-// N = 20 000 that rounding alone moves M by 2e-5 relative (measured with the oracle), more than the parity bar, so the
-// four sums are re-accumulated in exactly that order.  Adding 0.0f is the identity, and most (row, class) terms are
-// exactly zero (one-hot posteriors), so each tile is first compacted in order by the whole CTA (ballot + prefix), then
-// four threads in four different warps run the four dependent chains concurrently.
-constexpr int kSeqRows = 128;
-constexpr int kSeqTpb = 256;
-__global__ void __launch_bounds__(kSeqTpb)
-k_crit_seq(const float* __restrict__ terms, const double* __restrict__ rows, long long N, int K, double* __restrict__ out4) {
-  extern __shared__ float s_seq[];                       // sD[kSeqRows*K], sG[kSeqRows*K], then [kSeqRows*2] doubles
-  float* sD = s_seq;
-  float* sG = s_seq + (size_t)kSeqRows * K;
-  double* s_rows = reinterpret_cast<double*>(s_seq + (size_t)kSeqRows * K * 2);
-  __shared__ int s_wcnt[kSeqTpb / 32];
-  __shared__ int s_total;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const float2* terms2 = reinterpret_cast<const float2*>(terms);
-  float acc = 0.0f;                                      // thread 0: D, 32: G, 64: L, 96: Z
-  for (long long r0 = 0; r0 < N; r0 += kSeqRows) {
-    const int nr = (int)min((long long)kSeqRows, N - r0);
-    const int n = nr * K;
-    __syncthreads();
-    if (tid == 0) s_total = 0;
-    __syncthreads();
-    for (int c0 = 0; c0 < n; c0 += kSeqTpb) {           // ordered compaction of the non-zero (D, G) terms
-      const int t = c0 + tid;
-      float2 v = make_float2(0.0f, 0.0f);
-      if (t < n) v = terms2[(size_t)r0 * K + t];
-      const bool nz = (v.x != 0.0f) || (v.y != 0.0f);
-      const unsigned m = __ballot_sync(0xffffffffu, nz);
-      if (lane == 0) s_wcnt[wid] = __popc(m);
-      __syncthreads();
-      int off = s_total;
-      for (int q = 0; q < wid; q++) off += s_wcnt[q];
-      if (nz) { const int pos = off + __popc(m & ((1u << lane) - 1u)); sD[pos] = v.x; sG[pos] = v.y; }
-      __syncthreads();
-      if (tid == 0) { int tot = s_total; for (int q = 0; q < kSeqTpb / 32; q++) tot += s_wcnt[q]; s_total = tot; }
-      __syncthreads();
+// exclusive prefix sum of the region counts (one warp; a few thousand regions)
+__global__ void __launch_bounds__(32) k_crit_offsets(const int* __restrict__ counts, int n, int* __restrict__ offsets /*[n+1]*/) {
+  const int lane = threadIdx.x;
+  int carry = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int v = base + lane < n ? counts[base + lane] : 0;
+    int incl = v;
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
     }
-    for (int t = tid; t < nr * 2; t += kSeqTpb) s_rows[t] = rows[(size_t)r0 * 2 + t];
-    __syncthreads();
-    const int cnt = s_total;
-    if (tid == 0 || tid == 32) {
-      const float* src = tid == 0 ? sD : sG;
-      int t = 0;
-      for (; t + 8 <= cnt; t += 8) {                     // loads first (independent), then the dependent chain of adds
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = src[t + q];
-#pragma unroll
-        for (int q = 0; q < 8; q++) acc = __fadd_rn(acc, v[q]);
-      }
-      for (; t < cnt; t++) acc = __fadd_rn(acc, src[t]);
-    } else if (tid == 64) {
-      for (int r = 0; r < nr; r++) acc = (float)((double)acc + s_rows[2 * r]);        // L = L + log(fi)
-    } else if (tid == 96) {
-      for (int r = 0; r < nr; r++) acc = (float)((double)acc - s_rows[2 * r + 1]);    // Z = Z - log(zi)
-    }
+    if (base + lane < n) offsets[base + lane] = carry + incl - v;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
   }
-  if (tid == 0) out4[0] = (double)acc;
-  if (tid == 32) out4[1] = (double)acc;
-  if (tid == 64) out4[2] = (double)acc;
-  if (tid == 96) out4[3] = (double)acc;
+  if (lane == 0) offsets[n] = carry;
 }
 
-__global__ void k_crit_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ out4) {
-  if (threadIdx.x < 4 && blockIdx.x == 0) {
+// regions -> one dense array, order preserved (one warp per region)
+__global__ void __launch_bounds__(256)
+k_crit_compact(const float2* __restrict__ terms, const int* __restrict__ counts, const int* __restrict__ offsets, int n_regions,
+               long long rows_per_warp, int K, float2* __restrict__ dense) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_regions) return;
+  const int lane = threadIdx.x & 31;
+  const int n = counts[r];
+  const float2* src = terms + (size_t)r * rows_per_warp * K;
+  float2* dst = dense + offsets[r];
+  for (int t = lane; t < n; t += 32) dst[t] = src[t];
+}
+
+// D (warp 0) and G (warp 1) re-accumulated in float32 in the reference's order.  The warp loads 32 terms at a time
+// (coalesced, one block ahead of the adds) and hands them to the dependent chain of adds through shuffles.
+__global__ void __launch_bounds__(64)
+k_crit_chain(const float2* __restrict__ dense, const int* __restrict__ offsets, int n_regions, double* __restrict__ out4) {
+  const int lane = threadIdx.x & 31, which = threadIdx.x >> 5;   // 0: D, 1: G
+  const int total = offsets[n_regions];
+  auto fetch = [&](int t) -> float {
+    if (t < total) { const float2 v = dense[t]; return which == 0 ? v.x : v.y; }
+    return 0.0f;
+  };
+  float acc = 0.0f;
+  float x = fetch(lane), x1 = fetch(32 + lane);
+  for (int t0 = 0; t0 < total; t0 += 32) {
+    const float x2 = fetch(t0 + 64 + lane);       // two blocks ahead of the chain
+    // terms past `total` were fetched as 0.0f: adding them is the identity
+#pragma unroll
+    for (int q = 0; q < 32; q++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x, q));
+    x = x1; x1 = x2;
+  }
+  if (lane == 0) out4[which] = (double)acc;
+}
+
+__global__ void k_crit_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ out4, int first) {
+  // out4[first..3] = fp64 sums of the block partials (first = 0: all four; first = 2: only L and Z)
+  if (threadIdx.x < 4 && (int)threadIdx.x >= first && blockIdx.x == 0) {
     double t = 0.0;
     for (int b = 0; b < nblocks; b++) t += partial[(size_t)b * 4 + threadIdx.x];
     out4[threadIdx.x] = t;

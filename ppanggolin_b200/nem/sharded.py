@@ -76,11 +76,11 @@ class CudaBackend:
         return self.plan.stats_blocks()   # two contiguous blocks: int32 counts + class sizes, fp64 fuzzy sums + sizes
 
     def finalize(self):
-        self.plan.mstep_finalize(); self.launches += 1
+        self.plan.mstep_finalize(); self.launches += 3 if self.peer else 1   # peer mode: + signal + wait kernels
 
     def density(self, logf_local):
         if self.peer:   # stores into every rank's buffer and publishes the epoch: the all-gather, fused
-            self.plan.density_peers(self.bits, self.row_offset); self.launches += 2
+            self.plan.density_peers(self.bits, self.row_offset); self.launches += 3   # density + shard push + signal
         else:
             self.plan.density(self.bits, logf_local); self.launches += 1
 
