@@ -447,7 +447,7 @@ static int group_lanes(int units) {  // lanes cooperating on one row: smallest p
 }
 
 template <int KB, int KX>
-static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, const PeerOut& out, cudaStream_t st) {
+static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
   constexpr int RB = KB <= 4 ? 4 : (KB <= 8 ? 2 : 1);  // rows per lane group: bounded by registers (2 * RB * KB + 4 * RB)
   const int W4 = pl->Ws / 4;
   const int G = group_lanes(W4);
@@ -464,11 +464,11 @@ static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, const PeerO
   if (blocks < 1) blocks = 1;
   kern<<<(unsigned)blocks, kDensTpb, in_smem ? smem : 0, st>>>((const uint4*)bits, pl->N_local, W4, pl->K, G,
                                                           (const uint4*)pl->P.m1, (const uint4*)pl->P.valid, pl->P.L,
-                                                          pl->P.B, pl->P.has_half, out, in_smem);
+                                                          pl->P.B, pl->P.has_half, logf, in_smem);
   CK(cudaGetLastError());
   return 0;
 }
-static int dispatch_density_sk(nemb200_plan* pl, const uint32_t* bits, const PeerOut& logf, cudaStream_t st) {
+static int dispatch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
   switch (pl->K) {  // exact-K kernels for the common small K (no per-class predicates), buckets above
     case 1: case 2: return launch_density_sk<2, 0>(pl, bits, logf, st);
     case 3: return launch_density_sk<3, 3>(pl, bits, logf, st);
@@ -485,7 +485,7 @@ static int dispatch_density_sk(nemb200_plan* pl, const uint32_t* bits, const Pee
   return launch_density_sk<32, 0>(pl, bits, logf, st);
 }
 template <int KB>
-static int launch_density_skd(nemb200_plan* pl, const uint32_t* bits, const PeerOut& logf, cudaStream_t st) {
+static int launch_density_skd(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
   const int G = group_lanes(pl->Ws);
   const long long rows_per_block = (long long)(256 / 32) * (32 / G);
   long long blocks = (pl->N_local + rows_per_block - 1) / rows_per_block;
@@ -498,17 +498,15 @@ static int launch_density_skd(nemb200_plan* pl, const uint32_t* bits, const Peer
   return 0;
 }
 
-static int density_to(nemb200_plan* pl, const uint32_t* bits, const PeerOut& out, cudaStream_t st) {
-  if (pl->free_disp) return DISPATCH_KB(pl->K, launch_density_skd, pl, bits, out, st);
-  return dispatch_density_sk(pl, bits, out, st);
+static int density_to(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
+  if (pl->free_disp) return DISPATCH_KB(pl->K, launch_density_skd, pl, bits, logf, st);
+  return dispatch_density_sk(pl, bits, logf, st);
 }
 
 extern "C" int nemb200_density(nemb200_plan* pl, const uint32_t* bits, double* logf, void* stream_) {
   if (!pl || (pl->N_local > 0 && (!bits || !logf))) return fail(NEMB200_ERR_ARG, "density: null argument");
   if (pl->N_local == 0) return NEMB200_OK;
-  PeerOut out;
-  out.n = 1; out.ptr[0] = logf; out.row_off = 0;
-  return density_to(pl, bits, out, (cudaStream_t)stream_);
+  return density_to(pl, bits, logf, (cudaStream_t)stream_);
 }
 
 // ---- row-sharded exchange over peer memory -------------------------------------------------------------------------
@@ -568,9 +566,7 @@ extern "C" int nemb200_density_peers(nemb200_plan* pl, const uint32_t* bits, int
   if (pl->N_local > 0) {
     if (!bits) return fail(NEMB200_ERR_ARG, "density_peers: null matrix");
     // densities into this rank's own buffer at full streaming speed, then one wide push of the shard to every peer
-    PeerOut own;
-    own.n = 1; own.row_off = row_offset; own.ptr[0] = pl->logf_full;
-    int rc = density_to(pl, bits, own, st);
+    int rc = density_to(pl, bits, pl->logf_full + (size_t)row_offset * pl->K, st);
     if (rc) return rc;
     if (pl->world > 1) {
       PeerOut out;
@@ -634,7 +630,7 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
     if (per_sm < 1) return fail(NEMB200_ERR_CUDA, "sweep: kernel does not fit on an SM");
-    long long blocks = (long long)num_sms() * std::min(per_sm, 4);
+    long long blocks = (long long)num_sms() * per_sm;   // every resident slot: fewer passes per level
     const long long want = (N + rows_per_block - 1) / rows_per_block;
     if (blocks > want) blocks = std::max<long long>(want, 1);
     void* args[] = {&a};

@@ -59,14 +59,14 @@ struct Params {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Row-sharded multi-GPU exchange over NVLink peer memory (no collective library on the data path):
-//  * the density kernels store every log-density row straight into the logf buffer of EVERY rank (peer stores), which
-//    is the all-gather the replicated Gauss-Seidel sweep needs, fused into the producing kernel;
+//  * k_peer_broadcast pushes the shard of log-densities a rank has just computed into the logf buffer of EVERY rank
+//    (16-byte peer stores), which is the all-gather the replicated Gauss-Seidel sweep needs;
 //  * k_mstep_finalize reads the column statistics of every rank (peer loads) and adds them in rank order, which is the
 //    all-reduce of the M-step, fused into the consuming kernel (same order on every rank -> identical parameters);
 //  * k_peer_signal / k_peer_wait are the two tiny flag barriers per iteration that order those accesses.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
-struct PeerOut {            // where a density kernel writes: n buffers (own + peers), rows shifted by row_off
+struct PeerOut {            // k_peer_broadcast: ptr[1..n-1] = the peers' buffers; row_off = first double of the shard
   double* ptr[kMaxPeers];
   int n;
   long long row_off;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint
 template <int KB, int KX, int RB, bool HALF, typename PlanePtr>
 __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, long long N, int W4, int Krt, int G,
                                                 PlanePtr m1, PlanePtr valid, const double* __restrict__ L,
-                                                const double* __restrict__ B, const PeerOut& out) {
+                                                const double* __restrict__ B, double* __restrict__ logf) {
   const int K = KX > 0 ? KX : Krt;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
@@ -210,9 +210,7 @@ __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, 
           if (r0 + r < N) {
             // e_k <= 1e-20: L = +inf; a mismatch gives the reference's null density (nem_mod.c:663-665, :684-685)
             const double v = (h[r][k] == 0) ? Bk : (Bk - (double)h[r][k] * Lk);
-            const size_t o = (size_t)(out.row_off + r0 + r) * K + k;
-            out.ptr[0][o] = v;
-            for (int q = 1; q < out.n; q++) out.ptr[q][o] = v;      // peer stores over NVLink (row-sharded runs)
+            logf[(r0 + r) * K + k] = v;
           }
         }
       }
@@ -226,7 +224,7 @@ template <int KB, int KX, int RB>
 __global__ void __launch_bounds__(kDensTpb)
 k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
              const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
-             const int* __restrict__ has_half, PeerOut out, int planes_in_smem) {
+             const int* __restrict__ has_half, double* __restrict__ logf, int planes_in_smem) {
   extern __shared__ uint4 smem4[];
   const bool half = (*has_half != 0);   // any centre at 0.5 (exact median tie): needs the `valid` plane
   if (planes_in_smem) {
@@ -238,11 +236,11 @@ k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, 
     __syncthreads();
     const uint4* sm1 = smem4;            // shared-memory pointers: LDS, not generic loads
     const uint4* sval = smem4 + n;
-    if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, sm1, sval, L, B, out);
-    else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, sm1, sval, L, B, out);
+    if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, sm1, sval, L, B, logf);
+    else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, sm1, sval, L, B, logf);
   } else {
-    if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, m1g, validg, L, B, out);
-    else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, m1g, validg, L, B, out);
+    if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, m1g, validg, L, B, logf);
+    else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, m1g, validg, L, B, logf);
   }
 }
 
@@ -252,7 +250,7 @@ template <int KB>
 __global__ void __launch_bounds__(256)
 k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int Dpad, int G,
               const uint32_t* __restrict__ m1, const uint32_t* __restrict__ valid, const double* __restrict__ Lkd,
-              const double* __restrict__ Lword, const double* __restrict__ B, PeerOut out) {
+              const double* __restrict__ Lword, const double* __restrict__ B, double* __restrict__ logf) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
   const int grp = lane / G;
@@ -302,11 +300,7 @@ k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int
     }
 #pragma unroll
     for (int k = 0; k < KB; k++)
-      if (k < K && (k & (G - 1)) == sub && row < N) {
-        const size_t o = (size_t)(out.row_off + row) * K + k;
-        const double v = B[k] - s[k];
-        for (int q = 0; q < out.n; q++) out.ptr[q][o] = v;
-      }
+      if (k < K && (k & (G - 1)) == sub && row < N) logf[row * K + k] = B[k] - s[k];
   }
 }
 
