@@ -65,35 +65,62 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region: NVML in-process (10 ms period, no subprocesses that could
+    disturb the run); falls back to polling nvidia-smi."""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.sm, self.reason_bits, self.max_mhz, self._halt = index, [], 0, None, threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                return i
+        return i
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self.sm.append(int(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM)))
+                    try:
+                        self.reason_bits |= int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        self.reason_bits |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self._halt.wait(0.01)
+                else:
+                    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.sm.append(int(out[0])); self.max_mhz = int(out[1]); self.reason_bits |= int(out[2].strip(), 16)
+                    self._halt.wait(0.2)
             except Exception:
-                pass
-            self._halt.wait(0.02)
+                self._halt.wait(0.05)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=3)
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        sm = sorted(self.sm)
+        reasons = [n for n, bit in self.REASONS.items() if self.reason_bits & bit]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def b_iter_bytes(N, D, K, nnz):
@@ -242,12 +269,12 @@ def run_ours(a):
             dist.barrier(group=group)
             torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()   # started before the warm-up so that the short timed region is covered by several samples
     for _ in range(a.warmup):
         em.iterate(beta)
     barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     be.launches = 0
     be.plan.timing(True)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
