@@ -627,14 +627,18 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
     a.level_ptr = sched_level_ptr; a.level_rows = sched_rows; a.n_levels = n_levels;
     void* fn = GS == 4 ? (void*)k_sweep<true, 4> : GS == 8 ? (void*)k_sweep<true, 8> : GS == 16 ? (void*)k_sweep<true, 16>
                                                                                              : (void*)k_sweep<true, 32>;
+    // few, fat CTAs: the grid barrier between levels is the fixed cost of this kernel (ncu: more than half of the
+    // warp samples sit in it with 592 CTAs of 256 threads), and its price grows with the number of arriving CTAs
+    const int tpb = 1024;
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, tpb, 0));
     if (per_sm < 1) return fail(NEMB200_ERR_CUDA, "sweep: kernel does not fit on an SM");
-    long long blocks = (long long)num_sms() * per_sm;   // every resident slot: fewer passes per level
-    const long long want = (N + rows_per_block - 1) / rows_per_block;
+    long long blocks = (long long)num_sms() * per_sm;
+    const long long rows_per_cta = (long long)(tpb / 32) * (32 / GS);
+    const long long want = (N + rows_per_cta - 1) / rows_per_cta;
     if (blocks > want) blocks = std::max<long long>(want, 1);
     void* args[] = {&a};
-    CK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(256), args, 0, st));
+    CK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(tpb), args, 0, st));
   } else {
     a.level_ptr = nullptr; a.level_rows = nullptr; a.n_levels = 1;
     long long blocks = (N + rows_per_block - 1) / rows_per_block;

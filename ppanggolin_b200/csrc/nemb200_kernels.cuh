@@ -384,7 +384,7 @@ __device__ __forceinline__ void sweep_row(const SweepArgs& a, long long i, bool 
 }
 
 template <bool COOP, int GS>
-__global__ void __launch_bounds__(256) k_sweep(SweepArgs a) {
+__global__ void __launch_bounds__(COOP ? 1024 : 256) k_sweep(SweepArgs a) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (GS - 1), grp = lane / GS;
   constexpr int RPW = 32 / GS;  // rows per warp
