@@ -179,8 +179,106 @@ def save_export_golden(ref_partition, pan):
     print("export golden", X.shape, ew, nb_fam)
 
 
+def gbff_layouts(gbff_dir="/root/reference/testingDataset/GBFF"):
+    """BASELINE config 1 surrogate: the Chlamydia trachomatis test genomes of the reference
+    (GenBank flat files), CDS order per replicon, families = clusters of identical protein translations.  The real
+    pipeline clusters with mmseqs2 (absent here), so the golden partition counts of expected_info_files/*.yaml do not
+    apply; parity is ours vs the reference on the SAME surrogate pangenome.  Returns per genome a list of contigs, each a
+    list of family ids in gene order."""
+    import gzip
+    import re
+    from pathlib import Path as _P
+    fam_of = {}
+    genomes = []
+    for f in sorted(_P(gbff_dir).glob("*.gbff.gz")):
+        contigs, cur, in_tr, tr = [], None, False, []
+        with gzip.open(f, "rt") as fh:
+            for line in fh:
+                if line.startswith("LOCUS"):
+                    cur = []
+                    contigs.append(cur)
+                elif in_tr:
+                    tr.append(line.strip())
+                    if line.rstrip().endswith('"'):
+                        in_tr = False
+                        seq = "".join(tr).strip('"').replace(" ", "")
+                        cur.append(fam_of.setdefault(seq, len(fam_of)))
+                elif "/translation=" in line:
+                    tr = [line.split("/translation=", 1)[1].strip()]
+                    if tr[0].count('"') == 2:
+                        seq = tr[0].strip('"')
+                        cur.append(fam_of.setdefault(seq, len(fam_of)))
+                    else:
+                        in_tr = True
+        genomes.append([c for c in contigs if len(c) > 0])
+    return genomes, len(fam_of)
+
+
+def build_reference_pangenome_contigs(genomes, n_fam):
+    """Like build_reference_pangenome, several circular contigs per genome (graph/makeGraph.py:114-136 semantics)."""
+    from ppanggolin.pangenome import Pangenome
+    from ppanggolin.genome import Organism, Contig, Gene
+    from ppanggolin.geneFamily import GeneFamily
+    pan = Pangenome()
+    fams = [GeneFamily(i, f"fam{i}") for i in range(n_fam)]
+    used = sorted(set(int(f) for g in genomes for c in g for f in c))
+    for i in used:
+        pan.add_gene_family(fams[i])
+    cid = 0
+    for g, contigs in enumerate(genomes):
+        org = Organism(f"org{g}")
+        pan.add_organism(org)
+        for ci, lay in enumerate(contigs):
+            ctg = Contig(cid, f"ctg{g}_{ci}", is_circular=True)
+            cid += 1
+            org.add(ctg)
+            genes = []
+            for pos, f in enumerate(lay):
+                gene = Gene(f"g{g}_{ci}_{pos}")
+                gene.fill_annotations(start=pos * 100 + 1, stop=pos * 100 + 90, strand="+", position=pos)
+                gene.fill_parents(org, ctg)
+                ctg.add(gene)
+                fams[int(f)].add(gene)
+                genes.append(gene)
+            prev = None
+            for gene in genes:
+                if prev is not None:
+                    pan.add_edge(gene, prev)
+                prev = gene
+            if prev is not None and len(genes) > 0:
+                pan.add_edge(genes[0], prev)
+    for k in ("genomesAnnotated", "genesClustered", "neighborsGraph"):
+        pan.status[k] = "Computed"
+    return pan
+
+
+def gbff_case(ref_partition):
+    """partition() of the reference on the GBFF-derived surrogate pangenome: defaults of `ppanggolin all` (auto K over
+    krange [3, 20], beta 2.5, max degree smoothing 10, chunk size 500, seed 42)."""
+    genomes, n_fam = gbff_layouts()
+    pan = build_reference_pangenome_contigs(genomes, n_fam)
+    ref_partition.samples = []
+    random.seed(1234)
+    kw = dict(kval=-1, chunk_size=500, beta=2.5, free_dispersion=False, krange=[3, 20])
+    with tempfile.TemporaryDirectory() as td:
+        ref_partition.partition(pan, output=Path(td), tmpdir=Path(td), cpu=8, disable_bar=True, seed=42, **kw)
+    labels = {fam.name: fam.partition for fam in pan.gene_families}
+    names = sorted(labels, key=lambda s: int(s[3:]))
+    params = pan.parameters["partition"]
+    flat = np.concatenate([np.asarray(c, np.int32) for g in genomes for c in g])
+    contig_ptr = np.cumsum([0] + [len(c) for g in genomes for c in g])
+    genome_ptr = np.cumsum([0] + [len(g) for g in genomes])          # in contigs
+    np.savez_compressed(OUT / "partition_gbff.npz", n_fam=n_fam, families=flat, contig_ptr=contig_ptr, genome_ptr=genome_ptr,
+                        fam_names=np.array(names), labels=np.array([labels[n] for n in names]), kwargs=json.dumps(kw),
+                        params=json.dumps(params))
+    from collections import Counter
+    print("gbff", len(genomes), "genomes", n_fam, "families", pan.number_of_edges, "edges",
+          Counter(v[0] if v else "?" for v in labels.values()), params)
+
+
 def partition_cases():
     ref_partition = import_reference_partition()
+    gbff_case(ref_partition)
     cases = [("fixedK", dict(n_fam=900, n_org=60, seed=21), dict(kval=3, chunk_size=500, beta=2.5, free_dispersion=False)),
              ("fixedK_fd", dict(n_fam=900, n_org=60, seed=21), dict(kval=3, chunk_size=500, beta=2.6, free_dispersion=True)),
              ("autoK", dict(n_fam=700, n_org=50, seed=22), dict(kval=-1, chunk_size=500, beta=2.5, free_dispersion=False, krange=[3, 12])),

@@ -96,3 +96,34 @@ def build_from_layouts(layouts, n_fam):
         pan.status[k] = "Computed"
     pan.status["partitioned"] = "No"
     return pan
+
+
+def build_from_contigs(genomes, n_fam):
+    """``genomes[g]`` = list of contigs, each the family ids along a circular contig."""
+    pan = Pangenome()
+    fams = [GeneFamily(f"fam{i}") for i in range(n_fam)]
+    used = set()
+    for g, contigs in enumerate(genomes):
+        org = Organism(f"org{g}")
+        pan._orgs[org.name] = org
+        for ci, lay in enumerate(contigs):
+            prev = None
+            first = None
+            for pos, f in enumerate(lay):
+                fam = fams[int(f)]
+                fam._orgs[org] = True
+                used.add(int(f))
+                gene = (g, ci, pos)
+                if prev is not None:
+                    pan.add_edge(fam, prev[0], org, (gene, prev[1]))
+                else:
+                    first = (fam, gene)
+                prev = (fam, gene)
+            if prev is not None and len(lay) > 0:
+                pan.add_edge(first[0], prev[0], org, (first[1], prev[1]))
+    for i in sorted(used):
+        pan._fams[fams[i].name] = fams[i]
+    for k in ("genomesAnnotated", "genesClustered", "neighborsGraph"):
+        pan.status[k] = "Computed"
+    pan.status["partitioned"] = "No"
+    return pan

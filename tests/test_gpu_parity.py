@@ -386,3 +386,32 @@ def test_file_based_nem_entry_point(eng, name, tmp_path):
         ruf = (ref_dir / f"nem_file_{g['K']}.uf").read_text().splitlines()
         uf = (tmp_path / f"nem_file_{g['K']}.uf").read_text().splitlines()
         assert len(ruf) == len(uf) and np.mean([a == b for a, b in zip(ruf, uf)]) >= 0.99
+
+
+def test_partition_on_reference_genomes(eng, tmp_path):
+    """BASELINE config 1 (surrogate): the reference's Chlamydia trachomatis GenBank genomes, families =
+    identical translations, graph by gene order; `partition()` with the defaults of `ppanggolin all` (auto K in 3..20).
+    The strict clustering makes the reference choose K = 19 here -- nineteen nearly identical shell classes -- so the
+    test asks for the partition letter (persistent / shell / cloud) of >= 99.9 % of the families and for a chosen K
+    within one of the reference's."""
+    import random
+    from collections import Counter
+    import minipan
+    from goldens import load_partition_gbff
+    from ppanggolin_b200.nem import partition as part
+    g = load_partition_gbff()
+    pan = minipan.build_from_contigs(g["genomes"], g["n_fam"])
+    random.seed(1234)
+    part.partition(pan, output=tmp_path, tmpdir=tmp_path, cpu=1, disable_bar=True, seed=42, **g["kwargs"])
+    ours = {f.name: f.partition for f in pan.gene_families}
+    ref = dict(zip(g["fam_names"], g["labels"]))
+    assert sorted(ours) == sorted(ref)
+    letters = np.mean([ours[n][:1] == ref[n][:1] for n in ref])
+    exact = np.mean([ours[n] == ref[n] for n in ref])
+    k_ours, k_ref = pan.parameters["partition"]["# final nb of partitions"], g["params"]["# final nb of partitions"]
+    print("gbff surrogate: K", k_ours, "vs", k_ref, "letters", letters, "exact labels", exact,
+          Counter(v[:1] for v in ours.values()), Counter(v[:1] for v in ref.values()))
+    assert abs(k_ours - k_ref) <= 1
+    assert letters >= 0.999
+    if k_ours == k_ref:
+        assert exact >= 0.99
