@@ -1,0 +1,209 @@
+#!/usr/bin/env python3
+"""Second caller of the NEM API: rarefaction (SURVEY.md section 8(f)-2;
+/root/reference/ppanggolin/nem/rarefaction.py:36-203 ``raref_nem`` / ``launch_raref_nem``, :538-724
+``make_rarefaction_curve``).
+
+Same names, arguments and results for the partitioning part: genome samples of growing size, per sample the exact /
+soft core and accessory counts and the NEM partition counts, written to ``rarefaction.csv`` with the reference's
+columns (rarefaction.py:214-252).  Differences, all below the API:
+
+* no fork pool (rarefaction.py:707): a CUDA context does not survive ``fork``; samples run one after the other, each
+  instance derived from the cached array form of the pangenome (``export_arrays``) and run through the C ABI;
+* the per-sample core / soft-core statistics use the presence tensor (column gather + row sums) instead of gmpy2
+  bitarrays (rarefaction.py:657-684) -- same integer counts;
+* the Heaps'-law fit and the plotly figures (``draw_curve``, rarefaction.py:254-535) are not part of the hot path: the
+  CSV is written, the fit and the HTML are produced only when scipy / plotly are importable (``draw_curve``).
+"""
+from __future__ import annotations
+
+import logging
+import random
+import tempfile
+from collections import Counter
+from pathlib import Path
+from typing import Dict, List, Tuple, Union
+
+from . import partition as ppp
+
+samples: List[set] = []
+
+CSV_COLUMNS = ["genomes_count", "persistent", "shell", "cloud", "undefined", "exact_core", "exact_accessory", "soft_core",
+               "soft_accessory", "pangenome", "K"]
+
+
+def raref_nem(index: int, tmpdir: Path, beta: float = 2.5, sm_degree: int = 10, free_dispersion: bool = False,
+              chunk_size: int = 500, kval: int = -1, krange: list = None, seed: int = 42) -> Tuple[Dict[str, int], int]:
+    """rarefaction.py:36-189: partition counts of sample ``index`` (chunked voting when the sample exceeds chunk_size)."""
+    samp = samples[index]
+    currtmpdir = Path(tmpdir) / f"{str(index)}"
+    kmm = [3, 20] if krange is None else krange
+    if kval < 3:
+        kval = ppp.evaluate_nb_partitions(organisms=samp, sm_degree=sm_degree, free_dispersion=free_dispersion,
+                                          chunk_size=chunk_size, krange=kmm, seed=seed, tmpdir=Path(tmpdir) / f"{str(index)}_eval")
+    if len(samp) <= chunk_size:
+        edges_weight, nb_fam = ppp.write_nem_input_files(tmpdir=currtmpdir, organisms=set(samp), sm_degree=sm_degree)
+        try:
+            cpt_partition = ppp.run_partitioning(currtmpdir, len(samp), beta * (nb_fam / edges_weight), free_dispersion,
+                                                 kval=kval, seed=seed, init="param_file")[0]
+        finally:
+            ppp.export.release(currtmpdir)
+    else:
+        families = set()
+        cpt_partition = {}
+        validated = set()
+        cpt = 0
+
+        def validate_family(result):   # rarefaction.py:100-122
+            for node, nem_class in result[0].items():
+                cpt_partition[node][nem_class[0]] += 1
+                sum_partitioning = sum(cpt_partition[node].values())
+                if (sum_partitioning > len(samp) / chunk_size and max(cpt_partition[node].values()) >= sum_partitioning * 0.5) \
+                        or (sum_partitioning > len(samp)):
+                    if node not in validated:
+                        if max(cpt_partition[node].values()) < sum_partitioning * 0.5:
+                            cpt_partition[node]["U"] = len(samp)
+                        validated.add(node)
+
+        for fam in ppp.pan.gene_families:
+            if not samp.isdisjoint(set(fam.organisms)):
+                families.add(fam)
+                cpt_partition[fam.name] = {"P": 0, "S": 0, "C": 0, "U": 0}
+        org_nb_sample = Counter()
+        for org in samp:
+            org_nb_sample[org] = 0
+        condition = len(samp) / chunk_size
+        while len(validated) < len(families):
+            org_samples = []
+            while not all(val >= condition for val in org_nb_sample.values()):
+                shuffled_orgs = list(samp)
+                random.shuffle(shuffled_orgs)
+                while len(shuffled_orgs) > chunk_size:
+                    org_samples.append(set(shuffled_orgs[:chunk_size]))
+                    for org in org_samples[-1]:
+                        org_nb_sample[org] += 1
+                    shuffled_orgs = shuffled_orgs[chunk_size:]
+            for sub in org_samples:
+                d = currtmpdir / f"{str(cpt)}"
+                edges_weight, nb_fam = ppp.write_nem_input_files(d, sub, sm_degree=sm_degree)
+                try:
+                    validate_family(ppp.run_partitioning(d, len(sub), beta * (nb_fam / edges_weight), free_dispersion,
+                                                         kval=kval, seed=seed, init="param_file"))
+                finally:
+                    ppp.export.release(d)
+                cpt += 1
+            condition += 1   # the reference loops forever if one pass does not validate every family; draw more instead
+    if len(cpt_partition) == 0:
+        counts = {"persistent": "NA", "shell": "NA", "cloud": "NA", "undefined": "NA", "K": kval}
+    else:
+        counts = {"persistent": 0, "shell": 0, "cloud": 0, "undefined": 0, "K": kval}
+        for val in cpt_partition.values():
+            part = val if isinstance(val, str) else max(val, key=val.get)
+            if part.startswith("P"):
+                counts["persistent"] += 1
+            elif part.startswith("C"):
+                counts["cloud"] += 1
+            elif part.startswith("S"):
+                counts["shell"] += 1
+            else:
+                counts["undefined"] += 1
+    return counts, index
+
+
+def launch_raref_nem(args) -> Tuple[Dict[str, int], int]:
+    """rarefaction.py:192-203"""
+    return raref_nem(*args)
+
+
+def sample_family_stats(arrays, all_samples: List[set], soft_core: float = 0.95) -> List[Counter]:
+    """rarefaction.py:657-684 on the presence tensor: per sample, families present in all / in >= soft_core of the
+    sample's genomes (exact / soft core) and the others that occur at least once (exact / soft accessory)."""
+    import torch
+    out = []
+    for samp in all_samples:
+        cols = torch.tensor(sorted(arrays.org_index[o] for o in samp), dtype=torch.long, device=arrays.device)
+        nb = arrays.presence.index_select(1, cols).sum(1)
+        present = nb > 0
+        n = len(samp)
+        part = Counter()
+        part["nborgs"] = n
+        part["exact_core"] = int((nb == n).sum().item())
+        part["exact_accessory"] = int((present & (nb != n)).sum().item())
+        soft = present & (nb.to(torch.float64) >= n * soft_core)
+        part["soft_core"] = int(soft.sum().item())
+        part["soft_accessory"] = int((present & ~soft).sum().item())
+        out.append(part)
+    return out
+
+
+def write_rarefaction_csv(output: Path, data: list) -> Path:
+    """rarefaction.py:214-252"""
+    name = Path(output) / "rarefaction.csv"
+    with open(name, "w") as raref:
+        raref.write(",".join(CSV_COLUMNS) + "\n")
+        for part in data:
+            raref.write(",".join(map(str, [part["nborgs"], part["persistent"], part["shell"], part["cloud"], part["undefined"],
+                                           part["exact_core"], part["exact_accessory"], part["soft_core"],
+                                           part["soft_accessory"], part["exact_core"] + part["exact_accessory"], part["K"]])) + "\n")
+    return name
+
+
+def make_rarefaction_curve(pangenome, output: Path, tmpdir: Path = None, beta: float = 2.5, depth: int = 30,
+                           min_sampling: int = 1, max_sampling: int = 100, sm_degree: int = 10, free_dispersion: bool = False,
+                           chunk_size: int = 500, kval: int = -1, krange: list = None, cpu: int = 1, seed: int = 42,
+                           kestimate: bool = False, soft_core: float = 0.95, disable_bar: bool = False):
+    """rarefaction.py:538-724, same parameters; returns the per-sample records that go into ``rarefaction.csv``."""
+    logger = logging.getLogger("PPanGGOLiN")
+    tmpdir = Path(tempfile.gettempdir()) if tmpdir is None else Path(tmpdir)
+    if krange is None:
+        krange = [3, -1]
+    ppp.pan = pangenome
+    try:
+        final_k = ppp.pan.parameters["partition"]["# final nb of partitions"]
+        krange = [final_k if krange[0] < 0 else krange[0], final_k if krange[1] < 0 else krange[1]]
+    except KeyError:
+        krange = [3, 20]
+    ppp.check_pangenome_info(pangenome, need_annotations=True, need_families=True, need_graph=True, disable_bar=disable_bar)
+    tmpdir_obj = tempfile.TemporaryDirectory(dir=tmpdir)
+    tmp_path = Path(tmpdir_obj.name)
+    organisms = list(pangenome.organisms)
+    max_sampling = len(organisms) if float(len(organisms)) < max_sampling else int(max_sampling)
+    arrays = ppp.prepare_arrays(pangenome)   # one traversal of the objects for every sample below
+
+    if kval < 3 and kestimate is False:
+        try:
+            kval = ppp.pan.parameters["partition"]["# final nb of partitions"]
+            logger.info(f"Reuse the number of partitions {kval}")
+        except KeyError:
+            logger.info("Estimating the number of partitions...")
+            kval = ppp.evaluate_nb_partitions(organisms=set(organisms), sm_degree=sm_degree, free_dispersion=free_dispersion,
+                                              chunk_size=chunk_size, krange=krange, cpu=cpu, seed=seed, tmpdir=tmp_path)
+            logger.info(f"The number of partitions has been evaluated at {kval}")
+
+    logger.info("Extracting samples ...")
+    all_samples = []
+    for i in range(min_sampling, max_sampling):
+        for _ in range(depth):
+            all_samples.append(set(random.sample(organisms, i + 1)))
+    logger.info(f"Done sampling genomes in the pan, there are {len(all_samples)} samples")
+
+    if arrays is None:
+        from .export_arrays import PangenomeArrays
+        stats_arrays = PangenomeArrays.from_pangenome(pangenome, "cpu")
+    else:
+        stats_arrays = arrays
+    samp_nb_per_part = sample_family_stats(stats_arrays, all_samples, soft_core)
+
+    global samples
+    samples = all_samples
+    logger.info(" Partitioning all samples...")
+    for index in range(len(samples)):
+        counts, idx = launch_raref_nem((index, tmp_path, beta, sm_degree, free_dispersion, chunk_size, kval, krange, seed))
+        samp_nb_per_part[idx] = {**counts, **samp_nb_per_part[idx]}
+    logger.info("Done  partitioning everything")
+    if output is not None:
+        Path(output).mkdir(parents=True, exist_ok=True)
+        write_rarefaction_csv(Path(output), samp_nb_per_part)
+    tmpdir_obj.cleanup()
+    ppp._ARRAYS["pan"], ppp._ARRAYS["arrays"] = None, None
+    logger.info("Done making the rarefaction curves")
+    return samp_nb_per_part

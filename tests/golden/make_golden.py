@@ -302,7 +302,33 @@ def partition_cases():
         print(name, Counter(v[0] if v else "?" for v in labels.values()), params)
 
 
+def rarefaction_case():
+    """Reference raref_nem (rarefaction.py:36-189) on fixed genome samples of growing size: partition counts per sample."""
+    ref_partition = import_reference_partition()
+    import ppanggolin.nem.rarefaction as ref_raref
+    g = dict(n_fam=700, n_org=50, seed=24)
+    layouts = make_layouts(**g)
+    pan = build_reference_pangenome(layouts, g["n_fam"])
+    ref_partition.pan = pan
+    orgs = {o.name: o for o in pan.organisms}
+    rng = random.Random(7)
+    names = sorted(orgs, key=lambda s: int(s[3:]))
+    sample_names = [sorted(rng.sample(names, n)) for n in (12, 12, 20, 20, 35, 35, 50)]
+    ref_raref.samples = [set(orgs[n] for n in sn) for sn in sample_names]
+    out = []
+    with tempfile.TemporaryDirectory() as td:
+        for i in range(len(sample_names)):
+            counts, idx = ref_raref.raref_nem(i, Path(td), beta=2.5, sm_degree=10, free_dispersion=False, chunk_size=500, kval=3,
+                                              krange=[3, 20], seed=42)
+            out.append(counts)
+            print("raref", len(sample_names[i]), counts)
+    np.savez_compressed(OUT / "rarefaction.npz", n_fam=g["n_fam"], layouts=np.concatenate(layouts),
+                        layout_ptr=np.cumsum([0] + [len(l) for l in layouts]), samples=json.dumps(sample_names),
+                        counts=json.dumps(out))
+
+
 if __name__ == "__main__":
     refnem.build()
     nem_cases()
     partition_cases()
+    rarefaction_case()

@@ -414,4 +414,70 @@ def test_partition_on_reference_genomes(eng, tmp_path):
     assert abs(k_ours - k_ref) <= 1
     assert letters >= 0.999
     if k_ours == k_ref:
-        assert exact >= 0.99
+        assert exact >= 0.999
+
+
+def test_rarefaction_caller_matches_reference(eng, tmp_path):
+    """Second caller of the API: ``raref_nem`` on fixed genome samples vs the reference's
+    ``raref_nem`` (tests/golden/rarefaction.npz), then ``make_rarefaction_curve`` end to end (CSV, core statistics)."""
+    import json as _json
+    import random
+    import minipan
+    from goldens import GOLD
+    from ppanggolin_b200.nem import partition as part, rarefaction as raref
+    z = np.load(GOLD / "rarefaction.npz")
+    ptr = z["layout_ptr"]
+    layouts = [z["layouts"][ptr[i]:ptr[i + 1]] for i in range(len(ptr) - 1)]
+    pan = minipan.build_from_layouts(layouts, int(z["n_fam"]))
+    part.pan = pan
+    orgs = {o.name: o for o in pan.organisms}
+    sample_names, ref_counts = _json.loads(str(z["samples"])), _json.loads(str(z["counts"]))
+    raref.samples = [set(orgs[n] for n in sn) for sn in sample_names]
+    for use_arrays in (False, True):
+        if use_arrays:
+            part.prepare_arrays(pan)
+        for i, want in enumerate(ref_counts):
+            got, idx = raref.raref_nem(i, tmp_path / f"a{int(use_arrays)}", beta=2.5, sm_degree=10, free_dispersion=False,
+                                       chunk_size=500, kval=3, krange=[3, 20], seed=42)
+            assert idx == i and got["K"] == want["K"]
+            tot = want["persistent"] + want["shell"] + want["cloud"] + want["undefined"]
+            assert got["persistent"] + got["shell"] + got["cloud"] + got["undefined"] == tot
+            assert sum(abs(got[k] - want[k]) for k in ("persistent", "shell", "cloud", "undefined")) <= max(2, 0.002 * tot)
+    part._ARRAYS["pan"], part._ARRAYS["arrays"] = None, None
+    # end to end: samples of 1..11 genomes x 2, K fixed; the CSV and the exact / soft core counts
+    random.seed(5)
+    pan.parameters["partition"] = {"# final nb of partitions": 3}
+    data = raref.make_rarefaction_curve(pan, tmp_path / "out", tmpdir=tmp_path, depth=2, min_sampling=1, max_sampling=12, kval=3,
+                                        chunk_size=500, soft_core=0.9)
+    lines = (tmp_path / "out" / "rarefaction.csv").read_text().splitlines()
+    assert lines[0].split(",") == raref.CSV_COLUMNS and len(lines) == 1 + len(data) == 1 + 11 * 2
+    X = {f.name: set(o.name for o in f.organisms) for f in pan.gene_families}
+    for rec, samp in zip(data, raref.samples):
+        names = set(o.name for o in samp)
+        nb = [len(v & names) for v in X.values()]
+        n = len(names)
+        assert rec["nborgs"] == n
+        assert rec["exact_core"] == sum(1 for v in nb if v == n) and rec["exact_accessory"] == sum(1 for v in nb if 0 < v < n)
+        assert rec["soft_core"] == sum(1 for v in nb if v > 0 and v >= n * 0.9)
+        assert rec["persistent"] + rec["shell"] + rec["cloud"] + rec["undefined"] == rec["exact_core"] + rec["exact_accessory"]
+
+
+def test_rarefaction_chunked_samples(eng, tmp_path):
+    """A sample larger than chunk_size goes through the chunk votes of rarefaction.py:92-160."""
+    import random
+    import minipan
+    from goldens import load_partition
+    from ppanggolin_b200.nem import partition as part, rarefaction as raref
+    g = load_partition("chunked")
+    pan = minipan.build_from_layouts(g["layouts"], g["n_fam"])
+    part.pan = pan
+    orgs = list(pan.organisms)
+    raref.samples = [set(orgs[:60])]
+    random.seed(3)
+    part.prepare_arrays(pan)
+    voted, _ = raref.raref_nem(0, tmp_path, chunk_size=25, kval=3)
+    whole, _ = raref.raref_nem(0, tmp_path / "w", chunk_size=500, kval=3)
+    part._ARRAYS["pan"], part._ARRAYS["arrays"] = None, None
+    tot = sum(whole[k] for k in ("persistent", "shell", "cloud", "undefined"))
+    assert sum(voted[k] for k in ("persistent", "shell", "cloud", "undefined")) == tot
+    assert sum(abs(voted[k] - whole[k]) for k in ("persistent", "shell", "cloud")) <= 0.08 * tot
