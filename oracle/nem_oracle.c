@@ -237,7 +237,10 @@ static int mstep_fp64(work_t* w, const float* C, float* pk, float* mu, float* ep
       for (int i = 0; i < N; i++) if (xc[i]) s1 += (double)C[(size_t)i * K + k];
       double s0 = nk[k] - s1, in;
       float m;
-      if (s1 > s0) { m = 1.0f; in = s0; } else if (s1 < s0) { m = 0.0f; in = s1; } else { m = 0.5f; in = 0.5 * nk[k]; }
+      /* the reference compares float32 sums (nem_mod.c:1417-1474): weights below the float32 resolution of the class size
+       * are absorbed, which turns near-ties into exact ties (centre 0.5); compare at that resolution */
+      float w0 = (float)s0, half = (float)nk[k] * 0.5f;
+      if (w0 > half) { m = 0.0f; in = s1; } else if (w0 < half) { m = 1.0f; in = s0; } else { m = 0.5f; in = 0.5 * nk[k]; }
       mu[k * D + d] = m;
       sum_iner += in;
       if (p->free_disp) eps[k * D + d] = (float)(in / nk[k]);

@@ -789,9 +789,14 @@ k_mstep_finalize(Params P, PeerStats ps, long long N_total, double* __restrict__
       for (int q = 0; q < kMaxPeers; q++) { c_i += ci[q]; c_f += cf[q]; }
       const double s1 = (double)c_i + c_f;
       const double s0 = nk - s1;
-      if (s1 > s0) { m = 1.0f; iner = s0; }
-      else if (s1 < s0) { m = 0.0f; iner = s1; }
-      else { m = 0.5f; iner = 0.5 * nk; any_half = 1; }   // exact tie: midway between a 0 and a 1 (nem_mod.c:1463-1471)
+      // Weighted median of a 0/1 column (nem_mod.c:1417-1474): 0 if the weight of the zero rows exceeds half the class
+      // size, 1 if it falls short, midway (0.5) on a tie.  The reference compares float32 sums, in which weights below
+      // the float32 resolution of the class size are absorbed -- near-ties become exact ties there -- so the comparison
+      // is made at that resolution.
+      const float w0 = (float)s0, half = (float)nk * 0.5f;
+      if (w0 > half) { m = 0.0f; iner = s1; }
+      else if (w0 < half) { m = 1.0f; iner = s0; }
+      else { m = 0.5f; iner = 0.5 * nk; any_half = 1; }   // tie: midway between a 0 and a 1 (nem_mod.c:1463-1471)
       P.mu[(size_t)k * D + d] = m;
       if (P.free_disp) {
         const float e = (float)(iner / nk);                // nem_mod.c:1162-1163

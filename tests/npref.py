@@ -57,8 +57,9 @@ def mstep(X, T, free_disp):
     nk = Td.sum(0)
     s1 = Td.T @ X
     s0 = nk[:, None] - s1
-    mu = np.where(s1 > s0, 1.0, np.where(s1 < s0, 0.0, 0.5)).astype(np.float32)
-    iner = np.where(s1 > s0, s0, np.where(s1 < s0, s1, 0.5 * nk[:, None]))
+    w0 = s0.astype(np.float32); half = (nk.astype(np.float32) * np.float32(0.5))[:, None]   # float32-resolution comparison
+    mu = np.where(w0 < half, 1.0, np.where(w0 > half, 0.0, 0.5)).astype(np.float32)
+    iner = np.where(w0 < half, s0, np.where(w0 > half, s1, 0.5 * nk[:, None]))
     if free_disp:
         eps = (iner / nk[:, None]).astype(np.float32)
     else:
