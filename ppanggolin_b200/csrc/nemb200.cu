@@ -361,7 +361,20 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
       CK(cudaEventRecord(e0, st));
     }
-    k_mstep_onehot<<<grid, kMsTpb, 0, st>>>((const uint2*)bits, W2, tile_w, K, pl->offsets, pl->perm, pl->cnt_local, pl->Dpad);
+    // wide matrices: one fat CTA per SM, rows staged with cp.async (k_mstep_onehot_ring); NEMB200_ONEHOT_RING=0/1 forces
+    const char* force = getenv("NEMB200_ONEHOT_RING");
+    const int W4 = pl->Ws / 4;
+    if (force ? atoi(force) != 0 : W4 >= kOhTpb / 2) {
+      const int ntx = (W4 + kOhTpb - 1) / kOhTpb;
+      const int tw = (W4 + ntx - 1) / ntx;
+      const size_t smem = onehot_ring_smem();
+      CK(cudaFuncSetAttribute(k_mstep_onehot_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const long long sl = std::min<long long>(std::max<long long>(num_sms() / ntx, 1), 65535);
+      k_mstep_onehot_ring<<<dim3(ntx, (unsigned)sl), kOhTpb, smem, st>>>((const uint4*)bits, W4, tw, K, pl->offsets, pl->perm,
+                                                                        pl->cnt_local, pl->Dpad);
+    } else {
+      k_mstep_onehot<<<grid, kMsTpb, 0, st>>>((const uint2*)bits, W2, tile_w, K, pl->offsets, pl->perm, pl->cnt_local, pl->Dpad);
+    }
     CK(cudaGetLastError());
     if (pl->timing) {
       CK(cudaEventRecord(e1, st));
@@ -468,21 +481,56 @@ static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* log
   CK(cudaGetLastError());
   return 0;
 }
+// Shared-memory-ring variant (k_density_sk_ring): one fat CTA per SM, matrix words staged with cp.async.  Used when the
+// shard has enough rows to give every SM full CTAs and the ring plus both centre planes fit in shared memory; small
+// instances keep the 128-thread kernel, which spreads few rows over more SMs.  NEMB200_DENS_RING=0/1 forces the choice
+// (tests run both on the same inputs: the results are integers, so they must be identical).
+template <int KB, int KX>
+static int launch_density_ring(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st, bool* done) {
+  constexpr int RB = KB <= 4 ? 4 : (KB <= 8 ? 2 : 1);
+  constexpr int TPB = KB <= 3 ? 640 : 512;          // registers: 96 at K <= 3, up to 127 above
+  constexpr int P = RB == 4 ? 3 : (RB == 2 ? 4 : 6);  // steps in flight per thread (RB x 16 B each)
+  *done = false;
+  const int W4 = pl->Ws / 4;
+  const int G = group_lanes(W4);
+  const size_t smem = ((size_t)P * RB * TPB + (size_t)2 * pl->K * W4) * sizeof(uint4);
+  const long long rows_per_block = (long long)(TPB / 32) * (32 / G) * RB;
+  const char* force = getenv("NEMB200_DENS_RING");
+  if (smem > 220 * 1024) return 0;
+  if (force ? atoi(force) == 0 : pl->N_local < rows_per_block * num_sms()) return 0;
+  auto kern = k_density_sk_ring<KB, KX, RB, P, TPB>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long blocks = (pl->N_local + rows_per_block - 1) / rows_per_block;
+  if (blocks > num_sms()) blocks = num_sms();
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, TPB, smem, st>>>((const uint4*)bits, pl->N_local, W4, pl->K, G, (const uint4*)pl->P.m1,
+                                            (const uint4*)pl->P.valid, pl->P.L, pl->P.B, pl->P.has_half, logf);
+  CK(cudaGetLastError());
+  *done = true;
+  return 0;
+}
+template <int KB, int KX>
+static int launch_density_any(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
+  bool done = false;
+  const int rc = launch_density_ring<KB, KX>(pl, bits, logf, st, &done);
+  if (rc != 0 || done) return rc;
+  return launch_density_sk<KB, KX>(pl, bits, logf, st);
+}
 static int dispatch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
   switch (pl->K) {  // exact-K kernels for the common small K (no per-class predicates), buckets above
-    case 1: case 2: return launch_density_sk<2, 0>(pl, bits, logf, st);
-    case 3: return launch_density_sk<3, 3>(pl, bits, logf, st);
-    case 4: return launch_density_sk<4, 4>(pl, bits, logf, st);
-    case 5: return launch_density_sk<5, 5>(pl, bits, logf, st);
-    case 6: return launch_density_sk<6, 6>(pl, bits, logf, st);
-    case 7: return launch_density_sk<7, 7>(pl, bits, logf, st);
-    case 8: return launch_density_sk<8, 8>(pl, bits, logf, st);
+    case 1: case 2: return launch_density_any<2, 0>(pl, bits, logf, st);
+    case 3: return launch_density_any<3, 3>(pl, bits, logf, st);
+    case 4: return launch_density_any<4, 4>(pl, bits, logf, st);
+    case 5: return launch_density_any<5, 5>(pl, bits, logf, st);
+    case 6: return launch_density_any<6, 6>(pl, bits, logf, st);
+    case 7: return launch_density_any<7, 7>(pl, bits, logf, st);
+    case 8: return launch_density_any<8, 8>(pl, bits, logf, st);
     default: break;
   }
-  if (pl->K <= 12) return launch_density_sk<12, 0>(pl, bits, logf, st);
-  if (pl->K <= 16) return launch_density_sk<16, 0>(pl, bits, logf, st);
-  if (pl->K <= 20) return launch_density_sk<20, 0>(pl, bits, logf, st);
-  return launch_density_sk<32, 0>(pl, bits, logf, st);
+  if (pl->K <= 12) return launch_density_any<12, 0>(pl, bits, logf, st);
+  if (pl->K <= 16) return launch_density_any<16, 0>(pl, bits, logf, st);
+  if (pl->K <= 20) return launch_density_any<20, 0>(pl, bits, logf, st);
+  return launch_density_any<32, 0>(pl, bits, logf, st);
 }
 template <int KB>
 static int launch_density_skd(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {

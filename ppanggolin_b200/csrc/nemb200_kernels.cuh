@@ -118,10 +118,14 @@ __global__ void k_peer_wait(const int* sig /*own sig array*/, int n, int phase, 
 // fetched from shared memory once per RB matrix words.
 // ------------------------------------------------------------------------------------------------------------------
 // carry-save adder on 32 bit-columns at once: a + b + c = 2 * hi + lo
+// Written as two explicit LOP3 (majority 0xE8, parity 0x96): left to the compiler, the mismatch XORs feeding b and c get
+// folded into the adder as five 3-input LOP3 per adder instead of 2 + 2 (seen in the SASS; the ALU pipe is what bounds
+// the density kernel once the loads are staged through shared memory).
 __device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
-  const uint32_t u = a ^ b;
-  hi = (a & b) | (u & c);
-  lo = u ^ c;
+  uint32_t h, l;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(h) : "r"(a), "r"(b), "r"(c));
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(l) : "r"(a), "r"(b), "r"(c));
+  hi = h; lo = l;
 }
 
 // Pipe balance (measured with ncu on B200): one POPC per word and class saturates the quarter-rate XU pipe (80 % XU at
@@ -242,6 +246,162 @@ k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, 
     if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, m1g, validg, L, B, logf);
     else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, m1g, validg, L, B, logf);
   }
+}
+
+// ---- shared-memory ring variant -------------------------------------------------------------------------------------
+// Measured on B200 (tools/probes/stream_probe.cu): a read-only pass over the matrix needs >= 64 KB in flight per SM to
+// reach the HBM ceiling (7.0 TB/s), and ncu shows the register-prefetch kernel above stalled on the long scoreboard.
+// Here every thread keeps P steps of its own matrix words in flight with cp.async (LDGSTS, 16 B, L1 bypass) into
+// private shared-memory slots -- no registers are held by loads in flight, no barrier is needed (a thread only reads
+// what it copied itself), and the pipeline runs across row batches.  One fat CTA per SM shares one copy of the centre
+// planes.  Arithmetic is identical to density_sk_body.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ const uint4* ptr_plus16(const uint4* base, uint32_t idx) {   // base + idx (IMAD.WIDE: FMA pipe)
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"(idx), "l"((unsigned long long)base));
+  return reinterpret_cast<const uint4*>(r);
+}
+
+template <int KB, int KX, int RB, int P, int TPB, bool HALF>
+__device__ __forceinline__ void density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int Krt, int G,
+                                                const uint4* m1, const uint4* valid, uint4* ring /*[P][RB][TPB]*/,
+                                                const double* __restrict__ L, const double* __restrict__ B,
+                                                double* __restrict__ logf) {
+  const int K = KX > 0 ? KX : Krt;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (G - 1);
+  const int grp = lane / G;
+  const long long warp_global = (long long)blockIdx.x * (TPB >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (TPB >> 5);
+  const long long rows_per_warp = (long long)(32 / G) * RB;
+  const long long stride_rows = nwarps * rows_per_warp;
+  const int nsteps = (W4 + G - 1) / G;
+  const int my_steps = (W4 - sub + G - 1) / G;   // steps in which this lane has a matrix word (0 if sub >= W4)
+  constexpr uint32_t kStage = RB * TPB * 16;
+
+  const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(ring) + threadIdx.x * 16;
+  const char* myslot = reinterpret_cast<const char*>(ring + threadIdx.x);
+
+  // issue cursor: runs P-1 items (one item = RB x 16 B of this thread) ahead of the consume cursor, across row batches
+  long long ir0 = warp_global * rows_per_warp + (long long)grp * RB;
+  const uint4* ibr[RB];
+  int isteps = 0;       // my_steps while the cursor is on an existing batch, 0 afterwards
+  auto set_batch = [&]() {
+    isteps = ir0 < N ? my_steps : 0;
+#pragma unroll
+    for (int r = 0; r < RB; r++) ibr[r] = bits + (ir0 + r < N ? ir0 + r : N - 1) * W4 + sub;   // tail rows re-read the last row
+  };
+  set_batch();
+  uint32_t icol = 0;
+  int istep = 0;
+  int sj = 0;           // stage the next issue goes to; the item consumed in the same iteration sits in stage sj + 1 (mod P)
+  auto issue = [&]() {
+    if (istep < isteps) {
+      const uint32_t dst = slot0 + sj * kStage;
+#pragma unroll
+      for (int r = 0; r < RB; r++) cp_async16(dst + r * (TPB * 16), ptr_plus16(ibr[r], icol));
+    }
+    cp_async_commit();
+    sj = (sj + 1 == P) ? 0 : sj + 1;
+    icol += G;
+    if (++istep == nsteps) {
+      istep = 0; icol = 0;
+      ir0 += stride_rows;
+      set_batch();
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < P - 1; s++) issue();
+
+  for (long long base = warp_global * rows_per_warp; base < N; base += stride_rows) {
+    const long long r0 = base + (long long)grp * RB;
+    int h2[RB][KB];
+    uint32_t ones[RB][KB];
+#pragma unroll
+    for (int r = 0; r < RB; r++)
+#pragma unroll
+      for (int k = 0; k < KB; k++) { h2[r][k] = 0; ones[r][k] = 0; }
+    const uint4 *pm = m1 + sub, *pv = valid + sub;
+#pragma unroll 1
+    for (int step = 0; step < nsteps; step++) {
+      issue();                                // fills stage sj-1; afterwards sj is the stage of the item consumed now
+      cp_async_wait<P - 1>();
+      if (step < my_steps) {
+        const char* st = myslot + sj * kStage;
+        uint4 x[RB];
+#pragma unroll
+        for (int r = 0; r < RB; r++) x[r] = *reinterpret_cast<const uint4*>(st + r * (TPB * 16));
+#pragma unroll
+        for (int k = 0; k < KB; k++) {
+          if (KX > 0 || k < K) {
+            const uint4 a = pm[k * W4];
+            uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+            if (HALF) v = pv[k * W4];
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+              const uint32_t m0 = (x[r].x ^ a.x) & v.x, m1w = (x[r].y ^ a.y) & v.y;
+              const uint32_t m2 = (x[r].z ^ a.z) & v.z, m3 = (x[r].w ^ a.w) & v.w;
+              uint32_t c1, c2;
+              csa(c1, ones[r][k], ones[r][k], m0, m1w);
+              csa(c2, ones[r][k], ones[r][k], m2, m3);
+              h2[r][k] += __popc(c1) + __popc(c2);
+            }
+          }
+        }
+      }
+      pm += G; pv += G;
+    }
+    int h[RB][KB];
+#pragma unroll
+    for (int r = 0; r < RB; r++)
+#pragma unroll
+      for (int k = 0; k < KB; k++) h[r][k] = 2 * h2[r][k] + __popc(ones[r][k]);
+    for (int off = G >> 1; off > 0; off >>= 1) {
+#pragma unroll
+      for (int r = 0; r < RB; r++)
+#pragma unroll
+        for (int k = 0; k < KB; k++) h[r][k] += __shfl_xor_sync(0xffffffffu, h[r][k], off);
+    }
+#pragma unroll
+    for (int k = 0; k < KB; k++) {
+      if (k < K && (k & (G - 1)) == sub) {
+        const double Lk = L[k], Bk = B[k];
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+          if (r0 + r < N) {
+            const double v = (h[r][k] == 0) ? Bk : (Bk - (double)h[r][k] * Lk);   // see density_sk_body
+            logf[(r0 + r) * K + k] = v;
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int KB, int KX, int RB, int P, int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+k_density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
+                  const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
+                  const int* __restrict__ has_half, double* __restrict__ logf) {
+  extern __shared__ uint4 smem4[];
+  const bool half = (*has_half != 0);
+  uint4* ring = smem4;                       // [P][RB][TPB]
+  uint4* sm1 = smem4 + P * RB * TPB;         // [K][W4]
+  uint4* sval = sm1 + K * W4;                // [K][W4]
+  const int n = K * W4;
+  for (int t = threadIdx.x; t < n; t += TPB) {
+    sm1[t] = m1g[t];
+    if (half) sval[t] = validg[t];
+  }
+  __syncthreads();
+  if (half) density_sk_ring<KB, KX, RB, P, TPB, true>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf);
+  else      density_sk_ring<KB, KX, RB, P, TPB, false>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf);
 }
 
 // free dispersion ("skd"): per-column log-odds.  sum over mismatching columns of L_kd, taken over the set bits of the
@@ -676,6 +836,180 @@ k_mstep_onehot(const uint2* __restrict__ bits2, int W2, int tile_w, int K, const
           const int col = (blockIdx.x * tile_w + (t >> 5)) * 64 + half * 32 + (t & 31);
           if (c != 0 && col < Dpad) atomicAdd(&cnt[(size_t)cls * Dpad + col], sign * c);
         }
+      }
+    }
+  }
+}
+
+// ---- shared-memory ring variant for wide matrices -------------------------------------------------------------------
+// ncu on the kernel above: long-scoreboard stalls 10 per issue, ALU 38 % -- the loads in flight (16 x 8 B per thread,
+// held in registers) limit it, and a read-only pass needs >= 64 KB in flight per SM to reach the HBM ceiling
+// (tools/probes/stream_probe.cu; the same probe shows 1-D bulk copies of 3 KB row segments capped at 6.0 TB/s by their
+// per-copy cost, so the staging is done with per-thread cp.async instead).  One fat CTA per SM owns a column tile of
+// up to kOhTpb 128-bit words; a thread copies its own word of 8 listed rows per group into private shared-memory
+// slots, kOhGroups groups in flight (~100 KB per SM), no barrier in the streaming loop.  Counting (Harley-Seal over 8
+// rows, 12 bit-sliced planes per 32 columns) and flushing are the same integer arithmetic, so the counts are identical.
+constexpr int kOhTpb = 416;       // 13 warps: one 128-bit word column each
+constexpr int kOhRows = 8;        // rows per group
+constexpr int kOhGroups = 3;      // groups in the ring (kOhGroups - 1 in flight while one is summed)
+
+// 8 words -> the weight-8 carry, rippled into planes 3..11
+__device__ __forceinline__ void hs8(uint32_t (&p)[kPlanes], const uint32_t (&x)[kOhRows]) {
+  uint32_t t2a, t2b, t2c, t2d, t4a, t4b, c8;
+  csa(t2a, p[0], p[0], x[0], x[1]);
+  csa(t2b, p[0], p[0], x[2], x[3]);
+  csa(t2c, p[0], p[0], x[4], x[5]);
+  csa(t2d, p[0], p[0], x[6], x[7]);
+  csa(t4a, p[1], p[1], t2a, t2b);
+  csa(t4b, p[1], p[1], t2c, t2d);
+  csa(c8, p[2], p[2], t4a, t4b);
+  uint32_t carry = c8;
+#pragma unroll
+  for (int j = 3; j < kPlanes; j++) {
+    const uint32_t nc = p[j] & carry;
+    p[j] ^= carry;
+    carry = nc;
+  }
+}
+__device__ __forceinline__ void ripple1(uint32_t (&p)[kPlanes], uint32_t c) {
+#pragma unroll
+  for (int j = 0; j < kPlanes; j++) {
+    const uint32_t n = p[j] & c;
+    p[j] ^= c;
+    c = n;
+  }
+}
+
+// 12 bit-sliced planes of one 32-column word -> 32 counts (<= 4095) as 16-bit values.  Four planes at a time are
+// interleaved into nibbles (phase b holds columns 4i + b), bytes are assembled from the nibbles of two plane groups and
+// PRMT picks the (low byte, high byte) pair of each column: ~6 instructions per column instead of 36 for a bit loop.
+constexpr int kOhPitch16 = 130;   // 16-bit counts per thread row in shared memory: 128 + 2 (odd number of 32-bit words)
+__device__ __forceinline__ void planes_to_counts16(const uint32_t (&p)[kPlanes], unsigned short* dst /*[32]*/) {
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    uint32_t a[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int g = 0; g < 3; g++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t x = p[4 * g + j];
+        const uint32_t sh = b >= j ? (x >> (b - j)) : (x << (j - b));
+        a[g] |= sh & (0x11111111u << j);
+      }
+    // nibble i of a[g] = bits 4g..4g+3 of the count of column 4i + b
+    const uint32_t lo01 = (a[0] & 0x0F0F0F0Fu) | ((a[1] << 4) & 0xF0F0F0F0u);   // byte k: bits 0..7 of column 8k + b
+    const uint32_t hi01 = ((a[0] >> 4) & 0x0F0F0F0Fu) | (a[1] & 0xF0F0F0F0u);   // byte k: bits 0..7 of column 8k + 4 + b
+    const uint32_t lo2 = a[2] & 0x0F0F0F0Fu, hi2 = (a[2] >> 4) & 0x0F0F0F0Fu;    // byte k: bits 8..11
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      dst[8 * k + b] = (unsigned short)__byte_perm(lo01, lo2, k | ((4 + k) << 4));
+      dst[8 * k + 4 + b] = (unsigned short)__byte_perm(hi01, hi2, k | ((4 + k) << 4));
+    }
+  }
+}
+
+__host__ __device__ inline size_t onehot_ring_smem() {
+  return (size_t)kOhGroups * kOhRows * kOhTpb * 16 + (size_t)kMaxRun * 4;
+}
+
+__global__ void __launch_bounds__(kOhTpb, 1)
+k_mstep_onehot_ring(const uint4* __restrict__ bits4, int W4, int tile_w /*<= kOhTpb*/, int K, const int* __restrict__ offsets,
+                    const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad) {
+  extern __shared__ uint4 smem4[];
+  uint4* ring = smem4;                                            // [kOhGroups][kOhRows][kOhTpb]
+  int* s_rows = reinterpret_cast<int*>(ring + kOhGroups * kOhRows * kOhTpb);
+  unsigned short* s_cnt16 = reinterpret_cast<unsigned short*>(ring);   // the flush reuses the (drained) ring
+  constexpr uint32_t kGroupBytes = kOhRows * kOhTpb * 16;
+
+  const int total = offsets[2 * K];
+  const long long S = min((long long)gridDim.y, max(1LL, ((long long)total + 63) / 64));
+  if (blockIdx.y >= S) return;
+  const int lo = (int)((long long)total * blockIdx.y / S), hi = (int)((long long)total * (blockIdx.y + 1) / S);
+  if (lo >= hi) return;
+  const int word0 = blockIdx.x * tile_w;
+  const int nw = min(tile_w, W4 - word0);                         // 128-bit words of this tile
+  const bool active = (int)threadIdx.x < nw;
+  const uint4* colp = bits4 + word0 + (active ? threadIdx.x : 0);
+  const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(ring) + threadIdx.x * 16;
+  const char* myslot = reinterpret_cast<const char*>(ring + threadIdx.x);
+
+  for (int b = 0; b < 2 * K; b++) {
+    const int b0 = max(lo, offsets[b]), b1 = min(hi, offsets[b + 1]);
+    for (int start = b0; start < b1; start += kMaxRun) {
+      const int len = min(kMaxRun, b1 - start);
+      __syncthreads();                                    // the previous run's flush no longer reads s_cnt / s_rows
+      for (int t = threadIdx.x; t < len; t += kOhTpb) s_rows[t] = perm[start + t];
+      __syncthreads();
+      const int ngroups = (len + kOhRows - 1) / kOhRows;  // the last one may hold fewer rows
+      uint32_t pl[4][kPlanes];
+#pragma unroll
+      for (int w = 0; w < 4; w++)
+#pragma unroll
+        for (int j = 0; j < kPlanes; j++) pl[w][j] = 0;
+
+      int gi = 0, sj = 0;                                 // next group to issue, and the ring slot it goes to
+      auto issue = [&]() {
+        if (gi < ngroups && active) {
+          const int r0 = gi * kOhRows;
+          const uint32_t dst = slot0 + sj * kGroupBytes;
+          if (r0 + kOhRows <= len) {
+#pragma unroll
+            for (int j = 0; j < kOhRows; j += 4) {
+              const int4 rows = *reinterpret_cast<const int4*>(s_rows + r0 + j);
+              cp_async16(dst + (j + 0) * (kOhTpb * 16), colp + (size_t)rows.x * W4);
+              cp_async16(dst + (j + 1) * (kOhTpb * 16), colp + (size_t)rows.y * W4);
+              cp_async16(dst + (j + 2) * (kOhTpb * 16), colp + (size_t)rows.z * W4);
+              cp_async16(dst + (j + 3) * (kOhTpb * 16), colp + (size_t)rows.w * W4);
+            }
+          } else {
+            for (int j = 0; r0 + j < len; j++) cp_async16(dst + j * (kOhTpb * 16), colp + (size_t)s_rows[r0 + j] * W4);
+          }
+        }
+        cp_async_commit();
+        gi++;
+        sj = (sj + 1 == kOhGroups) ? 0 : sj + 1;
+      };
+#pragma unroll
+      for (int s = 0; s < kOhGroups - 1; s++) issue();
+      for (int g = 0; g < ngroups; g++) {
+        issue();                                          // afterwards sj is the slot of group g
+        cp_async_wait<kOhGroups - 1>();
+        if (active) {
+          const char* src = myslot + sj * kGroupBytes;
+          const int rows_in = min(kOhRows, len - g * kOhRows);
+          if (rows_in == kOhRows) {
+            uint32_t x0[kOhRows], x1[kOhRows], x2[kOhRows], x3[kOhRows];
+#pragma unroll
+            for (int j = 0; j < kOhRows; j++) {
+              const uint4 v = *reinterpret_cast<const uint4*>(src + j * (kOhTpb * 16));
+              x0[j] = v.x; x1[j] = v.y; x2[j] = v.z; x3[j] = v.w;
+            }
+            hs8(pl[0], x0);
+            hs8(pl[1], x1);
+            hs8(pl[2], x2);
+            hs8(pl[3], x3);
+          } else {
+            for (int j = 0; j < rows_in; j++) {           // tail rows of the run: ripple through all planes
+              const uint4 v = *reinterpret_cast<const uint4*>(src + j * (kOhTpb * 16));
+              ripple1(pl[0], v.x); ripple1(pl[1], v.y); ripple1(pl[2], v.z); ripple1(pl[3], v.w);
+            }
+          }
+        }
+      }
+      cp_async_wait<0>();
+      __syncthreads();                                    // every thread is done with the ring: reuse it as s_cnt
+      // expand the planes into 16-bit counts in shared memory (thread-major, odd word pitch), then walk the tile's
+      // columns in order: coalesced REDs to the global counters
+      const int cls = b < K ? b : b - K;
+      const int sign = b < K ? 1 : -1;
+      unsigned short* mine = s_cnt16 + threadIdx.x * kOhPitch16;
+#pragma unroll
+      for (int w = 0; w < 4; w++) planes_to_counts16(pl[w], mine + w * 32);
+      __syncthreads();
+      for (int t = threadIdx.x; t < nw * 128; t += kOhTpb) {
+        const int c = s_cnt16[(t >> 7) * kOhPitch16 + (t & 127)];
+        const int col = word0 * 128 + t;
+        if (c != 0 && col < Dpad) atomicAdd(&cnt[(size_t)cls * Dpad + col], sign * c);
       }
     }
   }

@@ -503,3 +503,93 @@ def test_edge_shapes(eng, N, D, K, beta, fd):
         assert abs(run.crit[3] - o["crit"][3]) <= 1e-5 * abs(o["crit"][3]) + 1e-9
         if run.n_iter == o["n_iter"]:
             assert np.abs(run.T.cpu().numpy() - o["T"]).max() < 2e-3 or K > 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,D,K", [(300, 50, 2), (1000, 500, 3), (777, 1000, 4), (513, 5000, 3), (400, 129, 5), (350, 4100, 8),
+                                   (260, 700, 12), (300, 300, 20), (257, 640, 32)])
+def test_density_ring_equals_small_cta_kernel(eng, N, D, K, monkeypatch):
+    """The two density kernels (cp.async shared-memory ring / 128-thread register prefetch) produce integers and must
+    agree bit for bit; centres include 0.5 ties (the `valid` plane) in a third of the columns."""
+    import torch
+    from ppanggolin_b200.synthetic import pack_rows
+    rng = np.random.default_rng(N + D + K)
+    X = (rng.random((N, D)) < rng.random(D)[None, :]).astype(np.uint8)
+    cls = np.arange(N) % K
+    tie_cols = np.arange(D) % 3 == 0
+    for k in range(K):                       # exact median ties: half of the class's rows hold a 1 in those columns
+        rows = np.flatnonzero(cls == k)
+        rows = rows[: len(rows) // 2 * 2]
+        X[np.ix_(rows[: len(rows) // 2], np.flatnonzero(tie_cols))] = 1
+        X[np.ix_(rows[len(rows) // 2:], np.flatnonzero(tie_cols))] = 0
+    keep = np.ones(N, bool)
+    for k in range(K):                       # classes of odd size: drop one row so the ties are exact
+        rows = np.flatnonzero(cls == k)
+        if len(rows) % 2:
+            keep[rows[-1]] = False
+    X, cls = X[keep], cls[keep]
+    n = X.shape[0]
+    bits = torch.from_numpy(pack_rows(X).view(np.int32)).cuda()
+    T = torch.zeros((n, K), dtype=torch.float32, device="cuda")
+    T[torch.arange(n), torch.from_numpy(cls).cuda()] = 1.0
+    plan = eng.Plan(n, n, D, bits.shape[1], K, False, eng.EPI_REF)
+    plan.init_params()
+    out = {}
+    for stage in ("init", "ties"):
+        if stage == "ties":
+            plan.mstep_accumulate(bits, T)
+            plan.mstep_finalize()
+            mu = plan.get_params()[0]
+            assert (mu[:, tie_cols] == 0.5).all()
+        for ring in ("0", "1"):
+            monkeypatch.setenv("NEMB200_DENS_RING", ring)
+            logf = torch.full((n, K), float("nan"), dtype=torch.float64, device="cuda")
+            plan.density(bits, logf)
+            torch.cuda.synchronize()
+            out[stage, ring] = logf
+        assert torch.equal(out[stage, "0"], out[stage, "1"])
+        assert not torch.isnan(out[stage, "1"]).any()
+    mu, eps = plan.get_params()[:2]
+    assert np.allclose(out["ties", "1"].cpu().numpy(), npref.logf(X, mu, eps), rtol=1e-11, atol=1e-8)
+    plan.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,D,K", [(3000, 30000, 3), (5000, 5000, 4), (2000, 64, 2), (700000, 64, 3), (1500, 52000, 5)])
+def test_onehot_counts_ring_equals_small_cta_kernel(eng, N, D, K, monkeypatch):
+    """Column counts of the one-hot rows: the shared-memory-ring kernel against the 128-thread kernel and against numpy,
+    first pass (full count) and an incremental update after 10 % of the rows changed class."""
+    import torch
+    from ppanggolin_b200.synthetic import pack_rows
+    rng = np.random.default_rng(N + D + K)
+    X = (rng.random((N, D)) < 0.3).astype(np.uint8)
+    bits = torch.from_numpy(pack_rows(X).view(np.int32)).cuda()
+    cls0 = rng.integers(0, K, N)
+    cls1 = cls0.copy()
+    moved = rng.random(N) < 0.1
+    cls1[moved] = rng.integers(0, K, int(moved.sum()))
+    fuzzy = rng.random(N) < 0.02                       # a few rows that are not one-hot: excluded from the integer counts
+
+    def posterior(cls):
+        T = np.zeros((N, K), np.float32)
+        T[np.arange(N), cls] = 1.0
+        T[fuzzy] = 1.0 / K
+        return torch.from_numpy(T).cuda()
+
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NEMB200_ONEHOT_RING", mode)
+        plan = eng.Plan(N, N, D, bits.shape[1], K, False, eng.EPI_REF)
+        plan.init_params()
+        got = []
+        for cls in (cls0, cls1):
+            plan.mstep_accumulate(bits, posterior(cls))
+            torch.cuda.synchronize()
+            got.append(plan.stats_tensors()[0].cpu().numpy().copy())
+        res[mode] = got
+        plan.close()
+    for step, cls in enumerate((cls0, cls1)):
+        want = np.stack([X[(cls == k) & ~fuzzy].sum(0, dtype=np.int64) for k in range(K)])
+        assert np.array_equal(res["0"][step], res["1"][step])
+        assert np.array_equal(res["1"][step][:, :D], want)
+        assert not res["1"][step][:, D:].any()
