@@ -146,6 +146,9 @@ struct nemb200_plan {
   // optional CUDA-event timing of k_mstep_onehot (bench.py's roofline): pairs recorded per launch, read back on demand
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> onehot_events;
+  // fork/join for the fuzzy-row sums, which run beside the one-hot count kernel (its fat CTAs leave room on every SM)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint32_t* flags2 = nullptr;     // [0] max |T_new - T_old| as float bits, [1] status (P.status points here)
   // row-sharded exchange over NVLink peer memory (nemb200_peer_*)
   double* logf_full = nullptr;    // [N_total][K] log-densities of ALL rows: every rank's density kernel stores into it
@@ -191,8 +194,10 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   // statistics that a multi-GPU driver all-reduces: one contiguous int32 block and one contiguous fp64 block
   pl->cnt = ar.take<int>(K * Dpad + K); pl->fsum = ar.take<double>(K * Dpad + K);
   pl->nk_cnt = pl->cnt + K * Dpad; pl->nk_fz = pl->fsum + K * Dpad;
+  // hist and cnt_local follow directly: one memset per M-step clears [nk_cnt .. hist] (and the counts on a full recount)
+  pl->hist = ar.take<int>(2 * K + 1);
   pl->cnt_local = ar.take<int>(K * Dpad);
-  pl->hist = ar.take<int>(2 * K + 1); pl->offsets = ar.take<int>(2 * K + 2); pl->cursor = ar.take<int>(2 * K + 1);
+  pl->offsets = ar.take<int>(2 * K + 2); pl->cursor = ar.take<int>(2 * K + 1);
   pl->prev = ar.take<int>(N); pl->ent = ar.take<int2>(N); pl->perm = ar.take<int>(2 * N);
   pl->Lword = ar.take<double>(K * Ws); pl->eps_init = ar.take<float>(K);
   pl->fin_partial = ar.take<double>((size_t)K * pl->fin_chunks * 2); pl->fin_tickets = ar.take<int>(K);
@@ -261,6 +266,9 @@ static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int6
 extern "C" void nemb200_plan_destroy(nemb200_plan* pl) {
   if (!pl) return;
   for (auto& pr : pl->onehot_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+  if (pl->ev_join) cudaEventDestroy(pl->ev_join);
+  if (pl->side) cudaStreamDestroy(pl->side);
   if (pl->attached) {
     cudaDeviceSynchronize();
     for (int r = 0; r < pl->world; r++)
@@ -290,6 +298,7 @@ extern "C" int nemb200_init_params(nemb200_plan* pl, void* stream_) {
   // a new run: no row is counted yet (kNone == -2 is the byte pattern 0xFE repeated)
   CK(cudaMemsetAsync(pl->prev, 0xFE, (size_t)std::max<long long>(pl->N_local, 1) * sizeof(int), st));
   CK(cudaMemsetAsync(pl->cnt_local, 0, (size_t)K * pl->Dpad * sizeof(int), st));
+  CK(cudaMemsetAsync(pl->cnt, 0, (size_t)K * pl->Dpad * sizeof(int), st));
   if (pl->free_disp) {
     const int n = K * pl->Ws;
     k_lword<<<(n + 255) / 256, 256, 0, st>>>(pl->P.L, K, pl->Ws, pl->Dpad, pl->Lword);
@@ -302,7 +311,8 @@ template <int KB>
 static int launch_classify(nemb200_plan* pl, const float* T, cudaStream_t st) {
   const long long N = pl->N_local;
   if (N > 0) {
-    k_classify<KB><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(T, N, pl->K, pl->prev, pl->ent, pl->hist, pl->nk_cnt, pl->nk_fz);
+    k_classify<KB><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(T, N, pl->K, pl->prev, pl->ent, pl->hist, pl->nk_cnt, pl->nk_fz,
+                                                                 (pl->flags & NEMB200_FULL_RECOUNT) ? 1 : 0);
     CK(cudaGetLastError());
   }
   return 0;
@@ -332,14 +342,16 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
   cudaStream_t st = (cudaStream_t)stream_;
   const int K = pl->K;
   const long long N = pl->N_local;
-  if (pl->flags & NEMB200_FULL_RECOUNT) {  // forget the running counts: every one-hot row is streamed again
-    CK(cudaMemsetAsync(pl->prev, 0xFE, (size_t)std::max<long long>(N, 1) * sizeof(int), st));
-    CK(cudaMemsetAsync(pl->cnt_local, 0, (size_t)K * pl->Dpad * sizeof(int), st));
+  // The running one-hot counts live in the exposed block itself unless a collective library reduces that block in place
+  // (row shard without peer mapping): then they are kept in cnt_local and copied out after every update.
+  const bool separate = pl->N_local < pl->N_total && pl->world <= 1;
+  int* cnt_acc = separate ? pl->cnt_local : pl->cnt;
+  {  // one memset: class sizes, fuzzy sums, bucket histogram -- plus the counts when every one-hot row is streamed again
+    const bool full = (pl->flags & NEMB200_FULL_RECOUNT) != 0;
+    char* z0 = (char*)((full && !separate) ? pl->cnt : pl->nk_cnt);
+    char* z1 = (full && separate) ? (char*)(pl->cnt_local + (size_t)K * pl->Dpad) : (char*)(pl->hist + 2 * K + 1);
+    CK(cudaMemsetAsync(z0, 0, (size_t)(z1 - z0), st));
   }
-  CK(cudaMemsetAsync(pl->fsum, 0, (size_t)K * pl->Dpad * sizeof(double), st));
-  CK(cudaMemsetAsync(pl->hist, 0, (2 * K + 1) * sizeof(int), st));
-  CK(cudaMemsetAsync(pl->nk_cnt, 0, K * sizeof(int), st));
-  CK(cudaMemsetAsync(pl->nk_fz, 0, K * sizeof(double), st));
   int rc = DISPATCH_KB(K, launch_classify, pl, T, st);
   if (rc) return rc;
   k_offsets<<<1, 32, 0, st>>>(pl->hist, 2 * K + 1, pl->offsets, pl->cursor);
@@ -356,6 +368,15 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
     const long long slots = (long long)num_sms() * std::max(per_sm, 1);
     const long long slices = std::min<long long>(std::max<long long>(slots / ntiles, 1), 65535);  // longer slices are walked in kMaxRun pieces
     dim3 grid(ntiles, (unsigned)slices);
+    static const bool fork_fuzzy = !(getenv("NEMB200_FUZZY_FORK") && atoi(getenv("NEMB200_FUZZY_FORK")) == 0);
+    if (fork_fuzzy) {
+      if (!pl->side) {
+        CK(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+      }
+      CK(cudaEventRecord(pl->ev_fork, st));   // the index lists are complete here
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (pl->timing) {
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -371,20 +392,28 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
       CK(cudaFuncSetAttribute(k_mstep_onehot_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const long long sl = std::min<long long>(std::max<long long>(num_sms() / ntx, 1), 65535);
       k_mstep_onehot_ring<<<dim3(ntx, (unsigned)sl), kOhTpb, smem, st>>>((const uint4*)bits, W4, tw, K, pl->offsets, pl->perm,
-                                                                        pl->cnt_local, pl->Dpad);
+                                                                        cnt_acc, pl->Dpad);
     } else {
-      k_mstep_onehot<<<grid, kMsTpb, 0, st>>>((const uint2*)bits, W2, tile_w, K, pl->offsets, pl->perm, pl->cnt_local, pl->Dpad);
+      k_mstep_onehot<<<grid, kMsTpb, 0, st>>>((const uint2*)bits, W2, tile_w, K, pl->offsets, pl->perm, cnt_acc, pl->Dpad);
     }
     CK(cudaGetLastError());
     if (pl->timing) {
       CK(cudaEventRecord(e1, st));
       pl->onehot_events.emplace_back(e0, e1);
     }
-    rc = DISPATCH_KB(K, launch_fuzzy, pl, bits, T, st);
-    if (rc) return rc;
+    if (fork_fuzzy) {
+      CK(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
+      rc = DISPATCH_KB(K, launch_fuzzy, pl, bits, T, pl->side);
+      if (rc) return rc;
+      CK(cudaEventRecord(pl->ev_join, pl->side));
+      CK(cudaStreamWaitEvent(st, pl->ev_join, 0));
+    } else {
+      rc = DISPATCH_KB(K, launch_fuzzy, pl, bits, T, st);
+      if (rc) return rc;
+    }
   }
   // the exposed statistics (all-reduced in place by a multi-GPU driver) start from this rank's running counts
-  CK(cudaMemcpyAsync(pl->cnt, pl->cnt_local, (size_t)K * pl->Dpad * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (separate) CK(cudaMemcpyAsync(pl->cnt, pl->cnt_local, (size_t)K * pl->Dpad * sizeof(int), cudaMemcpyDeviceToDevice, st));
   return NEMB200_OK;
 }
 

@@ -613,7 +613,7 @@ template <int KB>
 __global__ void __launch_bounds__(256)
 k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ prev /*[N] in/out: key of last M-step*/,
            int2* __restrict__ ent /*[N]: (remove bucket | -1, add/fuzzy bucket | -1)*/, int* __restrict__ hist /*[2K+1]*/,
-           int* __restrict__ nk_cnt /*[K]*/, double* __restrict__ nk_fz /*[K]*/) {
+           int* __restrict__ nk_cnt /*[K]*/, double* __restrict__ nk_fz /*[K]*/, int ignore_prev /*full recount*/) {
   __shared__ int s_hist[2 * KB + 1];
   __shared__ int s_nk[KB];
   __shared__ double s_fz[KB];
@@ -638,13 +638,13 @@ k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ pr
     int key;
     if (ones == 1 && zeros == K - 1) { key = arg; atomicAdd(&s_nk[key], 1); }
     else { key = K; fuzzy = true; }
-    const int old = prev[i];
+    const int old = ignore_prev ? kNone : prev[i];
     int e0 = -1, e1 = -1;
     if (key == K) e1 = 2 * K;                   // fuzzy: always recomputed
     if (old != key) {
       if (old >= 0 && old < K) e0 = K + old;    // leaves class `old`
       if (key < K) e1 = key;                     // enters class `key`
-      prev[i] = key;
+      if (!ignore_prev) prev[i] = key;
     }
     ent[i] = make_int2(e0, e1);
     if (e0 >= 0) atomicAdd(&s_hist[e0], 1);
