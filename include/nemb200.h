@@ -169,6 +169,11 @@ int nemb200_sweep(nemb200_plan* plan, int64_t N, const double* logf, const float
                   const int32_t* sched_level_ptr, const int32_t* sched_rows, int32_t n_levels,
                   float beta_now, uint32_t* maxdiff_bits, void* stream);
 
+/* A level-scheduled sweep keeps a schedule-ordered copy of the neighbour graph inside the plan, built on first use and
+ * reused while the same rowptr / col / w / sched_rows POINTERS and N are passed.  A caller that changes those arrays in
+ * place, or reuses their addresses for another graph, calls this before the next nemb200_sweep. */
+int nemb200_plan_graph_changed(nemb200_plan* plan);
+
 /* nem_alg.c:2160-2173 (HasConverged, CVTEST_CLAS) needs max |T_new - T_old|; nem_alg.c:1873-1892 needs the empty-class
  * status.  Both in one 8-byte device->host read (synchronises the stream). */
 int nemb200_read_flags(nemb200_plan* plan, float* maxdiff, int32_t* status, void* stream);

@@ -147,6 +147,11 @@ struct nemb200_plan {
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> onehot_events;
   // fork/join for the fuzzy-row sums, which run beside the one-hot count kernel (its fat CTAs leave room on every SM)
+  // schedule-ordered copy of the neighbour graph for the level-scheduled sweep (built on first use, keyed by the arrays)
+  void* ell = nullptr;
+  size_t ell_bytes = 0;
+  const void* ell_key[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long ell_N = 0;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint32_t* flags2 = nullptr;     // [0] max |T_new - T_old| as float bits, [1] status (P.status points here)
@@ -274,6 +279,7 @@ extern "C" void nemb200_plan_destroy(nemb200_plan* pl) {
     for (int r = 0; r < pl->world; r++)
       if (r != pl->rank && pl->peer_base[r]) cudaIpcCloseMemHandle(pl->peer_base[r]);
   }
+  if (pl->ell) cached_free(pl->ell, pl->ell_bytes);
   cached_free(pl->block, pl->block_bytes);
   delete pl;
 }
@@ -679,6 +685,12 @@ extern "C" int nemb200_peer_wait_densities(nemb200_plan* pl, void* stream_) {
   return NEMB200_OK;
 }
 
+extern "C" int nemb200_plan_graph_changed(nemb200_plan* pl) {
+  if (!pl) return fail(NEMB200_ERR_ARG, "plan_graph_changed: null plan");
+  pl->ell_N = 0;
+  return NEMB200_OK;
+}
+
 extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, const float* T_old, float* T_new,
                              const int32_t* rowptr, const int32_t* col, const float* w,
                              const int32_t* sched_level_ptr, const int32_t* sched_rows, int32_t n_levels,
@@ -695,6 +707,15 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
   a.logspace = (pl->flags & NEMB200_EPI_LOGSPACE) ? 1 : 0;
   a.jacobi = (pl->flags & NEMB200_JACOBI) ? 1 : 0;
   a.maxdiff_bits = maxdiff_bits;
+  a.ell_hdr = nullptr; a.ell_nb = nullptr; a.stamps = nullptr;
+#ifdef NEMB200_SWEEP_STAMPS
+  static unsigned long long* stampbuf = nullptr;
+  static int stampcalls = 0;
+  if (getenv("NEMB200_SWEEP_STAMPS")) {
+    if (!stampbuf) { cudaMallocManaged(&stampbuf, 256 * 64 * 8); memset(stampbuf, 0, 256 * 64 * 8); }
+    a.stamps = stampbuf;
+  }
+#endif
   const bool need_levels = (beta_now != 0.0f) && rowptr != nullptr && !a.jacobi;
   if (need_levels && (!sched_level_ptr || !sched_rows || n_levels < 1))
     return fail(NEMB200_ERR_ARG, "sweep: Gauss-Seidel sweep needs a level schedule (nemb200_gs_schedule)");
@@ -702,6 +723,25 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
   const long long rows_per_block = 8LL * (32 / GS);
   if (need_levels && n_levels > 1) {
     a.level_ptr = sched_level_ptr; a.level_rows = sched_rows; a.n_levels = n_levels;
+    {  // schedule-ordered graph copy: rebuilt only when the caller passes other arrays (they must not change in place)
+      const void* key[4] = {rowptr, col, w, sched_rows};
+      if (!pl->ell || pl->ell_N != N || memcmp(key, pl->ell_key, sizeof(key)) != 0) {
+        const size_t bytes = (size_t)N * (sizeof(int4) + kEllW * sizeof(int2));
+        if (pl->ell && pl->ell_bytes < bytes) { CK(cudaStreamSynchronize(st)); cached_free(pl->ell, pl->ell_bytes); pl->ell = nullptr; }
+        if (!pl->ell) {
+          int rc = cached_malloc(&pl->ell, bytes);
+          if (rc) return rc;
+          pl->ell_bytes = bytes;
+        }
+        k_sweep_ell_build<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, sched_rows, rowptr, col, w, (int4*)pl->ell,
+                                                                     (int2*)((int4*)pl->ell + N));
+        CK(cudaGetLastError());
+        memcpy(pl->ell_key, key, sizeof(key));
+        pl->ell_N = N;
+      }
+      a.ell_hdr = (const int4*)pl->ell;
+      a.ell_nb = (const int2*)((const int4*)pl->ell + N);
+    }
     void* fn = GS == 4 ? (void*)k_sweep<true, 4> : GS == 8 ? (void*)k_sweep<true, 8> : GS == 16 ? (void*)k_sweep<true, 16>
                                                                                              : (void*)k_sweep<true, 32>;
     // few, fat CTAs: the grid barrier between levels is the fixed cost of this kernel (ncu: more than half of the
@@ -716,6 +756,18 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
     if (blocks > want) blocks = std::max<long long>(want, 1);
     void* args[] = {&a};
     CK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(tpb), args, 0, st));
+#ifdef NEMB200_SWEEP_STAMPS
+    if (a.stamps && ++stampcalls == 20) {   // one warmed-up launch: first / last CTA to reach each stamp, relative to the first start
+      cudaStreamSynchronize(st);
+      unsigned long long t0 = ~0ull;
+      for (int c = 0; c < blocks; c++) t0 = std::min(t0, stampbuf[c * 64]);
+      for (int s2 = 0; s2 < std::min(2 * n_levels, 64); s2++) {
+        unsigned long long mn = ~0ull, mx = 0;
+        for (int c = 0; c < blocks; c++) { const unsigned long long v = stampbuf[c * 64 + s2]; if (v >= t0) { mn = std::min(mn, v); mx = std::max(mx, v); } }
+        if (mx) fprintf(stderr, "sweep stamp %2d (%s level %d): first CTA %7.2f us, last CTA %7.2f us\n", s2, (s2 & 1) ? "end of  " : "start of", s2 / 2, (mn - t0) / 1e3, (mx - t0) / 1e3);
+      }
+    }
+#endif
   } else {
     a.level_ptr = nullptr; a.level_rows = nullptr; a.n_levels = 1;
     long long blocks = (N + rows_per_block - 1) / rows_per_block;

@@ -487,26 +487,124 @@ struct SweepArgs {
   int logspace;
   int jacobi;
   unsigned* maxdiff_bits;
+  const int4* ell_hdr;   // [N] {row, degree, CSR offset, 0} in schedule order (level-scheduled sweeps)
+  const int2* ell_nb;    // [N][kEllW] (neighbour, weight bits), zero padded
+  unsigned long long* stamps;   // profiling builds (-DNEMB200_SWEEP_STAMPS): per CTA, %globaltimer at level start / end
 };
 
 // One group of GS lanes (GS = power of two >= K) updates one row; lane `sub` of the group owns class `sub`.
+//
+// The sweep is latency, not bandwidth (timed with %globaltimer stamps per level: ~2 us of grid barrier plus 2-4 us of
+// dependent L2 round trips per level, whatever the level's size).  Per row the chain is schedule -> rowptr -> (col, w)
+// -> neighbour posteriors, and only the last link depends on what other rows wrote.  So
+//  * the graph is copied once per (graph, schedule) into schedule order with the first 8 neighbours inline
+//    (k_sweep_ell_build: header {row, degree, CSR offset} + 8 x (j, w) per slot), which makes the graph side of a row
+//    ONE round trip, its address known from the slot number alone;
+//  * that round trip is taken BEFORE the barrier that precedes the row's level (SweepPre, spread over the lanes of the
+//    group: lane s keeps neighbours s, s + GS, ... and hands them out by shuffle);
+//  * after the barrier the neighbour posteriors, the row's log-densities and its old posterior are loaded together,
+//    and the neighbour terms are added in list order (float, no FMA: nem_alg.c:2954-2962).
+constexpr int kEllW = 8;          // neighbours held inline per slot; longer lists continue in the CSR arrays
+template <int GS> struct SweepCfg {
+  static constexpr int NS = GS >= kEllW ? 1 : kEllW / GS;   // neighbour slots per lane
+};
+template <int GS> struct SweepPre {
+  long long i;
+  int n0, deg;
+  int j[SweepCfg<GS>::NS];
+  float w[SweepCfg<GS>::NS];
+  bool valid;
+};
+
+__global__ void __launch_bounds__(256)
+k_sweep_ell_build(long long N, const int* __restrict__ level_rows, const int* __restrict__ rowptr, const int* __restrict__ col,
+                  const float* __restrict__ w, int4* __restrict__ hdr, int2* __restrict__ nb) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N) return;
+  const int i = level_rows[idx];
+  const int n0 = rowptr[i], deg = rowptr[i + 1] - n0;
+  hdr[idx] = make_int4(i, deg, n0, 0);
+#pragma unroll
+  for (int u = 0; u < kEllW; u++)
+    nb[idx * kEllW + u] = u < deg ? make_int2(col[n0 + u], __float_as_int(w[n0 + u])) : make_int2(0, 0);
+}
+
+// graph side of the row in schedule slot `idx` (ELL copy) ...
 template <int GS>
-__device__ __forceinline__ void sweep_row(const SweepArgs& a, long long i, bool valid, int sub, float& wmax) {
-  const int K = a.K;
-  const int k = sub < K ? sub : K - 1;
-  if (!valid) i = 0;
-  float ctx = 0.0f;
+__device__ __forceinline__ SweepPre<GS> sweep_preload_slot(const SweepArgs& a, long long idx, bool valid, int sub) {
+  constexpr int NS = SweepCfg<GS>::NS;
+  SweepPre<GS> p;
+  p.valid = valid;
+  const long long slot = valid ? idx : 0;
+  const int4 h = a.ell_hdr[slot];
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const int u = s * GS + sub;
+    int2 e = make_int2(0, 0);
+    if (u < kEllW) e = a.ell_nb[slot * kEllW + u];        // address independent of the header: one round trip in all
+    p.j[s] = e.x; p.w[s] = __int_as_float(e.y);
+  }
+  p.i = valid ? h.x : 0;
+  p.deg = (valid && a.beta != 0.0f) ? h.y : 0;
+  p.n0 = h.z;
+  return p;
+}
+// ... or of row i straight from the CSR arrays (single-level sweeps, no ELL copy)
+template <int GS>
+__device__ __forceinline__ SweepPre<GS> sweep_preload_csr(const SweepArgs& a, long long i, bool valid, int sub) {
+  constexpr int NS = SweepCfg<GS>::NS;
+  SweepPre<GS> p;
+  p.valid = valid;
+  p.i = valid ? i : 0;
+  p.n0 = 0; p.deg = 0;
+#pragma unroll
+  for (int s = 0; s < NS; s++) { p.j[s] = 0; p.w[s] = 0.0f; }
   if (valid && a.rowptr != nullptr && a.beta != 0.0f) {
-    const int n0 = a.rowptr[i], n1 = a.rowptr[i + 1];
-    for (int n = n0; n < n1; n++) {
-      const int j = a.col[n];
-      const float wt = a.w[n];
-      const float* src = (!a.jacobi && j < i) ? a.T_new : a.T_old;
-      const float c = __ldcg(src + (size_t)j * K + k);     // L2 read: T_new rows are written by other SMs in this launch
-      ctx = __fadd_rn(ctx, __fmul_rn(wt, c));               // float accumulate, no FMA (nem_alg.c:2954-2962)
+    p.n0 = a.rowptr[p.i];
+    p.deg = a.rowptr[p.i + 1] - p.n0;
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      const int u = s * GS + sub;
+      if (u < p.deg && u < kEllW) { p.j[s] = a.col[p.n0 + u]; p.w[s] = a.w[p.n0 + u]; }
     }
   }
+  return p;
+}
+
+template <int GS>
+__device__ __forceinline__ void sweep_finish(const SweepArgs& a, const SweepPre<GS>& p, int sub, float& wmax) {
+  const int K = a.K;
+  const int k = sub < K ? sub : K - 1;
+  const long long i = p.i;
   const double lf = a.logf[(size_t)i * K + k];
+  const float told = a.T_old[(size_t)i * K + k];
+  float ctx = 0.0f;
+  // deg is the same in all lanes of the group; groups of one warp may differ, the shuffles below are group-local and
+  // executed by every lane (invalid rows have deg = 0 but still take part)
+  const int dmax = min(kEllW, __reduce_max_sync(0xffffffffu, p.deg));
+  if (dmax > 0) {
+    float c[kEllW], wt[kEllW];
+#pragma unroll
+    for (int u = 0; u < kEllW; u++) {
+      c[u] = 0.0f; wt[u] = 0.0f;
+      if (u < dmax) {                                   // warp-uniform
+        const int jj = __shfl_sync(0xffffffffu, p.j[u / GS], u % GS, GS);
+        wt[u] = __shfl_sync(0xffffffffu, p.w[u / GS], u % GS, GS);
+        if (u < p.deg) {
+          const float* src = (!a.jacobi && jj < i) ? a.T_new : a.T_old;
+          c[u] = __ldcg(src + (size_t)jj * K + k);      // L2 read: T_new rows are written by other SMs in this launch
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kEllW; u++)
+      if (u < p.deg) ctx = __fadd_rn(ctx, __fmul_rn(wt[u], c[u]));
+    for (int n = p.n0 + kEllW; n < p.n0 + p.deg; n++) {  // rows with more than kEllW neighbours
+      const int j = a.col[n];
+      const float* src = (!a.jacobi && j < i) ? a.T_new : a.T_old;
+      ctx = __fadd_rn(ctx, __fmul_rn(a.w[n], __ldcg(src + (size_t)j * K + k)));
+    }
+  }
   float cnew;
   if (!a.logspace) {
     // reference arithmetic: nem_mod.c:677-679, nem_alg.c:2367, :2665-2698
@@ -534,10 +632,9 @@ __device__ __forceinline__ void sweep_row(const SweepArgs& a, long long i, bool 
     for (int kk = 0; kk < K; kk++) sum = sum + __shfl_sync(0xffffffffu, e, kk, GS);
     cnew = (m == -INFINITY) ? (float)(1.0 / K) : (float)(e / sum);
   }
-  if (valid && sub < K) {
-    const float old = a.T_old[(size_t)i * K + sub];
+  if (p.valid && sub < K) {
     __stcg(a.T_new + (size_t)i * K + sub, cnew);
-    float dif = cnew - old;
+    float dif = cnew - told;
     if (dif < 0) dif = -dif;
     wmax = fmaxf(wmax, dif);
   }
@@ -554,43 +651,75 @@ __global__ void __launch_bounds__(COOP ? 1024 : 256) k_sweep(SweepArgs a) {
   if (a.level_ptr == nullptr) {
     for (long long i0 = warp_global * RPW; i0 < a.N; i0 += nwarps * RPW) {
       const long long i = i0 + grp;
-      sweep_row<GS>(a, i, i < a.N, sub, wmax);
+      const SweepPre<GS> p = sweep_preload_csr<GS>(a, i, i < a.N, sub);
+      sweep_finish<GS>(a, p, sub, wmax);
     }
   } else {
     // Levels are separated by grid-wide barriers; a run of consecutive small levels (deep, thin tails of the schedule)
     // is instead walked by CTA 0 alone with block barriers, so the run costs one grid barrier instead of one per level.
     constexpr int kSmall = 256;
     const int block_warp = threadIdx.x >> 5, block_warps = blockDim.x >> 5;
+    const long long gidx = warp_global * RPW + grp, gtotal = nwarps * RPW;   // this lane group among all groups
+    SweepPre<GS> p0, p1;          // the group's first two rows of the coming grid-wide level, fetched before its barrier
+    bool have_pre = false;
     int L = 0;
+#ifdef NEMB200_SWEEP_STAMPS
+    auto stamp = [&](int slot) {
+      if (a.stamps && threadIdx.x == 0 && slot < 64) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.stamps[blockIdx.x * 64 + slot] = t;
+      }
+    };
+#else
+    auto stamp = [](int) {};
+#endif
+    stamp(0);
+    int b = a.level_ptr[0], e = a.level_ptr[1];
     while (L < a.n_levels) {
-      int b = a.level_ptr[L], e = a.level_ptr[L + 1];
+      int e_next = (L + 1 < a.n_levels) ? a.level_ptr[L + 2] : e;   // asked for early: needed only at the end of the level
       if (COOP && e - b <= kSmall) {
-        while (L < a.n_levels) {
-          b = a.level_ptr[L]; e = a.level_ptr[L + 1];
-          if (e - b > kSmall) break;
+        while (true) {
           if (blockIdx.x == 0) {
             for (long long idx0 = b + (long long)block_warp * RPW; idx0 < e; idx0 += (long long)block_warps * RPW) {
               const long long idx = idx0 + grp;
-              const bool valid = idx < e;
-              sweep_row<GS>(a, valid ? a.level_rows[idx] : 0, valid, sub, wmax);
+              const SweepPre<GS> p = sweep_preload_slot<GS>(a, idx, idx < e, sub);
+              sweep_finish<GS>(a, p, sub, wmax);
             }
             __syncthreads();
           }
-          L++;
+          L++; b = e; e = e_next;
+          if (L >= a.n_levels) break;
+          e_next = (L + 1 < a.n_levels) ? a.level_ptr[L + 2] : e;
+          if (e - b > kSmall) break;
         }
       } else {
-        for (long long idx0 = b + warp_global * RPW; idx0 < e; idx0 += nwarps * RPW) {
-          const long long idx = idx0 + grp;
-          const bool valid = idx < e;
-          sweep_row<GS>(a, valid ? a.level_rows[idx] : 0, valid, sub, wmax);
+        long long idx = b + gidx;
+        if (COOP && have_pre) {
+          sweep_finish<GS>(a, p0, sub, wmax);
+          if (b + gtotal < e) sweep_finish<GS>(a, p1, sub, wmax);   // grid-uniform condition
+          idx += 2 * gtotal;
         }
-        L++;
+        for (long long idx0 = idx - grp; idx0 < e; idx0 += gtotal) {   // idx0: the warp's first slot (warp-uniform loop)
+          const SweepPre<GS> p = sweep_preload_slot<GS>(a, idx0 + grp, idx0 + grp < e, sub);
+          sweep_finish<GS>(a, p, sub, wmax);
+        }
+        L++; b = e; e = e_next;
       }
+      have_pre = false;
       if (COOP && L < a.n_levels) {
+        if (e - b > kSmall) {             // graph side of the next level: independent of what this level wrote
+          p0 = sweep_preload_slot<GS>(a, b + gidx, b + gidx < e, sub);
+          if (b + gtotal < e) p1 = sweep_preload_slot<GS>(a, b + gidx + gtotal, b + gidx + gtotal < e, sub);
+          have_pre = true;
+        }
+        stamp(2 * L - 1);
         __threadfence();
         cg::this_grid().sync();
+        stamp(2 * L);
       }
     }
+    stamp(2 * a.n_levels - 1);
   }
   for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
   if (lane == 0 && wmax > 0.0f) atomicMax(a.maxdiff_bits, __float_as_uint(wmax));  // non-negative floats order as uints

@@ -68,6 +68,7 @@ SIGNATURES = {
     "nemb200_density_peers": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     "nemb200_peer_wait_densities": (ctypes.c_int, [_vp, _vp]),
     "nemb200_sweep": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp]),
+    "nemb200_plan_graph_changed": (ctypes.c_int, [_vp]),
     "nemb200_read_flags": (ctypes.c_int, [_vp, ctypes.POINTER(_f32), ctypes.POINTER(_i32), _vp]),
     "nemb200_criteria": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f32, ctypes.POINTER(ctypes.c_double * 5), _vp]),
     "nemb200_get_params": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.POINTER(_i32), _vp]),
@@ -458,6 +459,12 @@ class Plan:
 
     def sweep(self, N, logf, T_old, T_new, inp: Optional[DeviceInput], beta_now: float, maxdiff):
         g = inp is not None and inp.rowptr is not None
+        if g:   # the plan caches a schedule-ordered copy of the graph, keyed by the array addresses: tell it when the
+            # tensors behind them are other objects or were written to since the last sweep
+            key = tuple((id(t), t._version) for t in (inp.rowptr, inp.col, inp.w, inp.sched_rows))
+            if getattr(self, "_graph_key", None) not in (None, key):
+                _check(lib().nemb200_plan_graph_changed(self._h), "plan_graph_changed")
+            self._graph_key = key
         _check(lib().nemb200_sweep(self._h, N, _ptr(logf), _ptr(T_old), _ptr(T_new), _ptr(inp.rowptr) if g else 0,
                                    _ptr(inp.col) if g else 0, _ptr(inp.w) if g else 0, _ptr(inp.sched_ptr) if g else 0,
                                    _ptr(inp.sched_rows) if g else 0, inp.n_levels if g else 1,
