@@ -325,7 +325,8 @@ static int launch_classify(nemb200_plan* pl, const float* T, cudaStream_t st) {
 }
 template <int KB>
 static int launch_fuzzy(nemb200_plan* pl, const uint32_t* bits, const float* T, cudaStream_t st) {
-  const int col_tiles = (pl->Dpad + 255) / 256;
+  const int cols_per_cta = 256 * FuzzyCfg<KB>::WPT;
+  const int col_tiles = (pl->Dpad + cols_per_cta - 1) / cols_per_cta;
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mstep_fuzzy<KB>, 256, 0));
   const long long slots = (long long)num_sms() * std::max(per_sm, 1);

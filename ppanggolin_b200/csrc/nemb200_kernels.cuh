@@ -1144,12 +1144,15 @@ k_mstep_onehot_ring(const uint4* __restrict__ bits4, int W4, int tile_w /*<= kOh
   }
 }
 
-// Fuzzy rows: fsum[k][d] += T[i][k] for every set bit (i, d) of a fuzzy row.  One thread per genome column with fp64
-// accumulators per class; blockIdx.y owns an equal share of the fuzzy list (the host sizes the grid to the resident CTA
-// slots: in the K-selection sweep at K = 20 nearly every row is fuzzy and this kernel is the M-step).  The share's row
-// ids and posteriors (converted to fp64 once) are staged in shared memory, so the matrix loads of consecutive rows are
-// independent; a warp's 32 lanes look at the same matrix word, so all-zero words are skipped with a uniform branch.
+// Fuzzy rows: fsum[k][d] += T[i][k] for every set bit (i, d) of a fuzzy row.  A thread owns bit `lane` of WPT consecutive
+// matrix words (columns 32 apart) with fp64 accumulators per class; a warp's 32 lanes look at the same words (one
+// 4/8/16-byte broadcast load per row), so all-zero groups are skipped with a uniform branch and a row's posteriors
+// are fetched once for WPT words.  blockIdx.y owns an equal share of the fuzzy list (the host sizes the grid to the
+// resident CTA slots: in the K-selection sweep at K = 20 nearly every row is fuzzy and this kernel is the M-step).  The
+// share's row ids and posteriors (converted to fp64 once) are staged in shared memory, so the matrix loads of
+// consecutive rows are independent.  The kernel is instruction-bound (8 warps x n_fuzzy x Ws / WPT row visits).
 constexpr int kFzRows = 64;
+template <int KB> struct FuzzyCfg { static constexpr int WPT = KB <= 4 ? 4 : (KB <= 8 ? 2 : 1); };
 
 template <int KB>
 __global__ void __launch_bounds__(256)
@@ -1157,53 +1160,99 @@ k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int
               const int* __restrict__ perm, const float* __restrict__ T, double* __restrict__ fsum /*[K][Dpad]*/,
               int Dpad) {
   constexpr int KP = (KB + 1) & ~1;   // even: the staged posteriors are read as double2
-  __shared__ int s_row[kFzRows];
+  constexpr int WPT = FuzzyCfg<KB>::WPT;
+  constexpr int XW = 8 * WPT / 4;     // uint4 per row that the CTA's 8 warps look at (contiguous in the row)
   __shared__ __align__(16) double s_t[kFzRows][KP];
+  __shared__ uint4 s_x[kFzRows][XW];
   const int f0 = offsets[2 * K], f1 = offsets[2 * K + 1];   // the fuzzy bucket
   const int nf = f1 - f0;
   const long long S = min((long long)gridDim.y, max(1LL, ((long long)nf + kFzRows - 1) / kFzRows));
   if (blockIdx.y >= S) return;
   const int lo = f0 + (int)((long long)nf * blockIdx.y / S), hi = f0 + (int)((long long)nf * (blockIdx.y + 1) / S);
   if (lo >= hi) return;
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  const int word = d >> 5, bit = d & 31;
-  const bool in_range = word < Ws;
-  const uint32_t* colp = bits + (in_range ? word : 0);
-  double acc[KB];
+  const int bit = threadIdx.x & 31;
+  const int word0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * WPT;   // Ws is a multiple of 4 >= WPT
+  const bool in_range = word0 < Ws;
+  const int cta_word0 = blockIdx.x * 8 * WPT;
+  double acc[WPT][KB];
 #pragma unroll
-  for (int k = 0; k < KB; k++) acc[k] = 0.0;
+  for (int w = 0; w < WPT; w++)
+#pragma unroll
+    for (int k = 0; k < KB; k++) acc[w][k] = 0.0;
   for (int base = lo; base < hi; base += kFzRows) {
     const int n = min(kFzRows, hi - base);
     __syncthreads();
-    for (int t = threadIdx.x; t < n * KP; t += blockDim.x) {
-      const int r = t / KP, k = t - r * KP;
-      const int row = perm[base + r];
-      if (k == 0) s_row[r] = row;
-      s_t[r][k] = k < K ? (double)T[(size_t)row * K + k] : 0.0;
+    // the batch's posteriors and matrix words in one round of independent loads (row id first, then both)
+    for (int t = threadIdx.x; t < n * (KP + XW); t += blockDim.x) {
+      if (t < n * KP) {
+        const int r = t / KP, k = t - r * KP;
+        const int row = perm[base + r];
+        s_t[r][k] = k < K ? (double)T[(size_t)row * K + k] : 0.0;
+      } else {
+        const int u = t - n * KP;
+        const int r = u / XW, q = u - r * XW;
+        const int row = perm[base + r];
+        const int wq = cta_word0 + 4 * q;
+        s_x[r][q] = wq < Ws ? __ldg(reinterpret_cast<const uint4*>(bits + (size_t)row * Ws + wq)) : make_uint4(0u, 0u, 0u, 0u);
+      }
     }
     __syncthreads();
+    const uint32_t* myx = reinterpret_cast<const uint32_t*>(&s_x[0][0]) + (threadIdx.x >> 5) * WPT;
 #pragma unroll 4
     for (int r = 0; r < n; r++) {
-      const uint32_t x = in_range ? __ldg(colp + (size_t)s_row[r] * Ws) : 0u;
-      if (x != 0u) {                       // warp-uniform: the 32 lanes of a warp share the word
-        if ((x >> bit) & 1u) {
+      uint32_t x[WPT];
+      const uint32_t* src = myx + r * (XW * 4);
+      if (WPT == 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src);
+        x[0] = v.x; x[1 % WPT] = v.y; x[2 % WPT] = v.z; x[3 % WPT] = v.w;
+      } else if (WPT == 2) {
+        const uint2 v = *reinterpret_cast<const uint2*>(src);
+        x[0] = v.x; x[1 % WPT] = v.y;
+      } else {
+        x[0] = *src;
+      }
+      uint32_t any = 0u;
+#pragma unroll
+      for (int w = 0; w < WPT; w++) any |= x[w];
+      if (WPT == 1) {
+        if (any != 0u && ((x[0] >> bit) & 1u)) {
           const double2* tr = reinterpret_cast<const double2*>(&s_t[r][0]);
 #pragma unroll
           for (int k2 = 0; k2 < KP / 2; k2++) {
             if (2 * k2 < K) {
               const double2 v = tr[k2];
-              acc[2 * k2] += v.x;
-              if (2 * k2 + 1 < KB) acc[2 * k2 + 1] += v.y;
+              acc[0][2 * k2] += v.x;
+              if (2 * k2 + 1 < KB) acc[0][2 * k2 + 1] += v.y;
             }
+          }
+        }
+      } else if (any != 0u) {              // warp-uniform: the 32 lanes of a warp share the words
+        double t[KP];
+        const double2* tr = reinterpret_cast<const double2*>(&s_t[r][0]);
+#pragma unroll
+        for (int k2 = 0; k2 < KP / 2; k2++) {
+          t[2 * k2] = 0.0; t[2 * k2 + 1] = 0.0;
+          if (2 * k2 < K) { const double2 v = tr[k2]; t[2 * k2] = v.x; t[2 * k2 + 1] = v.y; }
+        }
+#pragma unroll
+        for (int w = 0; w < WPT; w++) {
+          if ((x[w] >> bit) & 1u) {
+#pragma unroll
+            for (int k = 0; k < KB; k++)
+              if (k < K) acc[w][k] += t[k];
           }
         }
       }
     }
   }
-  if (d < D) {
 #pragma unroll
-    for (int k = 0; k < KB; k++)
-      if (k < K && acc[k] != 0.0) atomicAdd(&fsum[(size_t)k * Dpad + d], acc[k]);
+  for (int w = 0; w < WPT; w++) {
+    const int d = (word0 + w) * 32 + bit;
+    if (in_range && d < D) {
+#pragma unroll
+      for (int k = 0; k < KB; k++)
+        if (k < K && acc[w][k] != 0.0) atomicAdd(&fsum[(size_t)k * Dpad + d], acc[w][k]);
+    }
   }
 }
 
