@@ -200,9 +200,9 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   pl->cnt = ar.take<int>(K * Dpad + K); pl->fsum = ar.take<double>(K * Dpad + K);
   pl->nk_cnt = pl->cnt + K * Dpad; pl->nk_fz = pl->fsum + K * Dpad;
   // hist and cnt_local follow directly: one memset per M-step clears [nk_cnt .. hist] (and the counts on a full recount)
-  pl->hist = ar.take<int>(2 * K + 1);
+  pl->hist = ar.take<int>(2 * K + 1); pl->cursor = ar.take<int>(2 * K + 1);
   pl->cnt_local = ar.take<int>(K * Dpad);
-  pl->offsets = ar.take<int>(2 * K + 2); pl->cursor = ar.take<int>(2 * K + 1);
+  pl->offsets = ar.take<int>(2 * K + 2);
   pl->prev = ar.take<int>(N); pl->ent = ar.take<int2>(N); pl->perm = ar.take<int>(2 * N);
   pl->Lword = ar.take<double>(K * Ws); pl->eps_init = ar.take<float>(K);
   pl->fin_partial = ar.take<double>((size_t)K * pl->fin_chunks * 2); pl->fin_tickets = ar.take<int>(K);
@@ -356,15 +356,13 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
   {  // one memset: class sizes, fuzzy sums, bucket histogram -- plus the counts when every one-hot row is streamed again
     const bool full = (pl->flags & NEMB200_FULL_RECOUNT) != 0;
     char* z0 = (char*)((full && !separate) ? pl->cnt : pl->nk_cnt);
-    char* z1 = (full && separate) ? (char*)(pl->cnt_local + (size_t)K * pl->Dpad) : (char*)(pl->hist + 2 * K + 1);
+    char* z1 = (full && separate) ? (char*)(pl->cnt_local + (size_t)K * pl->Dpad) : (char*)(pl->cursor + 2 * K + 1);
     CK(cudaMemsetAsync(z0, 0, (size_t)(z1 - z0), st));
   }
   int rc = DISPATCH_KB(K, launch_classify, pl, T, st);
   if (rc) return rc;
-  k_offsets<<<1, 32, 0, st>>>(pl->hist, 2 * K + 1, pl->offsets, pl->cursor);
-  CK(cudaGetLastError());
   if (N > 0) {
-    k_scatter<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pl->ent, N, pl->cursor, pl->perm);
+    k_scatter<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(pl->ent, N, pl->hist, 2 * K + 1, pl->offsets, pl->cursor, pl->perm);
     CK(cudaGetLastError());
     // column tiles of equal width; row slices sized so that the whole grid is one resident wave
     const int W2 = pl->Ws / 2;

@@ -800,40 +800,45 @@ k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ pr
   }
 }
 
-// offsets[b] = first slot of bucket b in perm (b = 0..2K; offsets[2K+1] = total); cursor = running copy for k_scatter
-__global__ void k_offsets(const int* __restrict__ hist, int nb, int* __restrict__ offsets /*[nb+1]*/,
-                          int* __restrict__ cursor /*[nb]*/) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int acc = 0;
-    for (int b = 0; b < nb; b++) {
-      offsets[b] = acc;
-      cursor[b] = acc;
-      acc += hist[b];
-    }
-    offsets[nb] = acc;
-  }
-}
-
 // rows -> perm, grouped by bucket.  One atomic per (warp, bucket present in the warp) instead of one per entry: the
 // handful of cursors is shared by all rows, and per-row atomics on them serialise (measured 70 us for 200 000 rows).
-__device__ __forceinline__ void scatter_one(int key, long long i, int lane, int* __restrict__ cursor, int* __restrict__ perm) {
+__device__ __forceinline__ void scatter_one(int key, long long i, int lane, const int* s_off, int* __restrict__ fill,
+                                            int* __restrict__ perm) {
   const unsigned peers = __match_any_sync(0xffffffffu, key);
   const int leader = __ffs(peers) - 1;
   const int rank = __popc(peers & ((1u << lane) - 1u));
   int base = 0;
-  if (key >= 0 && lane == leader) base = atomicAdd(&cursor[key], __popc(peers));
+  if (key >= 0 && lane == leader) base = s_off[key] + atomicAdd(&fill[key], __popc(peers));
   base = __shfl_sync(0xffffffffu, base, leader);
   if (key >= 0) perm[base + rank] = (int)i;
 }
 
+// offsets[b] = first slot of bucket b in perm (prefix sums of the histogram, b = 0..nb; offsets[nb] = total): every CTA
+// derives them itself (nb <= 65), CTA 0 also publishes them for the count kernels; `fill` (zeroed by the caller) counts
+// the slots handed out per bucket.
 __global__ void __launch_bounds__(256)
-k_scatter(const int2* __restrict__ ent, long long N, int* __restrict__ cursor, int* __restrict__ perm) {
+k_scatter(const int2* __restrict__ ent, long long N, const int* __restrict__ hist, int nb, int* __restrict__ offsets /*[nb+1]*/,
+          int* __restrict__ fill /*[nb]*/, int* __restrict__ perm) {
+  __shared__ int s_off[2 * NEMB200_MAX_K + 2];
+  if (threadIdx.x < 32) {   // warp scan over <= 65 buckets, 3 per lane
+    const int lane = threadIdx.x;
+    int h[3], tot = 0;
+#pragma unroll
+    for (int q = 0; q < 3; q++) { const int b = lane * 3 + q; h[q] = b < nb ? hist[b] : 0; tot += h[q]; }
+    int incl = tot;
+    for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+    int acc = incl - tot;
+#pragma unroll
+    for (int q = 0; q < 3; q++) { const int b = lane * 3 + q; if (b <= nb) s_off[b] = acc; acc += h[q]; }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) for (int b = threadIdx.x; b <= nb; b += blockDim.x) offsets[b] = s_off[b];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int2 e = make_int2(-1, -1);
   if (i < N) e = ent[i];
-  scatter_one(e.x, i, lane, cursor, perm);
-  scatter_one(e.y, i, lane, cursor, perm);
+  scatter_one(e.x, i, lane, s_off, fill, perm);
+  scatter_one(e.y, i, lane, s_off, fill, perm);
 }
 
 constexpr int kPlanes = 12;
@@ -1345,14 +1350,25 @@ k_mstep_finalize(Params P, PeerStats ps, long long N_total, double* __restrict__
     s_last = (atomicAdd(&tickets[k], 1) == nchunk - 1);
   }
   __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
+  if (!s_last || wid != 0) return;
   __threadfence();
-  tickets[k] = 0;  // ready for the next M-step
+  // chunk partials added in chunk order (deterministic); the loads of 32 chunks are in flight together
   double tot_iner = 0.0, tot_b = 0.0;
-  for (int c = 0; c < nchunk; c++) {
-    tot_iner += __ldcg(&partial[((size_t)k * nchunk + c) * 2 + 0]);
-    tot_b += __ldcg(&partial[((size_t)k * nchunk + c) * 2 + 1]);
+  for (int c0 = 0; c0 < nchunk; c0 += 32) {
+    const int c = c0 + lane;
+    double v0 = 0.0, v1 = 0.0;
+    if (c < nchunk) {
+      v0 = __ldcg(&partial[((size_t)k * nchunk + c) * 2 + 0]);
+      v1 = __ldcg(&partial[((size_t)k * nchunk + c) * 2 + 1]);
+    }
+    const int m = min(32, nchunk - c0);
+    for (int j = 0; j < m; j++) {
+      tot_iner += __shfl_sync(0xffffffffu, v0, j);
+      tot_b += __shfl_sync(0xffffffffu, v1, j);
+    }
   }
+  if (lane != 0) return;
+  tickets[k] = 0;  // ready for the next M-step
   const float pkf = (float)(nk / (double)N_total);       // nem_mod.c:455-459
   P.pk[k] = pkf;
   const double lp = ((double)pkf > kEps) ? log((double)pkf) : -INFINITY;  // nem_alg.c:2350-2356
