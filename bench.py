@@ -315,8 +315,8 @@ def run_ours(a):
     if rank == 0:
         peak, peak_src = measured_peaks()
         st_mean = stage.mean(0)
-        names = ["mstep_accumulate (classify/offsets/scatter + k_mstep_onehot + k_mstep_fuzzy)", "mstep_finalize (+ all-reduce)",
-                 "density (k_density_sk)", "sweep (k_sweep, level-scheduled; + all-gather)"]
+        names = ["mstep_accumulate (classify/scatter + k_mstep_onehot_ring with k_mstep_fuzzy beside it)", "mstep_finalize (+ all-reduce)",
+                 "density (k_density_sk_ring)", "sweep (k_sweep, level-scheduled; + all-gather)"]
         n_loc = hi - lo
         x_bytes = n_loc * ((D + 7) // 8)
         traffic = {}
@@ -324,9 +324,9 @@ def run_ours(a):
         if tp.is_file():
             traffic = json.loads(tp.read_text())
         kernels = {
-            "k_density_sk": {"ms": float(st_mean[2]), "bytes": x_bytes + n_loc * K * 8 + 2 * K * ((D + 7) // 8),
+            "k_density_sk_ring": {"ms": float(st_mean[2]), "bytes": x_bytes + n_loc * K * 8 + 2 * K * ((D + 7) // 8),
                              "what": "matrix bits + log-densities out + centre planes"},
-            "k_mstep_onehot": {"ms": onehot_ms / max(onehot_n, 1), "bytes": x_bytes + n_loc * 4 + K * D * 4,
+            "k_mstep_onehot_ring": {"ms": onehot_ms / max(onehot_n, 1), "bytes": x_bytes + n_loc * 4 + K * D * 4,
                                "what": "matrix bits + row lists + column counts out"}}
         for kk, v in kernels.items():
             v["achieved_GBs"] = v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else None
@@ -339,7 +339,7 @@ def run_ours(a):
                 "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit ops + f64 epilogue", "data": "synthetic",
                 "config": workload_config(a), "gpu_launches": launches, "clocks": clocks,
                 "mstep_mode": "incremental" if a.incremental else "full recount every iteration",
-                "exchange": ("none (1 GPU)" if world == 1 else ("NCCL all-reduce + all-gather" if a.nccl else "NVLink peer memory, fused into k_mstep_finalize / k_density_sk")),
+                "exchange": ("none (1 GPU)" if world == 1 else ("NCCL all-reduce + all-gather" if a.nccl else "NVLink peer memory: peer loads in k_mstep_finalize, k_peer_broadcast after the density kernel")),
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBs"], "peak": peak,
                              "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": tr, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": kernels[dom]["bytes"], "kernel_ms": kernels[dom]["ms"],
