@@ -381,6 +381,9 @@ def run_ours(a):
         del be, em
         sp.bits = None
         torch.cuda.empty_cache()
+        # one untimed call first (device allocator cache, module load), then the timed one: every timed call still moves
+        # the whole matrix host -> device and the posteriors back
+        engine.nem_run_host(hb, D, sp.rowptr, sp.col, sp.w, K, beta, False, 100, 0.01, engine.EPI_LOGSPACE)
         t0 = time.perf_counter()
         run = engine.nem_run_host(hb, D, sp.rowptr, sp.col, sp.w, K, beta, False, 100, 0.01, engine.EPI_LOGSPACE)
         dt = time.perf_counter() - t0
@@ -397,15 +400,20 @@ def run_ours(a):
         del be, em
         sp.bits = None
         torch.cuda.empty_cache()
+        def one_job():
+            dbits = host_bits.to(dev, non_blocking=True)
+            g2 = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), D, sp.rowptr, sp.col, sp.w, device=dev)
+            # a one-shot job: the CUDA-IPC mapping of the peer path costs more than it saves over ~13 iterations -> NCCL exchange
+            be2 = CudaBackend(dbits, D, N, K, False, engine.EPI_LOGSPACE, g2, peer_group=None, row_offset=lo)
+            res = ShardedEM(be2, N, K, rank, world, group).run(beta, 100, 0.01)
+            if rank == 0:
+                _ = res.T.cpu()
+            return res
+
+        one_job()          # untimed: NCCL communicator set-up, allocator cache
         barrier()
         t0 = time.perf_counter()
-        dbits = host_bits.to(dev, non_blocking=True)
-        g2 = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), D, sp.rowptr, sp.col, sp.w, device=dev)
-        # a one-shot job: the CUDA-IPC mapping of the peer path costs more than it saves over ~13 iterations -> NCCL exchange
-        be2 = CudaBackend(dbits, D, N, K, False, engine.EPI_LOGSPACE, g2, peer_group=None, row_offset=lo)
-        out = ShardedEM(be2, N, K, rank, world, group).run(beta, 100, 0.01)
-        if rank == 0:
-            _ = out.T.cpu()
+        out = one_job()
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)

@@ -70,7 +70,7 @@ class CudaBackend:
         self.plan.init_params(); self.launches += 1
 
     def accumulate(self, T_local):
-        self.plan.mstep_accumulate(self.bits, T_local); self.launches += 5
+        self.plan.mstep_accumulate(self.bits, T_local); self.launches += 4   # classify, scatter, one-hot counts, fuzzy sums
 
     def stats(self):
         return self.plan.stats_blocks()   # two contiguous blocks: int32 counts + class sizes, fp64 fuzzy sums + sizes
