@@ -233,6 +233,38 @@ def workload_config(a):
 
 
 # ---------------------------------------------------------------------------------------------------------- our arm
+class FlagPipe:
+    """The per-iteration convergence word max |T_new - T_old|, read the way the library's own run loop reads it: every
+    sweep writes its own device word, the word travels to pinned host memory right behind the sweep, and the host looks
+    at iteration s - 1 after it has enqueued iteration s -- so the GPU never waits for the host between iterations."""
+
+    def __init__(self, steps, dev):
+        import torch
+        self.torch = torch
+        self.dev_words = torch.zeros(steps, dtype=torch.int32, device=dev)
+        self.host_words = torch.zeros(steps, dtype=torch.int32, pin_memory=True)
+        self.events = [torch.cuda.Event() for _ in range(steps)]
+        self.maxdiff = []
+
+    def word(self, s):
+        return self.dev_words[s:s + 1]
+
+    def _collect(self, s):
+        self.events[s].synchronize()
+        self.maxdiff.append(float(self.host_words[s:s + 1].view(self.torch.float32).item()))
+
+    def step_enqueued(self, s):
+        self.host_words[s:s + 1].copy_(self.dev_words[s:s + 1], non_blocking=True)
+        self.events[s].record()
+        if s >= 1:
+            self._collect(s - 1)
+
+    def finish(self, be):
+        self._collect(len(self.events) - 1)
+        _, status = be.read_flags()
+        return [(md, status) for md in self.maxdiff]
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -275,29 +307,46 @@ def run_ours(a):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    be.launches = 0
-    be.plan.timing(True)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
     st = torch.cuda.current_stream()
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+
+    def one_step(pipe, s, e=None):
+        if e: e[0].record(st)
+        be.accumulate(be.T[em.cur][em.lo:em.hi])
+        if e: e[1].record(st)
+        em._allreduce_stats(); be.finalize()
+        if e: e[2].record(st)
+        be.density(be.logf_full[em.lo:em.hi])
+        if e: e[3].record(st)
+        em._allgather_logf(); be.sweep(be.T[em.cur], be.T[1 - em.cur], beta, pipe.word(s)); em.cur = 1 - em.cur
+        if e: e[4].record(st)
+        pipe.step_enqueued(s)
+
+    # ---- the timed region: exactly a.steps EM iterations, nothing but the iterations between the two events
+    be.launches = 0
+    pipe = FlagPipe(a.steps, dev)
     barrier()
     t_start.record(st)
-    statuses = []
     for s in range(a.steps):
-        e = ev[s]
-        e[0].record(st)
-        be.accumulate(be.T[em.cur][em.lo:em.hi]); e[1].record(st)
-        em._allreduce_stats(); be.finalize(); e[2].record(st)
-        be.density(be.logf_full[em.lo:em.hi]); e[3].record(st)
-        em._allgather_logf(); be.sweep(be.T[em.cur], be.T[1 - em.cur], beta); em.cur = 1 - em.cur; e[4].record(st)
-        statuses.append(be.read_flags())
+        one_step(pipe, s)
     t_end.record(st)
     barrier()
+    launches = be.launches
     clocks = sampler.stop() if sampler else None
+    statuses = pipe.finish(be)
+    # ---- the same iterations again with CUDA events between the stages (and around the one-hot count kernel, inside the
+    # library) for the per-kernel roofline: kept out of the timed region, an event record costs stream time too
+    n_prof = min(a.steps, 30)
+    be.plan.timing(True)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(n_prof)]
+    pipe2 = FlagPipe(n_prof, dev)
+    for s in range(n_prof):
+        one_step(pipe2, s, ev[s])
+    barrier()
+    pipe2.finish(be)
     onehot_ms, onehot_n = be.plan.timing(False)
     ms_total = t_start.elapsed_time(t_end)
     stage = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in ev])  # accumulate, finalize, density, sweep
-    launches = be.launches
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
@@ -357,11 +406,19 @@ def run_ours(a):
             em_i.iterate(beta)
         barrier()
         s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+        pipe_i = FlagPipe(a.steps, dev)
+        barrier()
         s0.record(st)
-        for _ in range(a.steps):
-            em_i.iterate(beta)
+        for s in range(a.steps):
+            em_i.m_step()
+            be_i.density(be_i.logf_full[em_i.lo:em_i.hi])
+            em_i._allgather_logf(); be_i.sweep(be_i.T[em_i.cur], be_i.T[1 - em_i.cur], beta, pipe_i.word(s)); em_i.cur = 1 - em_i.cur
+            pipe_i.step_enqueued(s)
         s1.record(st)
         barrier()
+        pipe_i.finish(be_i)
+        for _ in range(n_prof):      # as many iterations as the full-recount arm has done by now: the posteriors must be identical
+            em_i.iterate(beta)
         ms_i = s0.elapsed_time(s1)
         if world > 1:
             t = torch.tensor([ms_i], dtype=torch.float64, device=dev)

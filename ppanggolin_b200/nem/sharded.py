@@ -84,10 +84,12 @@ class CudaBackend:
         else:
             self.plan.density(self.bits, logf_local); self.launches += 1
 
-    def sweep(self, T_old, T_new, beta_now):
+    def sweep(self, T_old, T_new, beta_now, maxdiff=None):
+        """maxdiff: optional zeroed int32 device word receiving max |T_new - T_old| as float bits (a pipelined driver
+        reads it one iteration late); None uses the plan's own word, read with read_flags()."""
         if self.peer:
             self.plan.peer_wait_densities(); self.launches += 1
-        self.plan.sweep(self.N, self.logf_full, T_old, T_new, self.graph, beta_now, None); self.launches += 1
+        self.plan.sweep(self.N, self.logf_full, T_old, T_new, self.graph, beta_now, maxdiff); self.launches += 1
 
     def read_flags(self):
         """(max |T_new - T_old|, status) -- the only per-iteration device->host read."""
