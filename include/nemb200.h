@@ -19,7 +19,7 @@
  *
  * Conventions: plain pointers and sizes, no torch types.  Matrix layout: row-major uint32 words, bit b of word w of a
  * row is genome column 32*w+b; `row_stride_words` is a multiple of 4 (rows start 16-byte aligned) and padding bits
- * are zero.  All functions return NEMB200_OK (0) or a negative error; nemb200_last_error() gives the message of the
+ * are zero; for wide matrices a multiple of 32 (whole 128-byte lines) is what the streaming kernels run fastest on.  All functions return NEMB200_OK (0) or a negative error; nemb200_last_error() gives the message of the
  * calling thread's last failure.  A run whose EM hits an empty class reports it in result->status (the reference
  * then writes no .uf and partition.py:233-265 returns ({}, None, None)); that is not an API error.
  * There is no CPU fallback: without a CUDA device every compute entry fails with NEMB200_ERR_CUDA.
