@@ -167,6 +167,8 @@ struct nemb200_plan {
   const int* peer_iblock[kMaxPeers] = {nullptr};
   const double* peer_dblock[kMaxPeers] = {nullptr};
   int epoch_stats = 0, epoch_dens = 0;
+  int* bcast_ticket = nullptr;    // [1] CTAs of k_peer_broadcast that have finished
+  bool sweep_waits = false;       // the next sweep waits for every rank's densities (nemb200_peer_wait_densities)
   int fin_chunks = 0;
   float* eps_init = nullptr;
   double* crit_partial = nullptr;
@@ -207,7 +209,7 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   pl->Lword = ar.take<double>(K * Ws); pl->eps_init = ar.take<float>(K);
   pl->fin_partial = ar.take<double>((size_t)K * pl->fin_chunks * 2); pl->fin_tickets = ar.take<int>(K);
   pl->crit_partial = ar.take<double>((size_t)pl->crit_blocks * 4); pl->crit4 = ar.take<double>(8);
-  pl->sig = ar.take<int>(2 * kMaxPeers); pl->peer_err = ar.take<int>(1); pl->sig_ptrs = ar.take<int*>(kMaxPeers);
+  pl->sig = ar.take<int>(2 * kMaxPeers); pl->peer_err = ar.take<int>(1); pl->bcast_ticket = ar.take<int>(1); pl->sig_ptrs = ar.take<int*>(kMaxPeers);
   if (pl->flags & NEMB200_PEER_EXCHANGE) pl->logf_full = ar.take<double>((size_t)pl->N_total * K);
   // the sweep and the criteria run over all rows, also on a shard's plan; one region of ceil(N/warps) rows per warp
   pl->crit_terms = ar.take<float>(((size_t)pl->N_total + (size_t)pl->crit_blocks * 8) * K * 2);
@@ -259,7 +261,7 @@ static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int6
   Arena real;
   real.base = (char*)pl->block; real.counting = false;
   plan_layout(pl, real);
-  if (cudaMemset(pl->sig, 0, 2 * kMaxPeers * sizeof(int)) != cudaSuccess || cudaMemset(pl->peer_err, 0, sizeof(int)) != cudaSuccess ||
+  if (cudaMemset(pl->sig, 0, 2 * kMaxPeers * sizeof(int)) != cudaSuccess || cudaMemset(pl->peer_err, 0, sizeof(int)) != cudaSuccess || cudaMemset(pl->bcast_ticket, 0, sizeof(int)) != cudaSuccess ||
       cudaMemset(pl->fin_tickets, 0, K * sizeof(int)) != cudaSuccess) {
     nemb200_plan_destroy(pl);
     return fail(NEMB200_ERR_CUDA, "plan_create: memset");
@@ -470,9 +472,7 @@ extern "C" int nemb200_mstep_finalize(nemb200_plan* pl, void* stream_) {
     // the all-reduce of the M-step statistics, fused into this kernel: publish "my statistics of this iteration are
     // complete", wait for every rank's, then read and add all ranks' blocks in rank order (peer loads over NVLink)
     const int epoch = ++pl->epoch_stats;
-    k_peer_signal<<<1, 32, 0, st>>>(pl->sig_ptrs, pl->world, 0, pl->rank, epoch);
-    CK(cudaGetLastError());
-    k_peer_wait<<<1, 32, 0, st>>>(pl->sig, pl->world, 0, epoch, pl->peer_err);
+    k_peer_signal_wait<<<1, 32, 0, st>>>(pl->sig_ptrs, pl->sig, pl->world, 0, pl->rank, epoch, pl->peer_err);
     CK(cudaGetLastError());
     ps.n = pl->world;
     for (int r = 0; r < pl->world; r++) { ps.iblock[r] = pl->peer_iblock[r]; ps.dblock[r] = pl->peer_dblock[r]; }
@@ -659,15 +659,17 @@ extern "C" int nemb200_density_peers(nemb200_plan* pl, const uint32_t* bits, int
       if (first & 1) {                                  // 16-byte stores need an even start: leading double on its own
         PeerOut one = out;
         one.row_off = first;
-        k_peer_broadcast<<<dim3(1, pl->world - 1), 32, 0, st>>>(pl->logf_full, one, 1);
+        k_peer_broadcast<<<dim3(1, pl->world - 1), 32, 0, st>>>(pl->logf_full, one, 1, nullptr, nullptr, 0, 0, 0);
         CK(cudaGetLastError());
         first += 1; count -= 1;
       }
-      if (count > 0) {
+      if (count > 0) {   // the last CTA of the push publishes "densities of this epoch are in place"
         out.row_off = first;
         dim3 grid(std::max(1, std::min(32, (int)((count / 2 + 255) / 256))), pl->world - 1);
-        k_peer_broadcast<<<grid, 256, 0, st>>>(pl->logf_full, out, count);
+        k_peer_broadcast<<<grid, 256, 0, st>>>(pl->logf_full, out, count, pl->bcast_ticket, pl->sig_ptrs, 1, pl->rank,
+                                               ++pl->epoch_dens);
         CK(cudaGetLastError());
+        return NEMB200_OK;
       }
     }
   }
@@ -675,12 +677,10 @@ extern "C" int nemb200_density_peers(nemb200_plan* pl, const uint32_t* bits, int
   CK(cudaGetLastError());
   return NEMB200_OK;
 }
-
-/* Blocks the stream until every rank has published the current densities epoch (call before the sweep). */
 extern "C" int nemb200_peer_wait_densities(nemb200_plan* pl, void* stream_) {
   if (!pl || !pl->attached) return fail(NEMB200_ERR_ARG, "peer_wait_densities: plan is not attached to its peers");
-  k_peer_wait<<<1, 32, 0, (cudaStream_t)stream_>>>(pl->sig, pl->world, 1, pl->epoch_dens, pl->peer_err);
-  CK(cudaGetLastError());
+  (void)stream_;
+  pl->sweep_waits = true;   // folded into the next nemb200_sweep: its CTAs check the flags themselves
   return NEMB200_OK;
 }
 
@@ -707,6 +707,11 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
   a.jacobi = (pl->flags & NEMB200_JACOBI) ? 1 : 0;
   a.maxdiff_bits = maxdiff_bits;
   a.ell_hdr = nullptr; a.ell_nb = nullptr; a.stamps = nullptr;
+  a.wait_sig = nullptr; a.wait_n = 0; a.wait_epoch = 0; a.wait_err = nullptr;
+  if (pl->sweep_waits) {
+    a.wait_sig = pl->sig; a.wait_n = pl->world; a.wait_epoch = pl->epoch_dens; a.wait_err = pl->peer_err;
+    pl->sweep_waits = false;
+  }
 #ifdef NEMB200_SWEEP_STAMPS
   static unsigned long long* stampbuf = nullptr;
   static int stampcalls = 0;

@@ -78,17 +78,36 @@ struct PeerStats {          // where k_mstep_finalize reads: the statistic block
 };
 
 // push this rank's freshly computed shard of log-densities (contiguous rows of its own buffer) into the same rows of
-// every peer's buffer: 16-byte coalesced peer stores, one peer per blockIdx.y
+// every peer's buffer: 16-byte coalesced peer stores, one peer per blockIdx.y.  With `ticket` != null the last CTA to
+// finish (all stores fenced at system scope) also publishes the epoch in every rank's signal words: the "densities
+// ready" signal of the exchange, without a launch of its own.
 __global__ void __launch_bounds__(256)
-k_peer_broadcast(const double* __restrict__ own, PeerOut out /*ptr[1..n-1] = peers*/, long long n_doubles /*shard size*/) {
+k_peer_broadcast(const double* __restrict__ own, PeerOut out /*ptr[1..n-1] = peers*/, long long n_doubles /*shard size*/,
+                 int* ticket, int* const* peer_sig, int phase, int rank, int epoch) {
   const int peer = blockIdx.y + 1;
-  if (peer >= out.n) return;
-  const long long off = out.row_off;                  // in doubles, even (K * row_off rounded by the caller)
-  const double2* src = reinterpret_cast<const double2*>(own + off);
-  double2* dst = reinterpret_cast<double2*>(out.ptr[peer] + off);
-  const long long n2 = n_doubles / 2;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (long long)gridDim.x * blockDim.x) dst[t] = src[t];
-  if ((n_doubles & 1) && blockIdx.x == 0 && threadIdx.x == 0) out.ptr[peer][off + n_doubles - 1] = own[off + n_doubles - 1];
+  if (peer < out.n) {
+    const long long off = out.row_off;                  // in doubles, even (K * row_off rounded by the caller)
+    const double2* src = reinterpret_cast<const double2*>(own + off);
+    double2* dst = reinterpret_cast<double2*>(out.ptr[peer] + off);
+    const long long n2 = n_doubles / 2;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (long long)gridDim.x * blockDim.x) dst[t] = src[t];
+    if ((n_doubles & 1) && blockIdx.x == 0 && threadIdx.x == 0) out.ptr[peer][off + n_doubles - 1] = own[off + n_doubles - 1];
+  }
+  if (ticket == nullptr) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int total = gridDim.x * gridDim.y;
+    if (atomicAdd(ticket, 1) == total - 1) {
+      *ticket = 0;
+      __threadfence_system();
+      for (int r = 0; r < out.n; r++) {
+        volatile int* dst = peer_sig[r] + phase * kMaxPeers + rank;
+        *dst = epoch;
+      }
+      __threadfence_system();
+    }
+  }
 }
 
 // every rank owns sig[2][kMaxPeers] ints: sig[phase][r] = last epoch rank r has completed for that phase
@@ -100,6 +119,28 @@ __global__ void k_peer_signal(int* const* peer_sig /*[n] device pointers to the 
     *dst = epoch;
     __threadfence_system();
   }
+}
+__device__ __forceinline__ void peer_wait_lane(const int* sig, int n, int phase, int epoch, int* error) {
+  if (threadIdx.x < n) {
+    const volatile int* src = sig + phase * kMaxPeers + threadIdx.x;
+    long long spins = 0;
+    while (*src < epoch) {
+      __nanosleep(200);
+      if (++spins > (1LL << 24)) { atomicExch(error, 2); break; }   // ~several seconds: never hang the GPU
+    }
+    __threadfence_system();
+  }
+}
+// publish this rank's epoch, then wait for every rank's: the flag barrier in front of k_mstep_finalize in one launch
+__global__ void k_peer_signal_wait(int* const* peer_sig, const int* sig, int n, int phase, int rank, int epoch, int* error) {
+  if (blockIdx.x != 0) return;
+  if (threadIdx.x < n) {
+    __threadfence_system();
+    volatile int* dst = peer_sig[threadIdx.x] + phase * kMaxPeers + rank;
+    *dst = epoch;
+    __threadfence_system();
+  }
+  peer_wait_lane(sig, n, phase, epoch, error);
 }
 __global__ void k_peer_wait(const int* sig /*own sig array*/, int n, int phase, int epoch, int* error) {
   if (threadIdx.x < n && blockIdx.x == 0) {
@@ -489,6 +530,9 @@ struct SweepArgs {
   unsigned* maxdiff_bits;
   const int4* ell_hdr;   // [N] {row, degree, CSR offset, 0} in schedule order (level-scheduled sweeps)
   const int2* ell_nb;    // [N][kEllW] (neighbour, weight bits), zero padded
+  const int* wait_sig;   // row-sharded runs: the rank's signal words; the sweep starts when every rank's densities are in
+  int wait_n, wait_epoch;
+  int* wait_err;
   unsigned long long* stamps;   // profiling builds (-DNEMB200_SWEEP_STAMPS): per CTA, %globaltimer at level start / end
 };
 
@@ -648,6 +692,10 @@ __global__ void __launch_bounds__(COOP ? 1024 : 256) k_sweep(SweepArgs a) {
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   float wmax = 0.0f;
+  if (a.wait_sig != nullptr) {     // every CTA checks the flags itself (phase 1 = densities): no wait kernel in front
+    peer_wait_lane(a.wait_sig, a.wait_n, 1, a.wait_epoch, a.wait_err);
+    __syncthreads();
+  }
   if (a.level_ptr == nullptr) {
     for (long long i0 = warp_global * RPW; i0 < a.N; i0 += nwarps * RPW) {
       const long long i = i0 + grp;

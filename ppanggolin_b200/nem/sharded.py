@@ -76,11 +76,11 @@ class CudaBackend:
         return self.plan.stats_blocks()   # two contiguous blocks: int32 counts + class sizes, fp64 fuzzy sums + sizes
 
     def finalize(self):
-        self.plan.mstep_finalize(); self.launches += 3 if self.peer else 1   # peer mode: + signal + wait kernels
+        self.plan.mstep_finalize(); self.launches += 2 if self.peer else 1   # peer mode: + the signal-and-wait kernel
 
     def density(self, logf_local):
         if self.peer:   # stores into every rank's buffer and publishes the epoch: the all-gather, fused
-            self.plan.density_peers(self.bits, self.row_offset); self.launches += 3   # density + shard push + signal
+            self.plan.density_peers(self.bits, self.row_offset); self.launches += 2   # density + shard push (its last CTA signals)
         else:
             self.plan.density(self.bits, logf_local); self.launches += 1
 
@@ -88,7 +88,7 @@ class CudaBackend:
         """maxdiff: optional zeroed int32 device word receiving max |T_new - T_old| as float bits (a pipelined driver
         reads it one iteration late); None uses the plan's own word, read with read_flags()."""
         if self.peer:
-            self.plan.peer_wait_densities(); self.launches += 1
+            self.plan.peer_wait_densities()   # no launch: the sweep's CTAs check the flags themselves
         self.plan.sweep(self.N, self.logf_full, T_old, T_new, self.graph, beta_now, maxdiff); self.launches += 1
 
     def read_flags(self):

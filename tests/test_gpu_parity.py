@@ -593,3 +593,53 @@ def test_onehot_counts_ring_equals_small_cta_kernel(eng, N, D, K, monkeypatch):
         assert np.array_equal(res["0"][step], res["1"][step])
         assert np.array_equal(res["1"][step][:, :D], want)
         assert not res["1"][step][:, D:].any()
+
+
+@pytest.mark.gpu
+def test_sweep_graph_copy_is_refreshed_when_the_graph_changes(eng):
+    """The plan keeps a schedule-ordered copy of the neighbour graph, keyed by the array addresses.  Rewriting the graph
+    tensors in place (same addresses) must not leave a stale copy behind: the binding notices the version bump and calls
+    nemb200_plan_graph_changed."""
+    import torch
+    N, D, K = 3000, 200, 3
+    spa = synth_pangenome(N, D, seed=5)
+    spb = synth_pangenome(N, D, seed=6)
+    assert len(spa.col) != len(spb.col) or not np.array_equal(spa.col, spb.col)
+    nmax = max(len(spa.col), len(spb.col))
+
+    def padded(sp):   # same tensor sizes for both graphs so that one can be copied over the other
+        col = np.zeros(nmax, np.int32); col[:len(sp.col)] = sp.col
+        w = np.zeros(nmax, np.float32); w[:len(sp.w)] = sp.w
+        return sp.rowptr, col, w
+
+    def run(plan, inp, logf, beta):
+        T0 = torch.full((N, K), 1.0 / K, dtype=torch.float32, device="cuda")
+        T0[:, 0] += torch.linspace(0, 0.2, N, device="cuda")     # something the neighbour term can act on
+        T1 = torch.empty_like(T0)
+        plan.sweep(N, logf, T0, T1, inp, beta, None)
+        torch.cuda.synchronize()
+        return T1.clone()
+
+    plan = eng.Plan(N, N, D, spa.bits.shape[1], K, False, eng.EPI_REF)
+    plan.init_params()
+    bits_a = eng.DeviceInput.from_numpy(spa.bits, D, *padded(spa))
+    logf = torch.empty((N, K), dtype=torch.float64, device="cuda")
+    plan.density(bits_a.bits, logf)
+    beta = float(np.float32(spa.beta_eff(2.5)))
+    out_a = run(plan, bits_a, logf, beta)
+    # graph B written over graph A's tensors
+    inp_b = eng.DeviceInput.from_numpy(spb.bits, D, *padded(spb))
+    for name in ("rowptr", "col", "w", "sched_ptr", "sched_rows"):
+        dst, src = getattr(bits_a, name), getattr(inp_b, name)
+        if dst.shape == src.shape:
+            dst.copy_(src)
+        else:   # the level pointer array may differ in length: swap the tensor and the count
+            setattr(bits_a, name, src)
+    bits_a.n_levels = inp_b.n_levels
+    out_b_same_plan = run(plan, bits_a, logf, beta)
+    fresh = eng.Plan(N, N, D, spa.bits.shape[1], K, False, eng.EPI_REF)
+    fresh.init_params()
+    out_b_fresh = run(fresh, inp_b, logf, beta)
+    assert torch.equal(out_b_same_plan, out_b_fresh)
+    assert not torch.equal(out_a, out_b_fresh)
+    plan.close(); fresh.close()
