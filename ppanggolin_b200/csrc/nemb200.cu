@@ -168,6 +168,7 @@ struct nemb200_plan {
   const double* peer_dblock[kMaxPeers] = {nullptr};
   int epoch_stats = 0, epoch_dens = 0;
   int* bcast_ticket = nullptr;    // [1] CTAs of k_peer_broadcast that have finished
+  int sweep_cta_cap = 0;          // > 0: CTAs of the cooperative sweep (instances of a batch run side by side)
   bool sweep_waits = false;       // the next sweep waits for every rank's densities (nemb200_peer_wait_densities)
   int fin_chunks = 0;
   float* eps_init = nullptr;
@@ -758,6 +759,7 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
     const long long rows_per_cta = (long long)(tpb / 32) * (32 / GS);
     const long long want = (N + rows_per_cta - 1) / rows_per_cta;
     if (blocks > want) blocks = std::max<long long>(want, 1);
+    if (pl->sweep_cta_cap > 0) blocks = std::min<long long>(blocks, pl->sweep_cta_cap);   // batched instances share the SMs
     void* args[] = {&a};
     CK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(tpb), args, 0, st));
 #ifdef NEMB200_SWEEP_STAMPS
@@ -1099,6 +1101,9 @@ extern "C" int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* b
     if (cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking) != cudaSuccess) { rc = fail(NEMB200_ERR_CUDA, "nem_device_batch: stream"); break; }
     rc = plan_build(&plans[i], N[i], N[i], D[i], row_stride_words[i], K[i], free_disp[i], flags, true);
     if (rc) break;
+    // sweeps of up to four instances side by side: measured on 8 chunk instances (100 000 x 500), 9.7 -> 7.8 ms per batch,
+    // while a single instance loses nothing down to a third of the SMs (its levels hold < 2 rows per lane group)
+    if (n_inst > 1) plans[i]->sweep_cta_cap = std::max(num_sms() / 4, (num_sms() + n_inst - 1) / n_inst);
     EmRun& r = runs[i];
     r.pl = plans[i]; r.bits = bits[i];
     r.rowptr = graph ? rowptr[i] : nullptr; r.col = graph ? col[i] : nullptr; r.w = graph ? w[i] : nullptr;
