@@ -140,7 +140,8 @@ struct nemb200_plan {
   int* prev = nullptr;      // [N_local] key of every row at the previous M-step (kNone before the first)
   int2* ent = nullptr;      // [N_local] bucket entries of the current M-step
   int* perm = nullptr;      // [2 * N_local] rows grouped by bucket
-  double* Lword = nullptr;  // [K][Ws] (skd)
+  double* Ltab = nullptr;   // [K][Ws * 8][16] (skd): partial sums of the log-odds per nibble
+  double* Lword = nullptr;  // [K][Ws] (skd): totals per 32-column word
   double* fin_partial = nullptr;  // [K][nchunk][2]
   int* fin_tickets = nullptr;     // [K]
   // optional CUDA-event timing of k_mstep_onehot (bench.py's roofline): pairs recorded per launch, read back on demand
@@ -207,7 +208,7 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   pl->cnt_local = ar.take<int>(K * Dpad);
   pl->offsets = ar.take<int>(2 * K + 2);
   pl->prev = ar.take<int>(N); pl->ent = ar.take<int2>(N); pl->perm = ar.take<int>(2 * N);
-  pl->Lword = ar.take<double>(K * Ws); pl->eps_init = ar.take<float>(K);
+  pl->Ltab = ar.take<double>(pl->free_disp ? K * Ws * 128 : (size_t)1); pl->Lword = ar.take<double>(K * Ws); pl->eps_init = ar.take<float>(K);
   pl->fin_partial = ar.take<double>((size_t)K * pl->fin_chunks * 2); pl->fin_tickets = ar.take<int>(K);
   pl->crit_partial = ar.take<double>((size_t)pl->crit_blocks * 4); pl->crit4 = ar.take<double>(8);
   pl->sig = ar.take<int>(2 * kMaxPeers); pl->peer_err = ar.take<int>(1); pl->bcast_ticket = ar.take<int>(1); pl->sig_ptrs = ar.take<int*>(kMaxPeers);
@@ -309,8 +310,8 @@ extern "C" int nemb200_init_params(nemb200_plan* pl, void* stream_) {
   CK(cudaMemsetAsync(pl->cnt_local, 0, (size_t)K * pl->Dpad * sizeof(int), st));
   CK(cudaMemsetAsync(pl->cnt, 0, (size_t)K * pl->Dpad * sizeof(int), st));
   if (pl->free_disp) {
-    const int n = K * pl->Ws;
-    k_lword<<<(n + 255) / 256, 256, 0, st>>>(pl->P.L, K, pl->Ws, pl->Dpad, pl->Lword);
+    const long long n = (long long)K * pl->Ws;
+    k_ltab<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pl->P.L, K, pl->Ws, pl->Ltab, pl->Lword);
     CK(cudaGetLastError());
   }
   return NEMB200_OK;
@@ -481,8 +482,8 @@ extern "C" int nemb200_mstep_finalize(nemb200_plan* pl, void* stream_) {
   k_mstep_finalize<<<dim3(pl->fin_chunks, pl->K), 256, 0, st>>>(pl->P, ps, pl->N_total, pl->fin_partial, pl->fin_tickets);
   CK(cudaGetLastError());
   if (pl->free_disp) {
-    const int n = pl->K * pl->Ws;
-    k_lword<<<(n + 255) / 256, 256, 0, st>>>(pl->P.L, pl->K, pl->Ws, pl->Dpad, pl->Lword);
+    const long long n = (long long)pl->K * pl->Ws;
+    k_ltab<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pl->P.L, pl->K, pl->Ws, pl->Ltab, pl->Lword);
     CK(cudaGetLastError());
   }
   return NEMB200_OK;
@@ -575,8 +576,8 @@ static int launch_density_skd(nemb200_plan* pl, const uint32_t* bits, double* lo
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_density_skd<KB><<<(unsigned)blocks, 256, 0, st>>>(bits, pl->N_local, pl->Ws, pl->K, pl->Dpad, G, pl->P.m1,
-                                                      pl->P.valid, pl->P.L, pl->Lword, pl->P.B, logf);
+  k_density_skd<KB><<<(unsigned)blocks, 256, 0, st>>>(bits, pl->N_local, pl->Ws, pl->K, G, pl->P.m1, pl->P.valid, pl->Ltab,
+                                                      pl->Lword, pl->P.B, logf);
   CK(cudaGetLastError());
   return 0;
 }

@@ -445,13 +445,17 @@ k_density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int K, in
   else      density_sk_ring<KB, KX, RB, P, TPB, false>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf);
 }
 
-// free dispersion ("skd"): per-column log-odds.  sum over mismatching columns of L_kd, taken over the set bits of the
-// mismatch word or of its complement, whichever is sparser (Lsum holds the per-word totals).
+// free dispersion ("skd"): per-column log-odds, logf_ik = B_k - sum over mismatching columns d of L_kd.  The sum walks
+// the non-zero NIBBLES of the mismatch word -- or of its complement, subtracted from the word's total, whichever has
+// fewer set bits -- with one lookup per nibble in a table of the 16 partial sums of every nibble (k_ltab, rebuilt after
+// each M-step: K x D/4 x 16 doubles, 48 KB for a 500-genome chunk instance).  Rows that match their class or mismatch
+// almost everywhere (the common cases) cost 0-2 lookups per word, mixed rows at most 8.  +inf entries (e_kd <= 1e-20)
+// propagate to the reference's null density; a word whose total is infinite is summed directly.
 template <int KB>
 __global__ void __launch_bounds__(256)
-k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int Dpad, int G,
-              const uint32_t* __restrict__ m1, const uint32_t* __restrict__ valid, const double* __restrict__ Lkd,
-              const double* __restrict__ Lword, const double* __restrict__ B, double* __restrict__ logf) {
+k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int G,
+              const uint32_t* __restrict__ m1, const uint32_t* __restrict__ valid, const double* __restrict__ Ltab /*[K][Ws*8][16]*/,
+              const double* __restrict__ Lword /*[K][Ws]*/, const double* __restrict__ B, double* __restrict__ logf) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
   const int grp = lane / G;
@@ -469,27 +473,19 @@ k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int
 #pragma unroll
         for (int k = 0; k < KB; k++) {
           if (k < K) {
-            const uint32_t v = valid[k * Ws + c];
-            uint32_t mm = (x ^ m1[k * Ws + c]) & v;   // mismatching columns
-            const double* Lrow = Lkd + (size_t)k * Dpad + (size_t)c * 32;
-            if (__popc(mm) <= 16) {
-              double a = 0.0;
-              while (mm) { const int b = __ffs(mm) - 1; a += Lrow[b]; mm &= mm - 1; }
-              s[k] += a;
-            } else {
-              uint32_t ok = ~mm & v;  // matching, valid columns (padding columns carry L = 0)
-              double a = Lword[(size_t)k * Ws + c];
-              // subtract the matches; +inf entries (e == 0) cannot be subtracted -> handle by direct sum instead
-              if (isinf(a)) {
-                a = 0.0;
-                while (mm) { const int b = __ffs(mm) - 1; a += Lrow[b]; mm &= mm - 1; }
-              } else {
-                while (ok) { const int b = __ffs(ok) - 1; a -= Lrow[b]; ok &= ok - 1; }
-                // columns with mu == 0.5 are in neither set but are part of Lword: remove them
-                uint32_t half = ~v;
-                while (half) { const int b = __ffs(half) - 1; a -= Lrow[b]; half &= half - 1; }
+            const uint32_t mm = (x ^ m1[k * Ws + c]) & valid[k * Ws + c];   // mismatching columns
+            if (mm != 0u) {
+              const double* tab = Ltab + ((size_t)k * Ws + c) * 128;
+              const double lw = Lword[(size_t)k * Ws + c];     // all 32 columns of the word (padding and mu = 0.5 included)
+              const bool direct = __popc(mm) <= 16 || isinf(lw);
+              uint32_t it = direct ? mm : ~mm;                  // the complement holds matches, mu = 0.5 and padding columns
+              double acc = 0.0;
+              while (it) {
+                const int q = (__ffs(it) - 1) >> 2;
+                acc += __ldg(tab + q * 16 + ((it >> (4 * q)) & 15u));
+                it &= ~(15u << (4 * q));
               }
-              s[k] += a;
+              s[k] += direct ? acc : lw - acc;
             }
           }
         }
@@ -1444,15 +1440,28 @@ __global__ void k_expand_eps(Params P) {
   for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < P.D; d += gridDim.x * blockDim.x) P.eps[(size_t)k * P.D + d] = e;
 }
 
-// per-word totals of L_kd for the complement trick of k_density_skd
-__global__ void k_lword(const double* __restrict__ Lkd, int K, int Ws, int Dpad, double* __restrict__ Lword) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= K * Ws) return;
-  const int k = t / Ws, c = t % Ws;
-  const double* p = Lkd + (size_t)k * Dpad + (size_t)c * 32;
-  double s = 0.0;
-  for (int b = 0; b < 32; b++) s += p[b];
-  Lword[t] = s;
+// nibble tables of k_density_skd: Ltab[k][q][v] = sum of L_kd over the set bits b of v, d = 4 q + b  (q over Dpad / 4),
+// and the totals of every 32-column word.  One thread per (class, word).
+__global__ void k_ltab(const double* __restrict__ Lkd, int K, int Ws, double* __restrict__ Ltab, double* __restrict__ Lword) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (k, word): [K][Dpad] is contiguous
+  if (t >= (long long)K * Ws) return;
+  double total = 0.0;
+  for (int q = 0; q < 8; q++) {
+    const double* l = Lkd + t * 32 + q * 4;
+    const double l0 = l[0], l1 = l[1], l2 = l[2], l3 = l[3];
+    double* out = Ltab + (t * 8 + q) * 16;
+#pragma unroll
+    for (int v = 0; v < 16; v++) {
+      double a = 0.0;
+      if (v & 1) a += l0;
+      if (v & 2) a += l1;
+      if (v & 4) a += l2;
+      if (v & 8) a += l3;
+      out[v] = a;
+    }
+    total += ((l0 + l1) + l2) + l3;
+  }
+  Lword[t] = total;
 }
 
 // initial parameters: partition.py:65-85 (values) + nem_exe.c:1023-1040 (last proportion by subtraction)
