@@ -643,3 +643,25 @@ def test_sweep_graph_copy_is_refreshed_when_the_graph_changes(eng):
     assert torch.equal(out_b_same_plan, out_b_fresh)
     assert not torch.equal(out_a, out_b_fresh)
     plan.close(); fresh.close()
+
+
+@pytest.mark.gpu
+def test_file_based_entry_point_wide_matrix(eng, tmp_path):
+    """More than 64 words per row: the file reader pads rows to whole 128-byte lines (same rule as the array exporters).
+    Beyond the reference's numeric range (D > 1500), so the check is against the in-memory entry point on the same data."""
+    N, D, K = 400, 2100, 3
+    sp = synth_pangenome(N, D, seed=77)
+    assert sp.bits.shape[1] == 96
+    beta = float(np.float32(sp.beta_eff(2.5)))
+    w_text = [repr(round(float(v), 4)) for v in sp.w]
+    refnem.write_nem_files(tmp_path, sp.X, refnem.csr_to_nei_lists(N, sp.rowptr, sp.col, w_text))
+    refnem.write_init_file(tmp_path, K, D)
+    rc = _our_nem(tmp_path, K, beta, False, 20)
+    out = refnem.parse_ref_outputs(tmp_path, K, D)
+    run = eng.nem_run_host(sp.bits, D, sp.rowptr, sp.col, sp.w, K, beta, False, 20, 0.01, eng.EPI_REF)
+    assert (rc == 0) == (run.status == 0)
+    if run.status == 0:
+        T3 = np.rint(run.T.astype(np.float64) * 1000) / 1000
+        assert out is not None and out["n_iter"] == run.n_iter
+        assert np.abs(out["T3"] - T3).max() <= 1e-3 + 1e-9
+        assert abs(out["crit"][3] - run.crit[3]) <= 1e-5 * abs(run.crit[3])

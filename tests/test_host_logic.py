@@ -82,6 +82,21 @@ def test_pack_unpack_roundtrip():
         assert int(np.unpackbits(b.view(np.uint8), axis=1, bitorder="little")[:, D:].sum()) == 0
 
 
+def test_row_pitch_rules():
+    """The C ABI takes any multiple of 4 words that holds D bits; the exporters pad wide matrices to whole 128-byte lines
+    (the streaming kernels' cp.async copies need rows that start on a sector boundary) and keep narrow ones compact."""
+    from ppanggolin_b200.synthetic import row_stride_words
+    for D in (1, 31, 32, 33, 127, 128, 129, 500, 1000, 2047, 2048, 2049, 4100, 20000, 50000, 99999):
+        W = row_stride_words(D)
+        assert W * 32 >= D and W % 4 == 0
+        words = (D + 31) // 32
+        if words <= 64:
+            assert W < words + 4               # at most 3 padding words
+        else:
+            assert W % 32 == 0 and W < words + 32
+    assert row_stride_words(500) == 16 and row_stride_words(50000) == 1568
+
+
 def test_parser_flags_match_reference_defaults():
     import argparse
     p = argparse.ArgumentParser()
