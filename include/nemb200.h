@@ -174,6 +174,12 @@ int nemb200_sweep(nemb200_plan* plan, int64_t N, const double* logf, const float
  * place, or reuses their addresses for another graph, calls this before the next nemb200_sweep. */
 int nemb200_plan_graph_changed(nemb200_plan* plan);
 
+/* Diagnostics.  The criteria D and G are float32 sums taken in the reference's order (nem_alg.c:2813-2823); large
+ * instances compute them with a parallel scheme that must give the bits of the sequential sum.  This entry runs either
+ * implementation on caller-supplied terms (host arrays of n floats each) so that tests can compare them on adversarial
+ * inputs: out2[0] = sum of d, out2[1] = sum of g, each accumulated in float32 from 0 in index order. */
+int nemb200_selftest_float_chain(const float* d, const float* g, int64_t n, int32_t parallel, double out2[2]);
+
 /* nem_alg.c:2160-2173 (HasConverged, CVTEST_CLAS) needs max |T_new - T_old|; nem_alg.c:1873-1892 needs the empty-class
  * status.  Both in one 8-byte device->host read (synchronises the stream). */
 int nemb200_read_flags(nemb200_plan* plan, float* maxdiff, int32_t* status, void* stream);

@@ -180,6 +180,9 @@ struct nemb200_plan {
   int* crit_counts = nullptr;     // [crit_blocks * 8] terms per region
   int* crit_offsets = nullptr;    // [crit_blocks * 8 + 1]
   float* crit_dense = nullptr;    // the regions' terms, contiguous and in order
+  long long* crit_rec = nullptr;  // k_crit_chain_par: per (chunk, chain) records, 3 x int64 + flag
+  int* crit_recbad = nullptr;
+  CcState* crit_state = nullptr;
   // run buffers of the whole-run drivers (nem_host / nem_device / batch); not used by the stepwise interface
   bool with_run_buffers = false;
   double* run_logf = nullptr;
@@ -218,6 +221,10 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   pl->crit_counts = ar.take<int>((size_t)pl->crit_blocks * 8);
   pl->crit_offsets = ar.take<int>((size_t)pl->crit_blocks * 8 + 1);
   pl->crit_dense = ar.take<float>(((size_t)pl->N_total * K + 64) * 2);
+  {
+    const size_t nch = ((size_t)pl->N_total * K + kCcChunk - 1) / kCcChunk + 1;
+    pl->crit_rec = ar.take<long long>(nch * 2 * 3); pl->crit_recbad = ar.take<int>(nch * 2); pl->crit_state = ar.take<CcState>(1);
+  }
   if (pl->with_run_buffers) {
     pl->run_logf = ar.take<double>(N * K); pl->run_Ta = ar.take<float>(N * K); pl->run_Tb = ar.take<float>(N * K);
   }
@@ -817,8 +824,24 @@ static int criteria_enqueue(nemb200_plan* pl, int64_t N, const double* logf, con
     k_crit_compact<<<(n_warps + 7) / 8, 256, 0, st>>>((const float2*)pl->crit_terms, pl->crit_counts, pl->crit_offsets, n_warps,
                                                     a.rows_per_warp, pl->K, (float2*)pl->crit_dense);
     CK(cudaGetLastError());
-    k_crit_chain<<<1, 64, 0, st>>>((const float2*)pl->crit_dense, pl->crit_offsets, n_warps, pl->crit4);  // D, G
-    CK(cudaGetLastError());
+    // D, G: float32 sums in the reference's order -- sequential chain for small instances, the exact parallel scheme above it
+    const size_t nch = ((size_t)N * pl->K + kCcChunk - 1) / kCcChunk + 1;
+    const char* force = getenv("NEMB200_CRIT_SEQ");
+    if (force ? atoi(force) != 0 : (size_t)N * pl->K < 32768) {
+      k_crit_chain<<<1, 64, 0, st>>>((const float2*)pl->crit_dense, pl->crit_offsets, n_warps, pl->crit4);
+      CK(cudaGetLastError());
+    } else {
+      const float2* dense = (const float2*)pl->crit_dense;
+      const int* offs = pl->crit_offsets;
+      int nreg = n_warps;
+      long long *rR = pl->crit_rec, *rMn = pl->crit_rec + nch * 2, *rMx = pl->crit_rec + nch * 4;
+      int* rBad = pl->crit_recbad;
+      CcState* stp = pl->crit_state;
+      double* out = pl->crit4;
+      void* args[] = {&dense, &offs, &nreg, &rR, &rMn, &rMx, &rBad, &stp, &out};
+      const int blocks = (int)std::min<size_t>(std::max<size_t>(nch / 8, 1), (size_t)32);   // few CTAs: cheap barriers, batched instances side by side
+      CK(cudaLaunchCooperativeKernel((void*)k_crit_chain_par, dim3(blocks), dim3(256), args, 0, st));
+    }
   }
   return 0;
 }
@@ -853,6 +876,52 @@ extern "C" int nemb200_criteria(nemb200_plan* pl, int64_t N, const double* logf,
   int rc = criteria_enqueue(pl, N, logf, T, rowptr, col, w, beta, st);
   if (rc) return rc;
   return criteria_collect(pl, beta, crit_out, st);
+}
+
+extern "C" int nemb200_selftest_float_chain(const float* d, const float* g, int64_t n, int32_t parallel, double out2[2]) {
+  if (!d || !g || n < 0 || n > 0x7fffffffLL || !out2) return fail(NEMB200_ERR_ARG, "selftest_float_chain: bad argument");
+  std::vector<float2> h((size_t)std::max<int64_t>(n, 1));
+  for (int64_t i = 0; i < n; i++) h[(size_t)i] = make_float2(d[i], g[i]);
+  const size_t nch = ((size_t)n + kCcChunk - 1) / kCcChunk + 1;
+  const size_t b_dense = h.size() * sizeof(float2), b_rec = nch * 2 * 3 * sizeof(long long), b_bad = nch * 2 * sizeof(int);
+  void *p_dense = nullptr, *p_rec = nullptr, *p_bad = nullptr, *p_misc = nullptr;
+  int rc;
+  if ((rc = cached_malloc(&p_dense, b_dense))) return rc;
+  if ((rc = cached_malloc(&p_rec, b_rec))) { cached_free(p_dense, b_dense); return rc; }
+  if ((rc = cached_malloc(&p_bad, b_bad))) { cached_free(p_dense, b_dense); cached_free(p_rec, b_rec); return rc; }
+  if ((rc = cached_malloc(&p_misc, 256))) { cached_free(p_dense, b_dense); cached_free(p_rec, b_rec); cached_free(p_bad, b_bad); return rc; }
+  auto release = [&]() { cached_free(p_dense, b_dense); cached_free(p_rec, b_rec); cached_free(p_bad, b_bad); cached_free(p_misc, 256); };
+  int* offs = (int*)p_misc;                       // [2] offsets, then the state, then the two results
+  CcState* stp = (CcState*)((char*)p_misc + 64);
+  double* out = (double*)((char*)p_misc + 128);
+  const int hoffs[2] = {0, (int)n};
+  cudaError_t e = cudaMemcpy(p_dense, h.data(), b_dense, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(offs, hoffs, sizeof hoffs, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const float2* dense = (const float2*)p_dense;
+    const int* co = offs;
+    int nreg = 1;
+    if (parallel) {
+      long long *rR = (long long*)p_rec, *rMn = rR + nch * 2, *rMx = rR + nch * 4;
+      int* rBad = (int*)p_bad;
+      void* args[] = {&dense, &co, &nreg, &rR, &rMn, &rMx, &rBad, &stp, &out};
+      const int blocks = (int)std::min<size_t>(std::max<size_t>(nch / 8, 1), (size_t)32);
+      e = cudaLaunchCooperativeKernel((void*)k_crit_chain_par, dim3(blocks), dim3(256), args, 0, nullptr);
+    } else {
+      k_crit_chain<<<1, 64>>>(dense, co, nreg, out);
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out2, out, 2 * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && parallel && getenv("NEMB200_CHAIN_DEBUG")) {
+    CcState hs;
+    if (cudaMemcpy(&hs, stp, sizeof hs, cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "float chain: %lld terms, %zu chunks, %d rounds, chunks added sequentially: %d / %d\n", (long long)n, nch - 1, hs.rounds,
+              hs.seq_chunks[0], hs.seq_chunks[1]);
+  }
+  release();
+  if (e != cudaSuccess) return fail(NEMB200_ERR_CUDA, "selftest_float_chain: %s", cudaGetErrorString(e));
+  return NEMB200_OK;
 }
 
 extern "C" int nemb200_get_params(nemb200_plan* pl, float* mu, float* eps, float* pk, int32_t* status, void* stream_) {

@@ -18,6 +18,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <climits>
+
 namespace nemb200 {
 namespace cg = cooperative_groups;
 
@@ -1661,6 +1663,209 @@ k_crit_compact(const float2* __restrict__ terms, const int* __restrict__ counts,
   const float2* src = terms + (size_t)r * rows_per_warp * K;
   float2* dst = dense + offsets[r];
   for (int t = lane; t < n; t += 32) dst[t] = src[t];
+}
+
+// ---- the same float32 sequential sums, computed in parallel and still bit-exact ------------------------------------------
+// A dependent chain of float adds runs at one add per 2-3 ns: 3.2 ms for the 10^6 terms of a K = 20 instance, more than
+// its ten EM iterations.  But while the running sum s stays inside one binade [2^E, 2^(E+1)), every partial sum is a
+// multiple of u = ulp(s) = 2^(E-23), and fl(s + x) = s + rn_u(x): the rounded addend rn_u(x) (x rounded to the nearest
+// multiple of u) does not depend on s -- except on an exact tie, where round-to-even looks at s.  So, given the exact
+// state s at some term, the integers r_i = rn_u(x_i) / u of ALL following terms can be computed in parallel, summed per
+// chunk with integer prefix sums (which also give the smallest and largest partial sum inside the chunk), and the state
+// advances over whole chunks by integer addition for as long as the partial sums stay inside the binade and no tie
+// occurs.  At the first chunk where that fails (a binade crossing -- about log2(n) of them for sums that grow -- a tie,
+// or a zero / subnormal state) the chunk is added sequentially, and the following chunks are redone with the new u.
+// Cooperative kernel, rounds separated by grid barriers; in the worst case it degrades to plain sequential adds chunk
+// by chunk, never to a different result (tests compare it bit for bit with k_crit_chain on adversarial inputs).
+constexpr int kCcChunk = 512;
+constexpr int kCcMinTerms = 50000;   // below this many terms the plain chain wins
+struct CcState { float s[2]; int cur[2]; int rounds; int seq_chunks[2]; };   // per chain (0: D, 1: G): exact running sum, next chunk
+
+__device__ __forceinline__ bool cc_binade(float s, int& E) {   // normal, non-zero, finite
+  if (!(fabsf(s) >= 1.17549435e-38f) || !isfinite(s)) return false;
+  E = ilogbf(s);
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+k_crit_chain_par(const float2* __restrict__ dense, const int* __restrict__ offsets, int n_regions,
+                 long long* __restrict__ recR, long long* __restrict__ recMn, long long* __restrict__ recMx,
+                 int* __restrict__ recFlag /*each [nchunks][2]; flag bit 0: needs the sequential path, bit 1: all terms zero*/,
+                 CcState* state, double* __restrict__ out4) {
+  cg::grid_group grid = cg::this_grid();
+  const int total = offsets[n_regions];
+  const int nchunks = (total + kCcChunk - 1) / kCcChunk;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  volatile CcState* vs = state;
+  if (total < kCcMinTerms) {   // short sums: the plain chain is quicker than a dozen rounds (uniform branch: no barrier is skipped)
+    if (blockIdx.x == 0 && (threadIdx.x >> 5) < 2) {
+      const int which = threadIdx.x >> 5;
+      auto fetch = [&](int t) -> float {
+        if (t < total) { const float2 v = dense[t]; return which == 0 ? v.x : v.y; }
+        return 0.0f;
+      };
+      float acc = 0.0f;
+      float x = fetch(lane), x1 = fetch(32 + lane);
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const float x2 = fetch(t0 + 64 + lane);
+#pragma unroll
+        for (int q = 0; q < 32; q++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x, q));
+        x = x1; x1 = x2;
+      }
+      if (lane == 0) out4[which] = (double)acc;
+    }
+    return;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    vs->s[0] = 0.0f; vs->s[1] = 0.0f; vs->cur[0] = 0; vs->cur[1] = 0; vs->rounds = 0; vs->seq_chunks[0] = 0; vs->seq_chunks[1] = 0;
+  }
+  __threadfence();
+  grid.sync();
+  for (int round = 0; round < 2 * nchunks + 4; round++) {
+    const int cur0 = vs->cur[0], cur1 = vs->cur[1];
+    if (cur0 >= nchunks && cur1 >= nchunks) break;
+    const float s0 = vs->s[0], s1 = vs->s[1];
+    // ---- A: records of the next chunks for the current binade of each chain.  Only a window is prepared: a sum of
+    // like-signed terms cannot leave its binade before it has doubled, so about as many chunks as are behind it.
+    int E0 = 0, E1 = 0;
+    const bool ok0 = cc_binade(s0, E0), ok1 = cc_binade(s1, E1);
+    const int first = min(cur0, cur1);
+    const int last = min(nchunks, max(cur0 < nchunks ? 2 * cur0 + 64 : 0, cur1 < nchunks ? 2 * cur1 + 64 : 0));
+    for (int c = first + warp_global; c < last; c += nwarps) {
+      // lane l owns the 16 consecutive terms [16 l, 16 l + 16) of the chunk: a lane-local running sum with its extremes,
+      // then one scan over the 32 lane totals
+      constexpr int kPer = kCcChunk / 32;
+      const int t_end = min(total, (c + 1) * kCcChunk);
+      const int t_lane = c * kCcChunk + lane * kPer;
+      float2 vv[kPer];
+#pragma unroll
+      for (int j = 0; j < kPer; j++) vv[j] = (t_lane + j < t_end) ? dense[t_lane + j] : make_float2(0.0f, 0.0f);
+      long long run[2] = {0, 0}, mn[2] = {LLONG_MAX, LLONG_MAX}, mx[2] = {LLONG_MIN, LLONG_MIN};
+      int flag[2] = {2, 2};
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        if (c < (ch ? cur1 : cur0)) continue;                              // warp-uniform
+        bool nz = false, needseq = false;
+        long long pre = 0, lmn = LLONG_MAX, lmx = LLONG_MIN;
+        const bool okc = ch ? ok1 : ok0;
+        const int sh = 23 - (ch ? E1 : E0);
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+          const float x = ch ? vv[j].y : vv[j].x;
+          nz = nz || (x != 0.0f);
+          if (okc) {
+            const double q = scalbn((double)x, sh);                        // x / u, exact
+            needseq = needseq || (fabs(q - trunc(q)) == 0.5) || !(fabs(q) < 1073741824.0);   // tie; huge, inf or nan term
+            pre += (fabs(q) < 1073741824.0) ? (long long)rint(q) : 0;
+            if (t_lane + j < t_end) { lmn = min(lmn, pre); lmx = max(lmx, pre); }
+          }
+        }
+        if (__any_sync(0xffffffffu, nz)) flag[ch] &= ~2;
+        if (!okc || __any_sync(0xffffffffu, needseq)) flag[ch] |= 1;
+        long long incl = pre;                                              // inclusive scan of the lane totals
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const long long o = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += o;
+        }
+        const long long base = incl - pre;
+        long long lo = (lmn == LLONG_MAX) ? LLONG_MAX : base + lmn, hi = (lmx == LLONG_MIN) ? LLONG_MIN : base + lmx;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+          hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+        }
+        mn[ch] = lo; mx[ch] = hi;
+        run[ch] = __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane < 2) {
+        const int ch = lane;
+        if (c >= (ch ? cur1 : cur0)) {
+          const size_t i = (size_t)c * 2 + ch;
+          recR[i] = run[ch]; recMn[i] = mn[ch]; recMx[i] = mx[ch]; recFlag[i] = flag[ch];
+        }
+      }
+    }
+    __threadfence();
+    grid.sync();
+    // ---- B: CTA 0, warp ch walks chain ch over the prepared chunks; a chunk that cannot be taken by integer arithmetic
+    // is added the plain way, and the walk goes on as long as the records still fit the state
+    if (blockIdx.x == 0 && (threadIdx.x >> 5) < 2) {
+      const int ch = threadIdx.x >> 5;
+      int cur = ch ? cur1 : cur0;
+      if (cur < nchunks) {
+        float sacc = ch ? s1 : s0;
+        const bool have = ch ? ok1 : ok0;       // the records were made for exponent Ec
+        const int Ec = ch ? E1 : E0;
+        int nseq = 0;
+        while (cur < last) {
+          const int c = cur + lane;
+          int nvalid;
+          if (have) {
+            const long long S0 = (long long)scalbn((double)sacc, 23 - Ec);   // exact integer, 2^23 <= |S0| < 2^24
+            long long R = 0, mnv = 0, mxv = 0;
+            int fl = 1;
+            if (c < last) {
+              const size_t i = (size_t)c * 2 + ch;
+              R = __ldcg(recR + i); mnv = __ldcg(recMn + i); mxv = __ldcg(recMx + i); fl = __ldcg(recFlag + i);
+            }
+            long long incl = R;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+              const long long o = __shfl_up_sync(0xffffffffu, incl, off);
+              if (lane >= off) incl += o;
+            }
+            const long long Sstart = S0 + incl - R;
+            const long long lo = Sstart + mnv, hi = Sstart + mxv;
+            bool okc = !(fl & 1) && c < last;
+            if (S0 > 0) okc = okc && lo >= (1LL << 23) && hi <= (1LL << 24) - 1;
+            else        okc = okc && hi <= -(1LL << 23) && lo >= -((1LL << 24) - 1);
+            const unsigned m = __ballot_sync(0xffffffffu, !okc);
+            nvalid = m ? __ffs(m) - 1 : 32;
+            if (nvalid > 0) {
+              const long long Send = S0 + __shfl_sync(0xffffffffu, incl, nvalid - 1);
+              sacc = (float)scalbn((double)Send, Ec - 23);                   // exact: |Send| < 2^24, same binade
+            }
+          } else {                                                           // zero / subnormal state: only all-zero chunks are free
+            const bool z = c < last && (__ldcg(recFlag + (size_t)c * 2 + ch) & 2);
+            const unsigned m = __ballot_sync(0xffffffffu, !z);
+            nvalid = m ? __ffs(m) - 1 : 32;
+          }
+          cur += nvalid;
+          if (nvalid == 32) continue;
+          if (cur >= last) break;
+          {   // chunk `cur` the plain way
+            const int t_begin = cur * kCcChunk, t_end = min(total, t_begin + kCcChunk);
+            float xs[kCcChunk / 32];                                          // 16 independent loads, then the chain
+#pragma unroll
+            for (int b = 0; b < kCcChunk / 32; b++) {
+              const int t = t_begin + b * 32 + lane;
+              xs[b] = 0.0f;
+              if (t < t_end) { const float2 v = dense[t]; xs[b] = ch ? v.y : v.x; }
+            }
+            float acc = sacc;
+#pragma unroll
+            for (int b = 0; b < kCcChunk / 32; b++) {
+#pragma unroll
+              for (int q = 0; q < 32; q++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, xs[b], q));   // 0.0f past the end: identity
+            }
+            sacc = acc;
+            cur++; nseq++;
+          }
+          int En = 0;
+          const bool now = cc_binade(sacc, En);
+          if (have ? !(now && En == Ec) : now) break;                        // the next records must be made for another u
+        }
+        if (lane == 0) { vs->s[ch] = sacc; vs->cur[ch] = cur; vs->seq_chunks[ch] += nseq; }
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 64) vs->rounds = round + 1;
+    __threadfence();
+    grid.sync();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { out4[0] = (double)vs->s[0]; out4[1] = (double)vs->s[1]; }
 }
 
 // D (warp 0) and G (warp 1) re-accumulated in float32 in the reference's order.  The warp loads 32 terms at a time

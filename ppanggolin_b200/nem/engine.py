@@ -69,6 +69,7 @@ SIGNATURES = {
     "nemb200_peer_wait_densities": (ctypes.c_int, [_vp, _vp]),
     "nemb200_sweep": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp]),
     "nemb200_plan_graph_changed": (ctypes.c_int, [_vp]),
+    "nemb200_selftest_float_chain": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "nemb200_read_flags": (ctypes.c_int, [_vp, ctypes.POINTER(_f32), ctypes.POINTER(_i32), _vp]),
     "nemb200_criteria": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f32, ctypes.POINTER(ctypes.c_double * 5), _vp]),
     "nemb200_get_params": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.POINTER(_i32), _vp]),
@@ -331,6 +332,18 @@ def nem_run_batch(instances, cv_th: float = 0.01, flags: int = EPI_REF):
         runs.append(NemRun(T, mu.cpu().numpy(), eps.cpu().numpy(), pk.cpu().numpy(), list(r.crit), r.n_iter, bool(r.converged),
                            r.status, r.n_levels, r.elapsed_ms))
     return runs
+
+
+def float_chain(d: np.ndarray, g: np.ndarray, parallel: bool):
+    """Diagnostics: float32 sums of d and g accumulated from 0 in index order on the device, through the sequential chain
+    kernel or the exact parallel scheme (``nemb200_selftest_float_chain``)."""
+    _require_cuda()
+    d = np.ascontiguousarray(d, np.float32); g = np.ascontiguousarray(g, np.float32)
+    assert d.shape == g.shape and d.ndim == 1
+    out = (ctypes.c_double * 2)()
+    _check(lib().nemb200_selftest_float_chain(d.ctypes.data, g.ctypes.data, d.shape[0], int(parallel), ctypes.cast(out, _vp)),
+           "selftest_float_chain")
+    return np.float32(out[0]), np.float32(out[1])
 
 
 def labels_device(T):

@@ -665,3 +665,39 @@ def test_file_based_entry_point_wide_matrix(eng, tmp_path):
         assert out is not None and out["n_iter"] == run.n_iter
         assert np.abs(out["T3"] - T3).max() <= 1e-3 + 1e-9
         assert abs(out["crit"][3] - run.crit[3]) <= 1e-5 * abs(run.crit[3])
+
+
+@pytest.mark.gpu
+def test_parallel_float_chain_is_bit_exact(eng):
+    """The parallel re-accumulation of the float32 criteria sums against the sequential chain kernel and numpy's own
+    sequential float32 sum, on inputs chosen to hit every branch: growing sums (binade crossings), exact rounding ties,
+    sign changes and cancellation, absorbed tiny terms, zeros, huge terms, subnormal partial sums."""
+    rng = np.random.default_rng(11)
+
+    def seq(x):   # float32 running sum in index order
+        acc = np.float32(0)
+        for v in x.astype(np.float32):
+            acc = np.float32(acc + v)
+        return acc
+
+    n = 70_000
+    cases = {
+        "negative log-likelihood terms": -np.abs(rng.normal(120, 60, n)),
+        "small positive weights (absorbed late)": rng.random(n) * 1e-3,
+        "mixed signs": rng.normal(0, 1, n),
+        "ties": np.where(rng.random(n) < 0.3, 0.5, 1.0) * 2.0 ** rng.integers(-30, 3, n),
+        "cancellation to zero": np.concatenate([np.full(5000, 1.5), np.full(5000, -1.5), rng.normal(0, 1e-3, n - 10000)]),
+        "huge then tiny": np.concatenate([[3e37], rng.random(n - 1)]),
+        "subnormal sums": rng.random(n) * 1e-44,
+        "zeros": np.zeros(n),
+        "one term": np.array([0.1]),
+        "exact powers of two": 2.0 ** rng.integers(0, 8, n),
+    }
+    for name, x in cases.items():
+        x = x.astype(np.float32)
+        y = np.roll(x, 7) if len(x) > 7 else x
+        a = eng.float_chain(x, y, parallel=False)
+        b = eng.float_chain(x, y, parallel=True)
+        assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes(), name
+        if len(x) <= 70_000:
+            assert seq(x).tobytes() == b[0].tobytes(), name
