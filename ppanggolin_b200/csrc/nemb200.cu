@@ -814,10 +814,10 @@ static int criteria_enqueue(nemb200_plan* pl, int64_t N, const double* logf, con
   else k_criteria<32><<<pl->crit_blocks, 256, 0, st>>>(a);
   CK(cudaGetLastError());
   if (a.logspace) {
-    k_crit_reduce<<<1, 32, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4, 0);
+    k_crit_reduce<<<1, 128, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4, 0);
     CK(cudaGetLastError());
   } else {
-    k_crit_reduce<<<1, 32, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4, 2);       // L, Z: fp64 sums
+    k_crit_reduce<<<1, 128, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4, 2);       // L, Z: fp64 sums
     CK(cudaGetLastError());
     k_crit_offsets<<<1, 32, 0, st>>>(pl->crit_counts, n_warps, pl->crit_offsets);
     CK(cudaGetLastError());
@@ -959,14 +959,17 @@ extern "C" int nemb200_labels(const float* T, int64_t N, int32_t K, int32_t* lab
   if (!T || !labels_dev || N < 1 || K < 1) return fail(NEMB200_ERR_ARG, "labels: bad argument");
   cudaStream_t st = (cudaStream_t)stream_;
   const int blocks = (int)((N + 255) / 256);
-  double* part = nullptr;
-  CK(cudaMalloc(&part, (size_t)(blocks + 1) * sizeof(double)));
+  void* mem = nullptr;
+  const size_t bytes = (size_t)(blocks + 1) * sizeof(double);
+  int rc = cached_malloc(&mem, bytes);   // cudaMalloc / cudaFree would cost more than the two kernels
+  if (rc) return rc;
+  double* part = (double*)mem;
   k_labels<<<blocks, 256, 0, st>>>(T, N, K, labels_dev, part);
   k_sum_partials<<<1, 32, 0, st>>>(part, blocks, part + blocks);
   double e = 0.0;
   cudaError_t err = cudaMemcpyAsync(&e, part + blocks, sizeof(double), cudaMemcpyDeviceToHost, st);
   if (err == cudaSuccess) err = cudaStreamSynchronize(st);
-  cudaFree(part);
+  cached_free(mem, bytes);
   if (err != cudaSuccess) return fail(NEMB200_ERR_CUDA, "labels: %s", cudaGetErrorString(err));
   if (entropy_host) *entropy_host = e;
   return NEMB200_OK;

@@ -1890,13 +1890,26 @@ k_crit_chain(const float2* __restrict__ dense, const int* __restrict__ offsets, 
   if (lane == 0) out4[which] = (double)acc;
 }
 
-__global__ void k_crit_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ out4, int first) {
-  // out4[first..3] = fp64 sums of the block partials (first = 0: all four; first = 2: only L and Z)
-  if (threadIdx.x < 4 && (int)threadIdx.x >= first && blockIdx.x == 0) {
-    double t = 0.0;
-    for (int b = 0; b < nblocks; b++) t += partial[(size_t)b * 4 + threadIdx.x];
-    out4[threadIdx.x] = t;
+// fp64 sum of n values (stride apart) in index order: a warp loads 32 at a time, lane 0's adds take them by shuffle --
+// the order of a sequential loop without its load latency per element
+__device__ __forceinline__ double ordered_sum(const double* __restrict__ p, int n, int stride) {
+  const int lane = threadIdx.x & 31;
+  double t = 0.0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const double v = i < n ? p[(size_t)i * stride] : 0.0;
+    const int m = min(32, n - i0);
+    for (int j = 0; j < m; j++) t += __shfl_sync(0xffffffffu, v, j);
   }
+  return t;
+}
+
+// launched with 4 warps: out4[w] = fp64 sum of the block partials of criterion w (first = 0: all four; first = 2: only L and Z)
+__global__ void k_crit_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ out4, int first) {
+  const int w = threadIdx.x >> 5;
+  if (blockIdx.x != 0 || w >= 4 || w < first) return;
+  const double t = ordered_sum(partial + w, nblocks, 4);
+  if ((threadIdx.x & 31) == 0) out4[w] = t;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1930,11 +1943,9 @@ k_labels(const float* __restrict__ T, long long N, int K, int* __restrict__ labe
 }
 
 __global__ void k_sum_partials(const double* __restrict__ p, int n, double* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < n; i++) t += p[i];
-    *out = t;
-  }
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const double t = ordered_sum(p, n, 1);
+  if (threadIdx.x == 0) *out = t;
 }
 
 }  // namespace nemb200
