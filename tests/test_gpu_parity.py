@@ -507,7 +507,7 @@ def test_edge_shapes(eng, N, D, K, beta, fd):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,D,K", [(300, 50, 2), (1000, 500, 3), (777, 1000, 4), (513, 5000, 3), (400, 129, 5), (350, 4100, 8),
-                                   (260, 700, 12), (300, 300, 20), (257, 640, 32)])
+                                   (260, 700, 12), (300, 300, 20), (257, 640, 32), (300, 110000, 3), (200, 110000, 8)])
 def test_density_ring_equals_small_cta_kernel(eng, N, D, K, monkeypatch):
     """The two density kernels (cp.async shared-memory ring / 128-thread register prefetch) produce integers and must
     agree bit for bit; centres include 0.5 ties (the `valid` plane) in a third of the columns."""
@@ -555,7 +555,7 @@ def test_density_ring_equals_small_cta_kernel(eng, N, D, K, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,D,K", [(3000, 30000, 3), (5000, 5000, 4), (2000, 64, 2), (700000, 64, 3), (1500, 52000, 5)])
+@pytest.mark.parametrize("N,D,K", [(3000, 30000, 3), (5000, 5000, 4), (2000, 64, 2), (700000, 64, 3), (1500, 52000, 5), (600, 110000, 3)])
 def test_onehot_counts_ring_equals_small_cta_kernel(eng, N, D, K, monkeypatch):
     """Column counts of the one-hot rows: the shared-memory-ring kernel against the 128-thread kernel and against numpy,
     first pass (full count) and an incremental update after 10 % of the rows changed class."""
