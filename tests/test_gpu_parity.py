@@ -701,3 +701,25 @@ def test_parallel_float_chain_is_bit_exact(eng):
         assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes(), name
         if len(x) <= 70_000:
             assert seq(x).tobytes() == b[0].tobytes(), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,fd", [(3, False), (6, True)])
+def test_high_degree_rows_match_strict_oracle(eng, K, fd):
+    """Neighbour lists longer than the 8 entries the schedule-ordered graph copy keeps inline (sm_degree = 60: up to ~40
+    neighbours per family): the sweep continues such lists from the CSR arrays, in list order."""
+    N, D = 1500, 120
+    sp = synth_pangenome(N, D, seed=31, sm_degree=60)
+    deg = np.diff(sp.rowptr)
+    assert deg.max() > 8 and (deg > 8).mean() > 0.05
+    beta = sp.beta_eff(2.5)
+    inp = eng.DeviceInput.from_numpy(sp.bits, D, sp.rowptr, sp.col, sp.w)
+    run = eng.nem_run_device(inp, K, beta, fd, 30)
+    o = refnem.oracle_nem_run(sp.X, sp.rowptr, sp.col, sp.w, K, beta, fd, 30, mode=refnem.STRICT)
+    assert run.status == o["status"]
+    if run.status == 0:
+        assert abs(run.n_iter - o["n_iter"]) <= 1
+        lab, _ = eng.labels_device(run.T)
+        olab, _, _ = refnem.oracle_labels(o["T"])
+        assert (lab.cpu().numpy() == olab).mean() >= 0.999
+        assert abs(run.crit[3] - o["crit"][3]) <= 1e-5 * abs(o["crit"][3])
