@@ -241,7 +241,7 @@ def evaluate_nb_partitions(
     tmpdir = Path(tempfile.gettempdir()) if tmpdir is None else tmpdir
     newtmpdir = tmpdir / "eval_partitions"
     if len(organisms) > chunk_size:
-        select_organisms = set(random.sample(list(organisms), chunk_size))
+        select_organisms = _same_on_all_ranks(set(random.sample(list(organisms), chunk_size)), organisms)
     else:
         select_organisms = set(organisms)
 
@@ -267,13 +267,7 @@ def run_k_candidates(nem_dir_path: Path, nb_org: int, ks: List[int], free_disper
         raise FileNotFoundError(f"no exported NEM instance registered for {nem_dir_path}")
     if inp.device is None:
         inp.device = _device_input(inp)
-    rank, world = 0, 1
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            rank, world = dist.get_rank(), dist.get_world_size()
-    except ImportError:
-        dist = None
+    rank, world, dist = _rank_world()
     mine = ks[rank::world]
     runs = engine.nem_run_batch([(inp.device, k, 0.0, free_dispersion, 10) for k in mine], flags=_epilogue_flags(nb_org))
     results = []
@@ -497,10 +491,123 @@ def _draw_samples(organisms, chunk_size, org_nb_sample, condition):
 CHUNK_BATCH = 16   # chunk instances per batched GPU call
 
 
+def _same_on_all_ranks(chosen: set, organisms) -> set:
+    """Random genome samples must be the same on every rank of a process group, but they are drawn from sets of objects whose
+    iteration order depends on object addresses (SURVEY.md Appendix A #11): rank 0's draw is broadcast by genome name."""
+    rank, world, dist = _rank_world()
+    if world == 1:
+        return chosen
+    payload = [sorted(o.name for o in chosen) if rank == 0 else None]
+    dist.broadcast_object_list(payload, src=0)
+    if rank == 0:
+        return chosen
+    by_name = {o.name: o for o in organisms}
+    return {by_name[n] for n in payload[0]}
+
+
+def _draw_samples_synced(organisms, chunk_size, org_nb_sample, condition):
+    """``_draw_samples`` on rank 0; the other ranks take over its new samples (by genome name) and counters."""
+    rank, world, dist = _rank_world()
+    if world == 1:
+        _draw_samples(organisms, chunk_size, org_nb_sample, condition)
+        return
+    prev = len(samples)
+    if rank == 0:
+        _draw_samples(organisms, chunk_size, org_nb_sample, condition)
+    payload = [[sorted(o.name for o in smp) for smp in samples[prev:]] if rank == 0 else None]
+    dist.broadcast_object_list(payload, src=0)
+    if rank != 0:
+        by_name = {o.name: o for o in organisms}
+        for names in payload[0]:
+            smp = {by_name[n] for n in names}
+            samples.append(smp)
+            for org in smp:
+                org_nb_sample[org] += 1
+
+
+def _rank_world():
+    """(rank, world, torch.distributed or None): chunk samples and K candidates are independent NEM instances and are dealt
+    out to the ranks of an initialised process group (SURVEY.md section 8e, "independent instances")."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), dist
+    except ImportError:
+        pass
+    return 0, 1, None
+
+
+def _run_chunk_batch(arrays, sample_ids, kval, beta, sm_degree, free_dispersion, chunk_size):
+    """One batched GPU call for the chunk samples ``sample_ids``; returns per sample a code vector over ALL families of the
+    pangenome (int8: 0 = P, 1 = S, 2 = C, -1 = family absent from the chunk or run failed)."""
+    import torch
+    logger = logging.getLogger("PPanGGOLiN")
+    F = len(arrays.fam_names)
+    out = torch.full((len(sample_ids), F), -1, dtype=torch.int8, device=arrays.device)
+    if not sample_ids:
+        return out
+    insts = [arrays.instance(samples[i], sm_degree) for i in sample_ids]
+    jobs = [(_device_input(inp), kval, beta * (inp.N / inp.edges_weight), free_dispersion, 100) for inp in insts]
+    runs = engine.nem_run_batch(jobs, flags=_epilogue_flags(chunk_size))
+    for j, (inp, run) in enumerate(zip(insts, runs)):
+        if not run.ok:
+            logger.warning("A NEM run failed for this dataset/chunk and was skipped. In chunked mode, other chunks "
+                           "can still complete and final partitioning may still succeed.")
+            continue
+        lab, _ = engine.labels_device(run.T)
+        lab = lab.to(torch.long)
+        code = torch.where(lab == 0, 0, torch.where(lab == kval - 1, 2, 1))    # first letter: P / S (S1.., S_) / C
+        out[j, inp.fam_rows] = code.to(torch.int8)
+    return out
+
+
+def _apply_chunk_votes(votes, validated, codevec, n_org: int, chunk_size: int):
+    """``validate_family`` (partition.py:784-802) for one finished chunk, element-wise: ``codevec`` holds the chunk's label
+    per family (-1 = not in the chunk).  A family occurs at most once per chunk, so this is the reference's per-node rule."""
+    import torch
+    rows = (codevec >= 0).nonzero().squeeze(1)
+    if rows.numel() == 0:
+        return
+    code = codevec[rows].to(torch.long)
+    votes.index_put_((rows, code), torch.ones_like(code), accumulate=True)
+    v = votes[rows]
+    s = v.sum(1)
+    mx = v.max(1).values
+    cond = ((s > n_org / chunk_size) & (mx.to(torch.float64) >= s.to(torch.float64) * 0.5)) | (s > n_org)
+    newly = cond & ~validated[rows]
+    undecided = newly & (mx.to(torch.float64) < s.to(torch.float64) * 0.5)
+    if bool(undecided.any()):
+        votes[rows[undecided], 3] = n_org
+    validated[rows[newly]] = True
+
+
+def _chunk_round(sample_ids, F: int, device, run_batch, votes, validated, n_org: int, chunk_size: int):
+    """The chunk samples of one draw: dealt out round-robin to the ranks in groups of CHUNK_BATCH per rank, run, and the
+    per-chunk label vectors all-gathered, so that every rank applies every chunk's votes in sample order -- the same
+    votes, in the same order, as a single process."""
+    import torch
+    rank, world, dist = _rank_world()
+    for g0 in range(0, len(sample_ids), CHUNK_BATCH * world):
+        group = sample_ids[g0:g0 + CHUNK_BATCH * world]
+        mine = group[rank::world]
+        local = run_batch(mine)
+        if world > 1:
+            per_rank = (len(group) + world - 1) // world            # pad: ranks may hold one sample less
+            buf = torch.full((per_rank, F), -1, dtype=torch.int8, device=device)
+            buf[:local.shape[0]] = local
+            gathered = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(gathered, buf)
+            for pos in range(len(group)):                            # sample `pos` of the group ran on rank pos % world
+                _apply_chunk_votes(votes, validated, gathered[pos % world][pos // world], n_org, chunk_size)
+        else:
+            for j in range(local.shape[0]):
+                _apply_chunk_votes(votes, validated, local[j], n_org, chunk_size)
+
+
 def _partition_chunked_arrays(arrays, organisms, chunk_size, kval, beta, sm_degree, free_dispersion, pansize):
     """The chunked mode of partition.py:781-864 on tensors: every chunk instance is derived from the cached arrays,
-    instances run in batches on the GPU, and ``validate_family`` (partition.py:784-802) is applied to the whole result of
-    a chunk at once (a family occurs at most once per chunk, so the element-wise form is the same rule)."""
+    instances run in batches on the GPU (spread over the ranks of a process group, if one is initialised), and
+    ``validate_family`` (partition.py:784-802) is applied to the whole result of a chunk at once."""
     import torch
     logger = logging.getLogger("PPanGGOLiN")
     dev = arrays.device
@@ -512,34 +619,15 @@ def _partition_chunked_arrays(arrays, organisms, chunk_size, kval, beta, sm_degr
     for org in organisms:
         org_nb_sample[org] = 0
     condition = n_org / chunk_size
+
+    def run_batch(ids):
+        return _run_chunk_batch(arrays, ids, kval, beta, sm_degree, free_dispersion, chunk_size)
+
     while int(validated.sum().item()) < pansize:
         prev = len(samples)
-        _draw_samples(organisms, chunk_size, org_nb_sample, condition)
+        _draw_samples_synced(organisms, chunk_size, org_nb_sample, condition)
         logger.info("Launching NEM")
-        new = list(range(prev, len(samples)))
-        for b0 in range(0, len(new), CHUNK_BATCH):
-            insts = [arrays.instance(samples[i], sm_degree) for i in new[b0:b0 + CHUNK_BATCH]]
-            jobs = [(_device_input(inp), kval, beta * (inp.N / inp.edges_weight), free_dispersion, 100) for inp in insts]
-            runs = engine.nem_run_batch(jobs, flags=_epilogue_flags(chunk_size))
-            for inp, run in zip(insts, runs):
-                if not run.ok:
-                    logger.warning("A NEM run failed for this dataset/chunk and was skipped. In chunked mode, other chunks "
-                                   "can still complete and final partitioning may still succeed.")
-                    continue
-                lab, _ = engine.labels_device(run.T)
-                lab = lab.to(torch.long)
-                code = torch.where(lab == 0, 0, torch.where(lab == kval - 1, 2, 1))    # first letter: P / S (S1.., S_) / C
-                rows = inp.fam_rows
-                votes.index_put_((rows, code), torch.ones_like(code), accumulate=True)
-                v = votes[rows]
-                s = v.sum(1)
-                mx = v.max(1).values
-                cond = ((s > n_org / chunk_size) & (mx.to(torch.float64) >= s.to(torch.float64) * 0.5)) | (s > n_org)
-                newly = cond & ~validated[rows]
-                undecided = newly & (mx.to(torch.float64) < s.to(torch.float64) * 0.5)
-                if bool(undecided.any()):
-                    votes[rows[undecided], 3] = n_org
-                validated[rows[newly]] = True
+        _chunk_round(list(range(prev, len(samples))), F, dev, run_batch, votes, validated, n_org, chunk_size)
         condition += 1
         logger.debug(f"There are {int(validated.sum().item())} validated families out of {pansize} families.")
     best = votes.argmax(1).cpu().numpy()                                  # ties -> first of P, S, C, U like max(dict)

@@ -65,3 +65,55 @@ def test_two_rank_gloo_run_equals_single_process(tmp_path, N):
         assert np.array_equal(np.load(tmp_path / f"mu_2_{r}.npy"), np.load(tmp_path / "mu_1_0.npy"))
         assert np.allclose(np.load(tmp_path / f"flags_2_{r}.npy"), np.load(tmp_path / "flags_1_0.npy"))
     assert (T1.argmax(1) == 0).sum() > 0 and (T1.argmax(1) == K - 1).sum() > 0
+
+
+def _chunk_votes(rank, world, port, F, n_samples, out):
+    """Chunk samples dealt out to the ranks (partition._chunk_round) with a deterministic stand-in for the GPU runs."""
+    for p in (str(ROOT), str(ROOT / "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from ppanggolin_b200.nem import partition as ppp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_org, chunk_size = 40, 10
+
+    def fake_batch(ids):   # label vector of chunk i: depends only on i, some families absent, some chunks failed (-1 everywhere)
+        res = torch.full((len(ids), F), -1, dtype=torch.int8)
+        for j, i in enumerate(ids):
+            g = torch.Generator().manual_seed(1000 + i)
+            present = torch.rand(F, generator=g) < 0.7
+            code = torch.randint(0, 3, (F,), generator=g).to(torch.int8)
+            if i % 11 != 5:
+                res[j] = torch.where(present, code, torch.tensor(-1, dtype=torch.int8))
+        return res
+
+    votes = torch.zeros((F, 4), dtype=torch.long)
+    validated = torch.zeros(F, dtype=torch.bool)
+    old = ppp.CHUNK_BATCH
+    ppp.CHUNK_BATCH = 3          # several groups, the last one ragged
+    try:
+        ppp._chunk_round(list(range(n_samples)), F, torch.device("cpu"), fake_batch, votes, validated, n_org, chunk_size)
+    finally:
+        ppp.CHUNK_BATCH = old
+    np.save(f"{out}/votes_{world}_{rank}.npy", votes.numpy())
+    np.save(f"{out}/validated_{world}_{rank}.npy", validated.numpy())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_samples", [17, 24])
+def test_chunk_samples_dealt_to_two_ranks_give_the_same_votes(tmp_path, n_samples):
+    """Independent chunk instances on two ranks (gloo): every rank ends with the votes and the validation state of the
+    single-process run, applied in the same sample order (the "undefined" rule of validate_family depends on it)."""
+    F = 300
+    _chunk_votes(0, 1, _free_port(), F, n_samples, str(tmp_path))
+    port = _free_port()
+    mp.spawn(_chunk_votes, args=(2, port, F, n_samples, str(tmp_path)), nprocs=2, join=True)
+    v1 = np.load(tmp_path / "votes_1_0.npy"); ok1 = np.load(tmp_path / "validated_1_0.npy")
+    assert v1.sum() > 0 and ok1.any()
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"votes_2_{r}.npy"), v1)
+        assert np.array_equal(np.load(tmp_path / f"validated_2_{r}.npy"), ok1)
