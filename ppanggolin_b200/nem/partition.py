@@ -525,9 +525,29 @@ def _draw_samples_synced(organisms, chunk_size, org_nb_sample, condition):
                 org_nb_sample[org] += 1
 
 
+_local_only = 0
+
+
+class local_instances:
+    """Context in which this module does not deal work out to the process group: used by callers that already run
+    different jobs on different ranks (rarefaction samples), where a collective inside would not be matched."""
+
+    def __enter__(self):
+        global _local_only
+        _local_only += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _local_only
+        _local_only -= 1
+        return False
+
+
 def _rank_world():
     """(rank, world, torch.distributed or None): chunk samples and K candidates are independent NEM instances and are dealt
     out to the ranks of an initialised process group ("independent instances")."""
+    if _local_only:
+        return 0, 1, None
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():

@@ -180,10 +180,18 @@ def make_rarefaction_curve(pangenome, output: Path, tmpdir: Path = None, beta: f
             logger.info(f"The number of partitions has been evaluated at {kval}")
 
     logger.info("Extracting samples ...")
+    rank, world, dist = ppp._rank_world()
     all_samples = []
-    for i in range(min_sampling, max_sampling):
-        for _ in range(depth):
-            all_samples.append(set(random.sample(organisms, i + 1)))
+    if rank == 0:
+        for i in range(min_sampling, max_sampling):
+            for _ in range(depth):
+                all_samples.append(set(random.sample(organisms, i + 1)))
+    if world > 1:   # the same samples on every rank: rank 0's draw, by genome name (object order differs between processes)
+        payload = [[sorted(o.name for o in smp) for smp in all_samples] if rank == 0 else None]
+        dist.broadcast_object_list(payload, src=0)
+        if rank != 0:
+            by_name = {o.name: o for o in organisms}
+            all_samples = [{by_name[n] for n in names} for names in payload[0]]
     logger.info(f"Done sampling genomes in the pan, there are {len(all_samples)} samples")
 
     if arrays is None:
@@ -196,11 +204,21 @@ def make_rarefaction_curve(pangenome, output: Path, tmpdir: Path = None, beta: f
     global samples
     samples = all_samples
     logger.info(" Partitioning all samples...")
-    for index in range(len(samples)):
-        counts, idx = launch_raref_nem((index, tmp_path, beta, sm_degree, free_dispersion, chunk_size, kval, krange, seed))
+    # the samples are independent jobs: every rank takes its share (round-robin) and runs it without collectives inside,
+    # the per-sample counts are gathered at the end (the reference spreads them over a fork pool, rarefaction.py:707)
+    mine = {}
+    with ppp.local_instances():
+        for index in range(rank, len(samples), world):
+            counts, idx = launch_raref_nem((index, tmp_path, beta, sm_degree, free_dispersion, chunk_size, kval, krange, seed))
+            mine[idx] = counts
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        mine = {k: v for part in gathered for k, v in part.items()}
+    for idx, counts in mine.items():
         samp_nb_per_part[idx] = {**counts, **samp_nb_per_part[idx]}
     logger.info("Done  partitioning everything")
-    if output is not None:
+    if output is not None and rank == 0:
         Path(output).mkdir(parents=True, exist_ok=True)
         write_rarefaction_csv(Path(output), samp_nb_per_part)
     tmpdir_obj.cleanup()

@@ -52,6 +52,15 @@ for name, kw in [("chunked", dict(kval=3, chunk_size=60)), ("autoK", dict(kval=-
     digest = hashlib.sha256(labels.encode()).hexdigest()[:16]
     print(f"world {world} rank {rank} {name}: instances {len(part.samples)} K {pan.parameters['partition']['# final nb of partitions']} "
           f"counts {dict(Counter(f.partition[:1] for f in pan.gene_families))} digest {digest}", flush=True)
+from ppanggolin_b200.nem import rarefaction as raref
+for f in pan.gene_families:
+    f.partition = ""
+random.seed(99)
+with tempfile.TemporaryDirectory() as td:
+    recs = raref.make_rarefaction_curve(pan, output=None, tmpdir=Path(td), depth=2, min_sampling=20, max_sampling=40, chunk_size=30,
+                                        kval=3, disable_bar=True)
+text = ";".join(",".join(f"{k}={r[k]}" for k in sorted(r)) for r in recs)
+print(f"world {world} rank {rank} rarefaction: {len(recs)} samples digest {hashlib.sha256(text.encode()).hexdigest()[:16]}", flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
