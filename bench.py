@@ -484,7 +484,7 @@ def run_ours(a):
                            "call": "ShardedEM.run (pinned host shards -> H2D -> row-sharded EM to convergence, NCCL exchange -> posteriors D2H)"}
     elif rank == 0:
         line["e2e"] = None
-    if rank == 0 and not a.no_cpu:
+    if rank == 0 and world == 1 and not a.no_cpu:   # the CPU baseline is reported at N = 1 only
         cores = min(os.cpu_count() or 1, 32)
         try:
             cb = cpu_reference_run(N, D, a.cpu_sample_rows, a.seed, K, BETA, cores)
