@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(COOP ? 1024 : 256) k_sweep(SweepArgs a) {
 // change since the previous M-step contributes nothing new, so only rows that entered a class ("add" bucket k) or
 // left one ("remove" bucket K + k) are streamed again.  Integer arithmetic makes this bit-identical to a full recount;
 // the first M-step of a run (prev = kNone everywhere) is the full pass.  Fuzzy rows (bucket 2K) are always recomputed.
-// Buckets are materialised as index lists: k_classify (bucket histogram) -> k_offsets -> k_scatter.
+// Buckets are materialised as index lists: k_classify (bucket histogram) -> k_scatter (prefix sums + scatter).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kNone = -2;  // prev key of a row that is not counted anywhere yet
 
