@@ -50,14 +50,15 @@ class PangenomeArrays:
         fams = list(pan.gene_families)
         fam_index = {f: i for i, f in enumerate(fams)}
         F, G = len(fams), len(orgs)
-        rows, cols = [], []
-        for i, fam in enumerate(fams):
-            c = [org_index[o] for o in fam.organisms]
-            cols.extend(c)
-            rows.extend([i] * len(c))
+        cols, counts = [], []
+        for fam in fams:
+            n0 = len(cols)
+            cols.extend([org_index[o] for o in fam.organisms])
+            counts.append(len(cols) - n0)
         presence = torch.zeros((F, G), dtype=torch.bool)
-        if rows:
-            presence[torch.tensor(rows, dtype=torch.long), torch.tensor(cols, dtype=torch.long)] = True
+        if cols:   # numpy builds the index arrays (torch.tensor on a long Python list is several times slower)
+            rows = np.repeat(np.arange(F, dtype=np.int64), np.asarray(counts, dtype=np.int64))
+            presence[torch.from_numpy(rows), torch.from_numpy(np.asarray(cols, dtype=np.int64))] = True
         edge_index = {}
         adj_ptr = [0]
         adj_fam, adj_edge, adj_other = [], [], []
@@ -73,7 +74,7 @@ class PangenomeArrays:
                 other = edge.target if fam == edge.source else edge.source
                 adj_fam.append(i); adj_edge.append(eid); adj_other.append(fam_index[other])
             adj_ptr.append(len(adj_fam))
-        t = lambda a: torch.tensor(a, dtype=torch.long, device=device)
+        t = lambda a: torch.from_numpy(np.asarray(a, dtype=np.int64)).to(device)
         return PangenomeArrays([f.name for f in fams], [o.name for o in orgs], org_index, presence.to(device), t(adj_ptr),
                                t(adj_fam), t(adj_edge), t(adj_other), t(cov_edge), t(cov_org), t(cov_cnt), len(edge_index),
                                device)
