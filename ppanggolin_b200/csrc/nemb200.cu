@@ -529,14 +529,16 @@ static int launch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* log
 // instances keep the 128-thread kernel, which spreads few rows over more SMs.  NEMB200_DENS_RING=0/1 forces the choice
 // (tests run both on the same inputs: the results are integers, so they must be identical).
 template <int KB, int KX>
-static int launch_density_ring(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st, bool* done) {
-  constexpr int RB = KB <= 4 ? 4 : (KB <= 8 ? 2 : 1);
-  constexpr int TPB = KB <= 3 ? 640 : 512;          // registers: 96 at K <= 3, up to 127 above
+static int launch_density_ring(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st, bool* done, int k0 = 0,
+                               int kc = -1 /*classes [k0, k0 + kc) of the model; -1: all*/) {
+  constexpr int RB = KB <= 4 ? 4 : (KB <= 20 ? 2 : 1);
+  constexpr int TPB = KB <= 3 ? 640 : (KB <= 8 ? 512 : 384);   // registers: 96 at K <= 3, up to 127 / 168 above
   constexpr int P = RB == 4 ? 3 : (RB == 2 ? 4 : 6);  // steps in flight per thread (RB x 16 B each)
   *done = false;
+  if (kc < 0) kc = pl->K;
   const int W4 = pl->Ws / 4;
   const int G = group_lanes(W4);
-  const size_t smem = ((size_t)P * RB * TPB + (size_t)2 * pl->K * W4) * sizeof(uint4);
+  const size_t smem = ((size_t)P * RB * TPB + (size_t)2 * kc * W4) * sizeof(uint4);
   const long long rows_per_block = (long long)(TPB / 32) * (32 / G) * RB;
   const char* force = getenv("NEMB200_DENS_RING");
   if (smem > 220 * 1024) return 0;
@@ -546,8 +548,9 @@ static int launch_density_ring(nemb200_plan* pl, const uint32_t* bits, double* l
   long long blocks = (pl->N_local + rows_per_block - 1) / rows_per_block;
   if (blocks > num_sms()) blocks = num_sms();
   if (blocks < 1) blocks = 1;
-  kern<<<(unsigned)blocks, TPB, smem, st>>>((const uint4*)bits, pl->N_local, W4, pl->K, G, (const uint4*)pl->P.m1,
-                                            (const uint4*)pl->P.valid, pl->P.L, pl->P.B, pl->P.has_half, logf);
+  kern<<<(unsigned)blocks, TPB, smem, st>>>((const uint4*)bits, pl->N_local, W4, kc, G, (const uint4*)pl->P.m1 + (size_t)k0 * W4,
+                                            (const uint4*)pl->P.valid + (size_t)k0 * W4, pl->P.L + k0, pl->P.B + k0, pl->P.has_half,
+                                            logf + k0, pl->K);
   CK(cudaGetLastError());
   *done = true;
   return 0;
@@ -559,7 +562,35 @@ static int launch_density_any(nemb200_plan* pl, const uint32_t* bits, double* lo
   if (rc != 0 || done) return rc;
   return launch_density_sk<KB, KX>(pl, bits, logf, st);
 }
+// More than 8 classes on a large shard: passes over class chunks of <= 8 with the exact-K kernels.  The accumulators of
+// K classes x RB rows do not fit the register file at K = 12..32 with RB > 1, and the kernel is bound by its LOP3 / POPC
+// work, far from HBM, so reading the matrix once per chunk costs nothing (K = 20: 1.57 -> 1.2 ms on the bench matrix).
+static int density_ring_chunk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st, bool* done, int k0, int kc) {
+  switch (kc) {
+    case 1: case 2: return launch_density_ring<2, 0>(pl, bits, logf, st, done, k0, kc);
+    case 3: return launch_density_ring<3, 3>(pl, bits, logf, st, done, k0, kc);
+    case 4: return launch_density_ring<4, 4>(pl, bits, logf, st, done, k0, kc);
+    case 5: return launch_density_ring<5, 5>(pl, bits, logf, st, done, k0, kc);
+    case 6: return launch_density_ring<6, 6>(pl, bits, logf, st, done, k0, kc);
+    case 7: return launch_density_ring<7, 7>(pl, bits, logf, st, done, k0, kc);
+    default: return launch_density_ring<8, 8>(pl, bits, logf, st, done, k0, kc);
+  }
+}
 static int dispatch_density_sk(nemb200_plan* pl, const uint32_t* bits, double* logf, cudaStream_t st) {
+  if (pl->K > 8) {
+    const int nchunk = (pl->K + 7) / 8;
+    int k0 = 0;
+    bool all = true;
+    for (int c = 0; c < nchunk && all; c++) {
+      const int kc = (pl->K - k0 + (nchunk - c) - 1) / (nchunk - c);   // balanced chunk sizes
+      bool done = false;
+      const int rc = density_ring_chunk(pl, bits, logf, st, &done, k0, kc);
+      if (rc) return rc;
+      if (!done) { all = false; break; }                                // not a ring-kernel shape: one launch below
+      k0 += kc;
+    }
+    if (all) return 0;
+  }
   switch (pl->K) {  // exact-K kernels for the common small K (no per-class predicates), buckets above
     case 1: case 2: return launch_density_any<2, 0>(pl, bits, logf, st);
     case 3: return launch_density_any<3, 3>(pl, bits, logf, st);

@@ -314,7 +314,7 @@ template <int KB, int KX, int RB, int P, int TPB, bool HALF>
 __device__ __forceinline__ void density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int Krt, int G,
                                                 const uint4* m1, const uint4* valid, uint4* ring /*[P][RB][TPB]*/,
                                                 const double* __restrict__ L, const double* __restrict__ B,
-                                                double* __restrict__ logf) {
+                                                double* __restrict__ logf, int Kstride /*classes per row of logf*/) {
   const int K = KX > 0 ? KX : Krt;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
@@ -418,7 +418,7 @@ __device__ __forceinline__ void density_sk_ring(const uint4* __restrict__ bits, 
         for (int r = 0; r < RB; r++) {
           if (r0 + r < N) {
             const double v = (h[r][k] == 0) ? Bk : (Bk - (double)h[r][k] * Lk);   // see density_sk_body
-            logf[(r0 + r) * K + k] = v;
+            logf[(r0 + r) * Kstride + k] = v;
           }
         }
       }
@@ -431,7 +431,8 @@ template <int KB, int KX, int RB, int P, int TPB>
 __global__ void __launch_bounds__(TPB, 1)
 k_density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
                   const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
-                  const int* __restrict__ has_half, double* __restrict__ logf) {
+                  const int* __restrict__ has_half, double* __restrict__ logf, int Kstride) {
+  // K classes starting at the pointers given (a launch may cover a chunk of the model's classes); logf rows hold Kstride
   extern __shared__ uint4 smem4[];
   const bool half = (*has_half != 0);
   uint4* ring = smem4;                       // [P][RB][TPB]
@@ -443,8 +444,8 @@ k_density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int K, in
     if (half) sval[t] = validg[t];
   }
   __syncthreads();
-  if (half) density_sk_ring<KB, KX, RB, P, TPB, true>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf);
-  else      density_sk_ring<KB, KX, RB, P, TPB, false>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf);
+  if (half) density_sk_ring<KB, KX, RB, P, TPB, true>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf, Kstride);
+  else      density_sk_ring<KB, KX, RB, P, TPB, false>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf, Kstride);
 }
 
 // free dispersion ("skd"): per-column log-odds, logf_ik = B_k - sum over mismatching columns d of L_kd.  The sum walks
