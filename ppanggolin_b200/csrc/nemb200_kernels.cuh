@@ -65,7 +65,8 @@ struct Params {
 //    (16-byte peer stores), which is the all-gather the replicated Gauss-Seidel sweep needs;
 //  * k_mstep_finalize reads the column statistics of every rank (peer loads) and adds them in rank order, which is the
 //    all-reduce of the M-step, fused into the consuming kernel (same order on every rank -> identical parameters);
-//  * k_peer_signal / k_peer_wait are the two tiny flag barriers per iteration that order those accesses.
+//  * two flag barriers per iteration order those accesses: k_peer_signal_wait in front of k_mstep_finalize; the last
+//    CTA of k_peer_broadcast signals the densities, and the sweep kernel's CTAs wait for them (peer_wait_lane).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 struct PeerOut {            // k_peer_broadcast: ptr[1..n-1] = the peers' buffers; row_off = first double of the shard
@@ -144,18 +145,6 @@ __global__ void k_peer_signal_wait(int* const* peer_sig, const int* sig, int n, 
   }
   peer_wait_lane(sig, n, phase, epoch, error);
 }
-__global__ void k_peer_wait(const int* sig /*own sig array*/, int n, int phase, int epoch, int* error) {
-  if (threadIdx.x < n && blockIdx.x == 0) {
-    const volatile int* src = sig + phase * kMaxPeers + threadIdx.x;
-    long long spins = 0;
-    while (*src < epoch) {
-      __nanosleep(200);
-      if (++spins > (1LL << 24)) { atomicExch(error, 2); break; }   // ~several seconds: never hang the GPU
-    }
-    __threadfence_system();
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // E-step part 1: log densities.  A group of G lanes walks RB rows at once so that each class's centre words are
 // fetched from shared memory once per RB matrix words.
