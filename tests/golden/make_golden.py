@@ -69,7 +69,12 @@ def nem_cases():
     save_nem_case("wide1000", sp.X, sp.rowptr, sp.col, sp.w, 3, sp.beta_eff(2.5), False, 100)
     sp = synth_pangenome(600, 64, seed=14, chain_order=True)
     save_nem_case("chain_order", sp.X, sp.rowptr, sp.col, sp.w, 4, sp.beta_eff(2.5), False, 100)
-    # a run the reference abandons (empty class): tiny matrix, many classes
+    # neighbour term with more classes than the 3-class runs above (9 classes: 16 lanes per row in the sweep kernel) ...
+    sp = synth_pangenome(1400, 130, seed=15)
+    save_nem_case("graph_K9", sp.X, sp.rowptr, sp.col, sp.w, 9, sp.beta_eff(2.5), False, 100)
+    # ... and with neighbour lists of up to ~40 entries (sm_degree 60; the sweep keeps 8 inline per row)
+    sp = synth_pangenome(1500, 120, seed=31, sm_degree=60)
+    save_nem_case("highdeg", sp.X, sp.rowptr, sp.col, sp.w, 3, sp.beta_eff(2.5), False, 100)
     # a run the reference abandons (STS_W_EMPTYCLASS, no .uf): with 2000 columns the eps = 0.5 class underflows to an
     # exactly-zero posterior for every row, so its size is 0 at the first M-step
     X = np.zeros((40, 2000), np.uint8); X[:20] = 1
