@@ -79,6 +79,50 @@ def _device_input(inp):
     return engine.DeviceInput.from_numpy(inp.host_bits(), inp.D, inp.rowptr, inp.col, inp.w)
 
 
+# One instance whose matrix is at least this large is row-sharded over the ranks of an initialised process group (SURVEY.md
+# section 8e, "one large instance"); smaller ones run on the calling rank's GPU.
+SHARD_MIN_BYTES = int(os.environ.get("PPANGGOLIN_B200_SHARD_MIN_BYTES", str(256 << 20)))
+
+
+def _run_sharded(inp, kval: int, beta: float, free_dispersion: bool, itermax: int, flags: int):
+    """The instance through ``nem/sharded.py`` when a process group is active and the matrix is large: every rank keeps a
+    contiguous block of families, the exchange runs over NVLink peer memory inside the kernels, and every rank ends with
+    the same posteriors as a single-GPU run.  Returns None when the instance should run on one GPU."""
+    rank, world, dist = _rank_world()
+    dev_in = inp.device
+    N, Ws = dev_in.bits.shape
+    if world == 1 or N * Ws * 4 < SHARD_MIN_BYTES or N < 2 * world:
+        return None
+    # every rank must hold the same export (same family rows, same genome columns): column order comes from the iteration
+    # order of the caller's genome collection, which may differ between processes -- compare a digest first and let every
+    # rank run the whole instance itself if they differ (same answer, no speed-up)
+    import hashlib
+    import torch
+    colsum = torch.zeros(Ws * 32, dtype=torch.int64, device=dev_in.bits.device)
+    shifts = torch.arange(32, device=colsum.device, dtype=torch.int64)
+    for r0 in range(0, N, 65536):
+        blk = dev_in.bits[r0:r0 + 65536].to(torch.int64) & 0xFFFFFFFF
+        colsum += ((blk.unsqueeze(-1) >> shifts) & 1).sum(0).reshape(-1)
+    digest = hashlib.sha256(colsum.cpu().numpy().tobytes() + "|".join(inp.fam_names[:64] + inp.fam_names[-64:]).encode()).hexdigest()
+    seen = [None] * world
+    dist.all_gather_object(seen, digest)
+    if len(set(seen)) != 1:
+        logging.getLogger("PPanGGOLiN").warning("The ranks hold differently ordered exports of this NEM instance; "
+                                                "it runs unsharded on every rank.")
+        return None
+    from .sharded import CudaBackend, ShardedEM, shard_rows
+    beta32 = float(np.float32(beta))
+    lo, hi = shard_rows(N, world, rank)
+    graph = dev_in if beta32 != 0.0 else None
+    be = CudaBackend(dev_in.bits[lo:hi], inp.D, N, kval, free_dispersion, flags, graph, peer_group=dist.group.WORLD, row_offset=lo)
+    out = ShardedEM(be, N, kval, rank, world, dist.group.WORLD).run(beta32, itermax, 0.01)
+    mu, eps, pk, _ = be.plan.get_params()
+    run = engine.NemRun(out.T, mu, eps, pk, list(out.crit), out.n_iter, out.converged, out.status,
+                        dev_in.n_levels if graph is not None else 1, 0.0)
+    be.plan.close()
+    return run
+
+
 def _g(x: float, spec: str) -> float:
     """Value after the C printf/parse round trip the reference performs through the .mf file."""
     return float(spec % x)
@@ -110,8 +154,10 @@ def run_partitioning(
         raise FileNotFoundError(f"no exported NEM instance registered for {nem_dir_path}: call write_nem_input_files first")
     if inp.device is None:
         inp.device = _device_input(inp)
-    run = engine.nem_run_device(inp.device, kval, beta, free_dispersion, itermax=itermax, cv_th=0.01,
-                                flags=_epilogue_flags(nb_org))
+    run = _run_sharded(inp, kval, beta, free_dispersion, itermax, _epilogue_flags(nb_org))
+    if run is None:
+        run = engine.nem_run_device(inp.device, kval, beta, free_dispersion, itermax=itermax, cv_th=0.01,
+                                    flags=_epilogue_flags(nb_org))
     if not run.ok:
         # the reference writes no .uf in this case and partition.py:233-265 returns empty objects
         if just_log_likelihood:

@@ -40,7 +40,11 @@ if os.environ.get("CHUNK_DEBUG"):
 junk = [object() for _ in range(rank * 100003)]   # different heap layouts per rank: set iteration orders of objects differ
 layouts = mg.make_layouts(3000, 240, 31)
 pan = minipan.build_from_layouts(layouts, 3000)
-for name, kw in [("chunked", dict(kval=3, chunk_size=60)), ("autoK", dict(kval=-1, chunk_size=10**6, krange=[3, 12]))]:
+part.SHARD_MIN_BYTES = 1 << 62
+cases = [("chunked", dict(kval=3, chunk_size=60)), ("autoK", dict(kval=-1, chunk_size=10**6, krange=[3, 12])),
+         ("fixedK on one GPU per rank", dict(kval=3, chunk_size=10**6)), ("fixedK row-sharded", dict(kval=3, chunk_size=10**6))]
+for name, kw in cases:
+    part.SHARD_MIN_BYTES = 0 if name.endswith("row-sharded") else 1 << 62
     for f in pan.gene_families:
         f.partition = ""
     pan.status["partitioned"] = "No"
