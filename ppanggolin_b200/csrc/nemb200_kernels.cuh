@@ -873,8 +873,8 @@ k_scatter(const int2* __restrict__ ent, long long N, const int* __restrict__ his
   const int lane = threadIdx.x & 31;
   int2 e = make_int2(-1, -1);
   if (i < N) e = ent[i];
-  scatter_one(e.x, i, lane, s_off, fill, perm);
-  scatter_one(e.y, i, lane, s_off, fill, perm);
+  if (__any_sync(0xffffffffu, e.x >= 0)) scatter_one(e.x, i, lane, s_off, fill, perm);   // "leaves a class": rare, never on a full recount
+  if (__any_sync(0xffffffffu, e.y >= 0)) scatter_one(e.y, i, lane, s_off, fill, perm);
 }
 
 constexpr int kPlanes = 12;
