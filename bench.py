@@ -10,7 +10,11 @@ fits one GPU (1.25 GB of bits).  A *step* is one EM iteration: M-step (column st
 dispersions, proportions), E-step (log-densities of every family, then the level-scheduled Gauss-Seidel posterior
 sweep) and the convergence read-back.  The matrix is 10x larger than L2, so no L2 flush is needed between steps.
 
-`value`  : EM iterations / s with the matrix resident in HBM (max over ranks of the CUDA-event time of K steps).
+`value`  : EM iterations / s with the matrix resident in HBM (max over ranks of the CUDA-event time of K steps).  The timed
+           region holds the K iterations only, every one recounting all one-hot rows (`value_incremental`: the product
+           default, which re-streams only rows that changed class, bit-identical posteriors); the convergence word of
+           iteration s reaches the host after iteration s + 1 was enqueued, like in the library's own run loop; the
+           per-stage / per-kernel events of `roofline` are taken in a second pass after the timed one.
 `e2e`    : the same metric through the host-buffer C-ABI call `nemb200_nem_host` (pinned host matrix -> H2D -> EM to
            convergence -> posteriors D2H), i.e. what a caller of `run_partitioning` pays per instance.
 `roofline`: the dominant kernel of a step, algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json.
