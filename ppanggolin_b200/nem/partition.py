@@ -98,11 +98,9 @@ def _run_sharded(inp, kval: int, beta: float, free_dispersion: bool, itermax: in
     # rank run the whole instance itself if they differ (same answer, no speed-up)
     import hashlib
     import torch
-    colsum = torch.zeros(Ws * 32, dtype=torch.int64, device=dev_in.bits.device)
-    shifts = torch.arange(32, device=colsum.device, dtype=torch.int64)
-    for r0 in range(0, N, 65536):
-        blk = dev_in.bits[r0:r0 + 65536].to(torch.int64) & 0xFFFFFFFF
-        colsum += ((blk.unsqueeze(-1) >> shifts) & 1).sum(0).reshape(-1)
+    colsum = torch.zeros(Ws, dtype=torch.int64, device=dev_in.bits.device)     # per 32-column word: sum of the rows' words
+    for r0 in range(0, N, 8192):
+        colsum += (dev_in.bits[r0:r0 + 8192].to(torch.int64) & 0xFFFFFFFF).sum(0)
     digest = hashlib.sha256(colsum.cpu().numpy().tobytes() + "|".join(inp.fam_names[:64] + inp.fam_names[-64:]).encode()).hexdigest()
     seen = [None] * world
     dist.all_gather_object(seen, digest)
