@@ -95,11 +95,15 @@ class PangenomeArrays:
         N = int(fam_rows.numel())
         rowmap = torch.cumsum(present.to(torch.long), 0) - 1
         W = row_stride_words(Ds)
-        x = torch.zeros((N, W * 32), dtype=torch.bool, device=dev)
-        x[:, :Ds] = sub.index_select(0, fam_rows)
         shifts = torch.arange(32, device=dev, dtype=torch.int64)
-        words = (x.view(N, W, 32).to(torch.int64) << shifts).sum(-1)
-        bits = torch.where(words >= 2**31, words - 2**32, words).to(torch.int32)
+        bits = torch.empty((N, W), dtype=torch.int32, device=dev)
+        step = max(1, (1 << 24) // max(W * 32, 1))          # rows per block: the int64 expansion stays around 128 MB
+        for r0 in range(0, N, step):
+            rows = fam_rows[r0:r0 + step]
+            x = torch.zeros((rows.numel(), W * 32), dtype=torch.bool, device=dev)
+            x[:, :Ds] = sub.index_select(0, rows)
+            words = (x.view(rows.numel(), W, 32).to(torch.int64) << shifts).sum(-1)
+            bits[r0:r0 + step] = torch.where(words >= 2**31, words - 2**32, words).to(torch.int32)
         # ---- edge coverage in the subset (partition.py:399-407)
         mask = torch.zeros(self.presence.shape[1], dtype=torch.long, device=dev)
         mask[S] = 1
