@@ -117,3 +117,48 @@ def test_chunk_samples_dealt_to_two_ranks_give_the_same_votes(tmp_path, n_sample
     for r in range(2):
         assert np.array_equal(np.load(tmp_path / f"votes_2_{r}.npy"), v1)
         assert np.array_equal(np.load(tmp_path / f"validated_2_{r}.npy"), ok1)
+
+
+class _Org:
+    def __init__(self, name):
+        self.name = name
+
+
+def _sample_sync(rank, world, port, out):
+    """Random genome samples under a process group: rank 0's draw reaches every rank, by genome name."""
+    for p in (str(ROOT), str(ROOT / "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import json
+    import random
+    from collections import Counter
+    from ppanggolin_b200.nem import partition as ppp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orgs = [_Org(f"g{i:03d}") for i in range(57)]
+    random.seed(100 + rank)                   # the ranks' own random streams and collection orders differ on purpose
+    random.shuffle(orgs)
+    chosen = ppp._same_on_all_ranks(set(random.sample(orgs, 20)), orgs)
+    assert all(o in orgs for o in chosen)     # this rank's own objects, not unpickled copies
+    ppp.samples = []
+    counts = Counter({o: 0 for o in orgs})
+    ppp._draw_samples_synced(orgs, 10, counts, 2)
+    rec = {"chosen": sorted(o.name for o in chosen), "samples": [sorted(o.name for o in s) for s in ppp.samples],
+           "counts": sorted((o.name, c) for o, c in counts.items())}
+    with open(f"{out}/sync_{rank}.json", "w") as f:
+        json.dump(rec, f)
+    with ppp.local_instances():               # nested callers switch the dealing-out off
+        assert ppp._rank_world()[:2] == (0, 1)
+    assert ppp._rank_world()[:2] == (rank, world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_random_genome_samples_are_the_same_on_every_rank(tmp_path):
+    import json
+    mp.spawn(_sample_sync, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a = json.load(open(tmp_path / "sync_0.json")); b = json.load(open(tmp_path / "sync_1.json"))
+    assert a == b
+    assert len(a["chosen"]) == 20 and len(a["samples"]) >= 10 and all(len(s) == 10 for s in a["samples"])
+    assert all(c >= 2 for _, c in a["counts"])
