@@ -405,7 +405,13 @@ extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, 
       const int ntx = (W4 + kOhTpb - 1) / kOhTpb;
       const int tw = (W4 + ntx - 1) / ntx;
       const size_t smem = onehot_ring_smem();
-      CK(cudaFuncSetAttribute(k_mstep_onehot_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      static bool smem_set[64] = {false};
+      int dev = 0;
+      CK(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 64 || !smem_set[dev]) {
+        CK(cudaFuncSetAttribute(k_mstep_onehot_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) smem_set[dev] = true;
+      }
       const long long sl = std::min<long long>(std::max<long long>(num_sms() / ntx, 1), 65535);
       k_mstep_onehot_ring<<<dim3(ntx, (unsigned)sl), kOhTpb, smem, st>>>((const uint4*)bits, W4, tw, K, pl->offsets, pl->perm,
                                                                         cnt_acc, pl->Dpad);
@@ -544,7 +550,13 @@ static int launch_density_ring(nemb200_plan* pl, const uint32_t* bits, double* l
   if (smem > 220 * 1024) return 0;
   if (force ? atoi(force) == 0 : pl->N_local < rows_per_block * num_sms()) return 0;
   auto kern = k_density_sk_ring<KB, KX, RB, P, TPB>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set[64] = {0};   // per instantiation and device: the opt-in only has to grow
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || smem > smem_set[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) smem_set[dev] = smem;
+  }
   long long blocks = (pl->N_local + rows_per_block - 1) / rows_per_block;
   if (blocks > num_sms()) blocks = num_sms();
   if (blocks < 1) blocks = 1;
