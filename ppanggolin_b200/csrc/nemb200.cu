@@ -96,6 +96,9 @@ void cached_free(void* p, size_t bytes) {
   if (!p) return;
   int dev = 0;
   cudaGetDevice(&dev);
+  cudaPointerAttributes at;   // the block belongs to the device it was allocated on, whatever is current now
+  if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) dev = at.device;
+  else cudaGetLastError();
   bytes = block_size_of(bytes);
   std::lock_guard<std::mutex> lk(g_cache_mu);
   if (g_cache_bytes + bytes > kCacheLimit) { cudaFree(p); return; }
@@ -184,7 +187,10 @@ struct nemb200_plan {
   int* crit_recbad = nullptr;
   CcState* crit_state = nullptr;
   // run buffers of the whole-run drivers (nem_host / nem_device / batch); not used by the stepwise interface
+  bool stepwise_used = false;     // work was enqueued through the stepwise entry points on a stream this library does not own
   bool with_run_buffers = false;
+  bool batch_ell = false;         // batched runs: the schedule-ordered graph copy lives in the plan's block
+  void* ell_in_block = nullptr;
   double* run_logf = nullptr;
   float *run_Ta = nullptr, *run_Tb = nullptr;
   void* block = nullptr;          // the one device allocation everything above is carved from
@@ -201,8 +207,8 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   P.m1 = ar.take<uint32_t>(K * Ws); P.valid = ar.take<uint32_t>(K * Ws);
   P.L = ar.take<double>(pl->free_disp ? K * Dpad : (size_t)K); P.B = ar.take<double>(K);
   P.has_half = ar.take<int>(1);
-  pl->flags2 = ar.take<uint32_t>(2);
-  P.status = (int*)(pl->flags2 + 1);
+  pl->flags2 = ar.take<uint32_t>(kStWords + 8);   // kSt* state words of a run, then the sweep barrier counter of batched runs
+  P.status = (int*)(pl->flags2 + kStStatus);
   // statistics that a multi-GPU driver all-reduces: one contiguous int32 block and one contiguous fp64 block
   pl->cnt = ar.take<int>(K * Dpad + K); pl->fsum = ar.take<double>(K * Dpad + K);
   pl->nk_cnt = pl->cnt + K * Dpad; pl->nk_fz = pl->fsum + K * Dpad;
@@ -227,11 +233,12 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   }
   if (pl->with_run_buffers) {
     pl->run_logf = ar.take<double>(N * K); pl->run_Ta = ar.take<float>(N * K); pl->run_Tb = ar.take<float>(N * K);
+    if (pl->batch_ell) pl->ell_in_block = ar.take<char>(N * (sizeof(int4) + kEllW * sizeof(int2)));
   }
 }
 
 static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int64_t D, int64_t row_stride_words,
-                      int32_t K, int32_t free_disp, uint32_t flags, bool with_run_buffers);
+                      int32_t K, int32_t free_disp, uint32_t flags, bool with_run_buffers, bool batch_ell = false);
 
 extern "C" int nemb200_abi_version(void) { return NEMB200_ABI_VERSION; }
 extern "C" const char* nemb200_last_error(void) { return g_err.c_str(); }
@@ -247,7 +254,7 @@ extern "C" int nemb200_plan_create(nemb200_plan** out, int64_t N_local, int64_t 
 }
 
 static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int64_t D, int64_t row_stride_words,
-                      int32_t K, int32_t free_disp, uint32_t flags, bool with_run_buffers) {
+                      int32_t K, int32_t free_disp, uint32_t flags, bool with_run_buffers, bool batch_ell) {
   if (!out || N_local < 0 || N_total < 1 || D < 1 || K < 1 || K > NEMB200_MAX_K || row_stride_words % 4 != 0 ||
       row_stride_words * 32 < D || N_total > 0x7fffffffLL)
     return fail(NEMB200_ERR_ARG, "plan_create: bad shape N_local=%lld N_total=%lld D=%lld stride=%lld K=%d",
@@ -258,6 +265,7 @@ static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int6
   pl->N_local = N_local; pl->N_total = N_total; pl->D = (int)D; pl->Ws = (int)row_stride_words;
   pl->Dpad = pl->Ws * 32; pl->K = K; pl->free_disp = free_disp ? 1 : 0; pl->flags = flags;
   pl->with_run_buffers = with_run_buffers;
+  pl->batch_ell = batch_ell;
   Params& P = pl->P;
   P.K = K; P.D = pl->D; P.Ws = pl->Ws; P.Dpad = pl->Dpad; P.free_disp = pl->free_disp;
   pl->fin_chunks = (pl->Dpad + kFinCols - 1) / kFinCols;
@@ -285,6 +293,8 @@ extern "C" void nemb200_plan_destroy(nemb200_plan* pl) {
   if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
   if (pl->ev_join) cudaEventDestroy(pl->ev_join);
   if (pl->side) cudaStreamDestroy(pl->side);
+  // a block goes back to the cache only when nothing queued on the caller's streams can still touch it
+  if (pl->stepwise_used && !pl->attached) cudaDeviceSynchronize();
   if (pl->attached) {
     cudaDeviceSynchronize();
     for (int r = 0; r < pl->world; r++)
@@ -358,6 +368,7 @@ static int launch_fuzzy(nemb200_plan* pl, const uint32_t* bits, const float* T, 
 extern "C" int nemb200_mstep_accumulate(nemb200_plan* pl, const uint32_t* bits, const float* T, void* stream_) {
   if (!pl || (pl->N_local > 0 && (!bits || !T))) return fail(NEMB200_ERR_ARG, "mstep_accumulate: null argument");
   cudaStream_t st = (cudaStream_t)stream_;
+  pl->stepwise_used = true;
   const int K = pl->K;
   const long long N = pl->N_local;
   // The running one-hot counts live in the exposed block itself unless a collective library reduces that block in place
@@ -640,6 +651,7 @@ static int density_to(nemb200_plan* pl, const uint32_t* bits, double* logf, cuda
 extern "C" int nemb200_density(nemb200_plan* pl, const uint32_t* bits, double* logf, void* stream_) {
   if (!pl || (pl->N_local > 0 && (!bits || !logf))) return fail(NEMB200_ERR_ARG, "density: null argument");
   if (pl->N_local == 0) return NEMB200_OK;
+  pl->stepwise_used = true;
   return density_to(pl, bits, logf, (cudaStream_t)stream_);
 }
 
@@ -748,6 +760,7 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
                              float beta_now, uint32_t* maxdiff_bits, void* stream_) {
   if (!pl || !logf || !T_old || !T_new || N < 1) return fail(NEMB200_ERR_ARG, "sweep: null argument");
   cudaStream_t st = (cudaStream_t)stream_;
+  pl->stepwise_used = true;
   if (!maxdiff_bits) {  // use (and reset) the plan's own convergence word, read back with nemb200_read_flags
     maxdiff_bits = pl->flags2;
     CK(cudaMemsetAsync(pl->flags2, 0, sizeof(uint32_t), st));
@@ -1159,6 +1172,8 @@ static int run_em(nemb200_plan* pl, const uint32_t* bits, const int32_t* rowptr,
   return r.finish(T_out, res);
 }
 
+#include "nemb200_batch.inc"
+
 static int copy_params_out(nemb200_plan* pl, float* mu, float* eps, float* pk, cudaStream_t st) {
   const size_t kd = (size_t)pl->K * pl->D * sizeof(float);
   if (eps && !pl->free_disp) {
@@ -1180,12 +1195,23 @@ extern "C" int nemb200_nem_device(const uint32_t* bits, int64_t N, int64_t D, in
                                   void* stream_) {
   if (!bits || N < 1) return fail(NEMB200_ERR_ARG, "nem_device: null matrix");
   if (beta != 0.0f && (!rowptr || !col || !w)) return fail(NEMB200_ERR_ARG, "nem_device: beta != 0 needs the neighbour graph");
+  if (K < 1 || K > NEMB200_MAX_K || row_stride_words % 4 != 0 || row_stride_words * 32 < D || D < 1)
+    return fail(NEMB200_ERR_ARG, "nem_device: bad shape D=%lld stride=%lld K=%d", (long long)D, (long long)row_stride_words, K);
+  if (batch_eligible(N, row_stride_words, K)) {   // small instance: the device-resident loop (a batch of one)
+    nemb200_result tmp;
+    const std::vector<int> one{0};
+    return batch_run(one, &bits, &N, &D, &row_stride_words, &rowptr, &col, &w, &sched_level_ptr, &sched_rows, &n_levels, &K, &beta,
+                     &free_disp, &itermax, cv_th, flags, &T_out, &mu_out, &eps_out, &pk_out, result ? result : &tmp,
+                     (cudaStream_t)stream_, true);
+  }
   nemb200_plan* pl = nullptr;
   int rc = plan_build(&pl, N, N, D, row_stride_words, K, free_disp, flags, true);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream_;
   rc = run_em(pl, bits, rowptr, col, w, sched_level_ptr, sched_rows, n_levels, beta, itermax, cv_th, T_out, result, st);
   if (rc == 0) rc = copy_params_out(pl, mu_out, eps_out, pk_out, st);
+  cudaStreamSynchronize(st);
+  pl->stepwise_used = false;   // everything this run enqueued has completed
   nemb200_plan_destroy(pl);
   return rc;
 }
@@ -1200,6 +1226,24 @@ extern "C" int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* b
                                         float* const* pk_out, nemb200_result* results) {
   if (n_inst < 1 || !bits || !N || !D || !row_stride_words || !K || !beta || !free_disp || !itermax || !results)
     return fail(NEMB200_ERR_ARG, "nem_device_batch: null argument");
+  // small instances (every K candidate, every chunk sample): grouped, one launch per EM phase and group, convergence on
+  // the device; the others (matrices that want the streaming kernels) keep one stream each below
+  std::vector<int> small;
+  std::vector<char> is_small(n_inst, 0);
+  for (int i = 0; i < n_inst; i++) {
+    if (!bits[i] || N[i] < 1) return fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d has no matrix", i);
+    if (beta[i] != 0.0f && (!rowptr || !col || !w || !rowptr[i] || !col[i] || !w[i]))
+      return fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d needs its neighbour graph", i);
+    if (K[i] < 1 || K[i] > NEMB200_MAX_K || row_stride_words[i] % 4 != 0 || row_stride_words[i] * 32 < D[i] || D[i] < 1)
+      return fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d has a bad shape", i);
+    if (batch_eligible(N[i], row_stride_words[i], K[i])) { small.push_back(i); is_small[i] = 1; }
+  }
+  if (!small.empty()) {
+    const int brc = batch_run(small, bits, N, D, row_stride_words, rowptr, col, w, sched_level_ptr, sched_rows, n_levels, K, beta,
+                              free_disp, itermax, cv_th, flags, T_out, mu_out, eps_out, pk_out, results);
+    if (brc) return brc;
+    if ((int)small.size() == n_inst) return NEMB200_OK;
+  }
   std::vector<EmRun> runs(n_inst);
   std::vector<nemb200_plan*> plans(n_inst, nullptr);
   std::vector<cudaStream_t> streams(n_inst, nullptr);
@@ -1207,10 +1251,11 @@ extern "C" int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* b
   auto cleanup = [&]() {
     for (auto s : streams) if (s) { cudaStreamSynchronize(s); }
     runs.clear();                                   // frees the per-run device buffers
-    for (auto p : plans) nemb200_plan_destroy(p);
+    for (auto p : plans) { if (p) p->stepwise_used = false; nemb200_plan_destroy(p); }   // streams synchronised above
     for (auto s : streams) if (s) cudaStreamDestroy(s);
   };
   for (int i = 0; i < n_inst && rc == 0; i++) {
+    if (is_small[i]) { runs[i].active = false; continue; }
     const bool graph = beta[i] != 0.0f;
     if (!bits[i] || N[i] < 1) { rc = fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d has no matrix", i); break; }
     if (graph && (!rowptr || !col || !w || !rowptr[i] || !col[i] || !w[i])) { rc = fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d needs its neighbour graph", i); break; }
@@ -1238,8 +1283,9 @@ extern "C" int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* b
     for (int i = 0; i < n_inst && rc == 0; i++)
       if (runs[i].active) { rc = runs[i].poll(); any = any || runs[i].active; }
   }
-  for (int i = 0; i < n_inst && rc == 0; i++) rc = runs[i].finish_enqueue();   // all criteria kernels in flight together
+  for (int i = 0; i < n_inst && rc == 0; i++) if (!is_small[i]) rc = runs[i].finish_enqueue();   // all criteria kernels in flight together
   for (int i = 0; i < n_inst && rc == 0; i++) {
+    if (is_small[i]) continue;
     rc = runs[i].finish(T_out ? T_out[i] : nullptr, &results[i]);
     if (rc == 0) rc = copy_params_out(plans[i], mu_out ? mu_out[i] : nullptr, eps_out ? eps_out[i] : nullptr,
                                       pk_out ? pk_out[i] : nullptr, streams[i]);
@@ -1291,6 +1337,25 @@ extern "C" int nemb200_nem_host(const uint32_t* bits, int64_t N, int64_t D, int6
     CK(cudaStreamSynchronize(st));  // lp / lr are locals
   }
   if ((rc = dmal((void**)&d_T, (size_t)N * K * sizeof(float)))) return rc;
+  if (K >= 1 && K <= NEMB200_MAX_K && row_stride_words % 4 == 0 && batch_eligible(N, row_stride_words, K)) {
+    float *d_mu = nullptr, *d_eps = nullptr, *d_pk = nullptr;
+    const size_t kd = (size_t)K * D * sizeof(float);
+    if (mu_out && (rc = dmal((void**)&d_mu, kd))) return rc;
+    if (eps_out && (rc = dmal((void**)&d_eps, kd))) return rc;
+    if (pk_out && (rc = dmal((void**)&d_pk, K * sizeof(float)))) return rc;
+    nemb200_result tmp;
+    const std::vector<int> one{0};
+    const uint32_t* cb = d_bits; const int32_t *crp = d_rowptr, *ccol = d_col, *clp = d_lp, *clr = d_lr; const float* cw = d_w;
+    rc = batch_run(one, &cb, &N, &D, &row_stride_words, &crp, &ccol, &cw, &clp, &clr, &n_levels, &K, &beta, &free_disp, &itermax,
+                   cv_th, flags, &d_T, &d_mu, &d_eps, &d_pk, result ? result : &tmp, st, true);
+    if (rc) return rc;
+    if (T_out) CK(cudaMemcpyAsync(T_out, d_T, (size_t)N * K * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (mu_out) CK(cudaMemcpyAsync(mu_out, d_mu, kd, cudaMemcpyDeviceToHost, st));
+    if (eps_out) CK(cudaMemcpyAsync(eps_out, d_eps, kd, cudaMemcpyDeviceToHost, st));
+    if (pk_out) CK(cudaMemcpyAsync(pk_out, d_pk, K * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return NEMB200_OK;
+  }
   nemb200_plan* pl = nullptr;
   rc = plan_build(&pl, N, N, D, row_stride_words, K, free_disp, flags, true);
   if (rc) return rc;
@@ -1300,6 +1365,8 @@ extern "C" int nemb200_nem_host(const uint32_t* bits, int64_t N, int64_t D, int6
     if (e != cudaSuccess) rc = fail(NEMB200_ERR_CUDA, "nem_host: D2H %s", cudaGetErrorString(e));
   }
   if (rc == 0) rc = copy_params_out(pl, mu_out, eps_out, pk_out, st);
+  cudaStreamSynchronize(st);
+  pl->stepwise_used = false;
   nemb200_plan_destroy(pl);
   return rc;
 }

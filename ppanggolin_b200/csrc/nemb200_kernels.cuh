@@ -129,7 +129,7 @@ __device__ __forceinline__ void peer_wait_lane(const int* sig, int n, int phase,
     long long spins = 0;
     while (*src < epoch) {
       __nanosleep(200);
-      if (++spins > (1LL << 24)) { atomicExch(error, 2); break; }   // ~several seconds: never hang the GPU
+      if (++spins > (1LL << 27)) { atomicExch(error, 2); break; }   // ~half a minute: a stalled peer, never a hung GPU
     }
     __threadfence_system();
   }
@@ -257,10 +257,10 @@ __device__ __forceinline__ void density_sk_body(const uint4* __restrict__ bits, 
 constexpr int kDensTpb = 128;
 
 template <int KB, int KX, int RB>
-__global__ void __launch_bounds__(kDensTpb)
-k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
-             const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
-             const int* __restrict__ has_half, double* __restrict__ logf, int planes_in_smem) {
+__device__ __forceinline__ void
+density_sk_cta(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
+               const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
+               const int* __restrict__ has_half, double* __restrict__ logf, int planes_in_smem) {
   extern __shared__ uint4 smem4[];
   const bool half = (*has_half != 0);   // any centre at 0.5 (exact median tie): needs the `valid` plane
   if (planes_in_smem) {
@@ -278,6 +278,14 @@ k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, 
     if (half) density_sk_body<KB, KX, RB, true>(bits, N, W4, K, G, m1g, validg, L, B, logf);
     else      density_sk_body<KB, KX, RB, false>(bits, N, W4, K, G, m1g, validg, L, B, logf);
   }
+}
+
+template <int KB, int KX, int RB>
+__global__ void __launch_bounds__(kDensTpb)
+k_density_sk(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
+             const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
+             const int* __restrict__ has_half, double* __restrict__ logf, int planes_in_smem) {
+  density_sk_cta<KB, KX, RB>(bits, N, W4, K, G, m1g, validg, L, B, has_half, logf, planes_in_smem);
 }
 
 // ---- shared-memory ring variant -------------------------------------------------------------------------------------
@@ -444,10 +452,10 @@ k_density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int K, in
 // almost everywhere (the common cases) cost 0-2 lookups per word, mixed rows at most 8.  +inf entries (e_kd <= 1e-20)
 // propagate to the reference's null density; a word whose total is infinite is summed directly.
 template <int KB>
-__global__ void __launch_bounds__(256)
-k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int G,
-              const uint32_t* __restrict__ m1, const uint32_t* __restrict__ valid, const double* __restrict__ Ltab /*[K][Ws*8][16]*/,
-              const double* __restrict__ Lword /*[K][Ws]*/, const double* __restrict__ B, double* __restrict__ logf) {
+__device__ __forceinline__ void
+density_skd_body(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int G,
+                 const uint32_t* __restrict__ m1, const uint32_t* __restrict__ valid, const double* __restrict__ Ltab /*[K][Ws*8][16]*/,
+                 const double* __restrict__ Lword /*[K][Ws]*/, const double* __restrict__ B, double* __restrict__ logf) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
   const int grp = lane / G;
@@ -491,6 +499,14 @@ k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int
     for (int k = 0; k < KB; k++)
       if (k < K && (k & (G - 1)) == sub && row < N) logf[row * K + k] = B[k] - s[k];
   }
+}
+
+template <int KB>
+__global__ void __launch_bounds__(256)
+k_density_skd(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int G, const uint32_t* __restrict__ m1,
+              const uint32_t* __restrict__ valid, const double* __restrict__ Ltab, const double* __restrict__ Lword,
+              const double* __restrict__ B, double* __restrict__ logf) {
+  density_skd_body<KB>(bits, N, Ws, K, G, m1, valid, Ltab, Lword, B, logf);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -672,8 +688,32 @@ __device__ __forceinline__ void sweep_finish(const SweepArgs& a, const SweepPre<
   }
 }
 
-template <bool COOP, int GS>
-__global__ void __launch_bounds__(COOP ? 1024 : 256) k_sweep(SweepArgs a) {
+// Barrier between the levels of one sweep: the whole grid (single instance, cooperative launch) ...
+struct GridBar {
+  __device__ __forceinline__ void sync() const { __threadfence(); cg::this_grid().sync(); }
+};
+// ... or the CTAs of ONE instance of a batched launch (blockIdx.z = instance; all CTAs of the launch are co-resident --
+// cooperative launch -- so spinning is safe).  Monotonic counter: every CTA adds one per barrier and waits until the
+// count reaches the next multiple of the instance's CTA count; the counter is reset between launches by k_b_poll.
+struct InstBar {
+  unsigned* ctr;
+  unsigned nctas;
+  __device__ __forceinline__ void sync() const {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned t = atomicAdd(ctr, 1u);
+      const unsigned target = (t / nctas + 1u) * nctas;
+      unsigned v;
+      do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+};
+
+template <bool COOP, int GS, class Bar>
+__device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (GS - 1), grp = lane / GS;
   constexpr int RPW = 32 / GS;  // rows per warp
@@ -750,8 +790,7 @@ __global__ void __launch_bounds__(COOP ? 1024 : 256) k_sweep(SweepArgs a) {
           have_pre = true;
         }
         stamp(2 * L - 1);
-        __threadfence();
-        cg::this_grid().sync();
+        bar.sync();
         stamp(2 * L);
       }
     }
@@ -760,6 +799,9 @@ __global__ void __launch_bounds__(COOP ? 1024 : 256) k_sweep(SweepArgs a) {
   for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
   if (lane == 0 && wmax > 0.0f) atomicMax(a.maxdiff_bits, __float_as_uint(wmax));  // non-negative floats order as uints
 }
+
+template <bool COOP, int GS>
+__global__ void __launch_bounds__(COOP ? 1024 : 256) k_sweep(SweepArgs a) { sweep_body<COOP, GS>(a, GridBar()); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // M-step.  Rows whose posterior is exactly one-hot in float32 (the vast majority after the first iteration) only add
@@ -775,10 +817,10 @@ __global__ void __launch_bounds__(COOP ? 1024 : 256) k_sweep(SweepArgs a) {
 constexpr int kNone = -2;  // prev key of a row that is not counted anywhere yet
 
 template <int KB>
-__global__ void __launch_bounds__(256)
-k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ prev /*[N] in/out: key of last M-step*/,
-           int2* __restrict__ ent /*[N]: (remove bucket | -1, add/fuzzy bucket | -1)*/, int* __restrict__ hist /*[2K+1]*/,
-           int* __restrict__ nk_cnt /*[K]*/, double* __restrict__ nk_fz /*[K]*/, int ignore_prev /*full recount*/) {
+__device__ __forceinline__ void
+classify_body(const float* __restrict__ T, long long N, int K, int* __restrict__ prev /*[N] in/out: key of last M-step*/,
+              int2* __restrict__ ent /*[N]: (remove bucket | -1, add/fuzzy bucket | -1)*/, int* __restrict__ hist /*[2K+1]*/,
+              int* __restrict__ nk_cnt /*[K]*/, double* __restrict__ nk_fz /*[K]*/, int ignore_prev /*full recount*/) {
   __shared__ int s_hist[2 * KB + 1];
   __shared__ int s_nk[KB];
   __shared__ double s_fz[KB];
@@ -836,6 +878,13 @@ k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ pr
   }
 }
 
+template <int KB>
+__global__ void __launch_bounds__(256)
+k_classify(const float* __restrict__ T, long long N, int K, int* __restrict__ prev, int2* __restrict__ ent, int* __restrict__ hist,
+           int* __restrict__ nk_cnt, double* __restrict__ nk_fz, int ignore_prev) {
+  classify_body<KB>(T, N, K, prev, ent, hist, nk_cnt, nk_fz, ignore_prev);
+}
+
 // rows -> perm, grouped by bucket.  One atomic per (warp, bucket present in the warp) instead of one per entry: the
 // handful of cursors is shared by all rows, and per-row atomics on them serialise (measured 70 us for 200 000 rows).
 __device__ __forceinline__ void scatter_one(int key, long long i, int lane, const int* s_off, int* __restrict__ fill,
@@ -852,9 +901,9 @@ __device__ __forceinline__ void scatter_one(int key, long long i, int lane, cons
 // offsets[b] = first slot of bucket b in perm (prefix sums of the histogram, b = 0..nb; offsets[nb] = total): every CTA
 // derives them itself (nb <= 65), CTA 0 also publishes them for the count kernels; `fill` (zeroed by the caller) counts
 // the slots handed out per bucket.
-__global__ void __launch_bounds__(256)
-k_scatter(const int2* __restrict__ ent, long long N, const int* __restrict__ hist, int nb, int* __restrict__ offsets /*[nb+1]*/,
-          int* __restrict__ fill /*[nb]*/, int* __restrict__ perm) {
+__device__ __forceinline__ void
+scatter_body(const int2* __restrict__ ent, long long N, const int* __restrict__ hist, int nb, int* __restrict__ offsets /*[nb+1]*/,
+             int* __restrict__ fill /*[nb]*/, int* __restrict__ perm) {
   __shared__ int s_off[2 * NEMB200_MAX_K + 2];
   if (threadIdx.x < 32) {   // warp scan over <= 65 buckets, 3 per lane
     const int lane = threadIdx.x;
@@ -875,6 +924,12 @@ k_scatter(const int2* __restrict__ ent, long long N, const int* __restrict__ his
   if (i < N) e = ent[i];
   if (__any_sync(0xffffffffu, e.x >= 0)) scatter_one(e.x, i, lane, s_off, fill, perm);   // "leaves a class": rare, never on a full recount
   if (__any_sync(0xffffffffu, e.y >= 0)) scatter_one(e.y, i, lane, s_off, fill, perm);
+}
+
+__global__ void __launch_bounds__(256)
+k_scatter(const int2* __restrict__ ent, long long N, const int* __restrict__ hist, int nb, int* __restrict__ offsets,
+          int* __restrict__ fill, int* __restrict__ perm) {
+  scatter_body(ent, N, hist, nb, offsets, fill, perm);
 }
 
 constexpr int kPlanes = 12;
@@ -936,9 +991,9 @@ __device__ __forceinline__ void load_batch(uint32_t (&lo)[kBatch], uint32_t (&hi
 // (12 counter planes hold up to 4095).
 constexpr int kMaxRun = 4080;
 
-__global__ void __launch_bounds__(kMsTpb)
-k_mstep_onehot(const uint2* __restrict__ bits2, int W2, int tile_w, int K, const int* __restrict__ offsets,
-               const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad) {
+__device__ __forceinline__ void
+mstep_onehot_body(const uint2* __restrict__ bits2, int W2, int tile_w, int K, const int* __restrict__ offsets,
+                  const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad) {
   __shared__ __align__(16) int s_rows[kMaxRun];
   __shared__ int s_cnt[kMsTpb * 33];
   const int total = offsets[2 * K];                       // add + remove entries
@@ -1009,6 +1064,12 @@ k_mstep_onehot(const uint2* __restrict__ bits2, int W2, int tile_w, int K, const
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(kMsTpb)
+k_mstep_onehot(const uint2* __restrict__ bits2, int W2, int tile_w, int K, const int* __restrict__ offsets,
+               const int* __restrict__ perm, int* __restrict__ cnt, int Dpad) {
+  mstep_onehot_body(bits2, W2, tile_w, K, offsets, perm, cnt, Dpad);
 }
 
 // ---- shared-memory ring variant for wide matrices -------------------------------------------------------------------
@@ -1196,10 +1257,10 @@ constexpr int kFzRows = 64;
 template <int KB> struct FuzzyCfg { static constexpr int WPT = KB <= 4 ? 4 : (KB <= 8 ? 2 : 1); };
 
 template <int KB>
-__global__ void __launch_bounds__(256)
-k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int* __restrict__ offsets,
-              const int* __restrict__ perm, const float* __restrict__ T, double* __restrict__ fsum /*[K][Dpad]*/,
-              int Dpad) {
+__device__ __forceinline__ void
+mstep_fuzzy_body(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int* __restrict__ offsets,
+                 const int* __restrict__ perm, const float* __restrict__ T, double* __restrict__ fsum /*[K][Dpad]*/,
+                 int Dpad) {
   constexpr int KP = (KB + 1) & ~1;   // even: the staged posteriors are read as double2
   constexpr int WPT = FuzzyCfg<KB>::WPT;
   constexpr int XW = 8 * WPT / 4;     // uint4 per row that the CTA's 8 warps look at (contiguous in the row)
@@ -1297,6 +1358,13 @@ k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int
   }
 }
 
+template <int KB>
+__global__ void __launch_bounds__(256)
+k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int* __restrict__ offsets,
+              const int* __restrict__ perm, const float* __restrict__ T, double* __restrict__ fsum, int Dpad) {
+  mstep_fuzzy_body<KB>(bits, Ws, K, D, offsets, perm, T, fsum, Dpad);
+}
+
 // Parameters from the column statistics.  grid = (column chunks, K); every CTA handles kFinCols columns of one class:
 // centres (weighted median of a 0/1 column, nem_mod.c:1417-1474), inertia (nem_mod.c:1641-1699), centre bit planes and,
 // for "skd", the per-column dispersion and log-odds.  The last CTA of a class to finish (ticket counter) adds the chunk
@@ -1304,9 +1372,9 @@ k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int
 // dispersion of "sk_" (nem_mod.c:1053-1068, MISSING_IGNORE) and the E-step constants L_k, B_k.
 constexpr int kFinCols = 1024;
 
-__global__ void __launch_bounds__(256)
-k_mstep_finalize(Params P, PeerStats ps, long long N_total, double* __restrict__ partial /*[K][nchunk][2]*/,
-                 int* __restrict__ tickets /*[K]*/) {
+__device__ __forceinline__ void
+mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, double* __restrict__ partial /*[K][nchunk][2]*/,
+                    int* __restrict__ tickets /*[K]*/) {
   __shared__ double s_red[8][2];
   __shared__ int s_last;
   const int k = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
@@ -1425,6 +1493,11 @@ k_mstep_finalize(Params P, PeerStats ps, long long N_total, double* __restrict__
   }
 }
 
+__global__ void __launch_bounds__(256)
+k_mstep_finalize(Params P, PeerStats ps, long long N_total, double* __restrict__ partial, int* __restrict__ tickets) {
+  mstep_finalize_body(P, ps, N_total, partial, tickets);
+}
+
 // "sk_": the dispersion is one scalar per class; the K x D table PPanGGOLiN reads from .mf is materialised on demand
 __global__ void k_expand_eps(Params P) {
   const int k = blockIdx.y;
@@ -1434,7 +1507,8 @@ __global__ void k_expand_eps(Params P) {
 
 // nibble tables of k_density_skd: Ltab[k][q][v] = sum of L_kd over the set bits b of v, d = 4 q + b  (q over Dpad / 4),
 // and the totals of every 32-column word.  One thread per (class, word).
-__global__ void k_ltab(const double* __restrict__ Lkd, int K, int Ws, double* __restrict__ Ltab, double* __restrict__ Lword) {
+__device__ __forceinline__ void ltab_body(const double* __restrict__ Lkd, int K, int Ws, double* __restrict__ Ltab,
+                                          double* __restrict__ Lword) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (k, word): [K][Dpad] is contiguous
   if (t >= (long long)K * Ws) return;
   double total = 0.0;
@@ -1456,8 +1530,12 @@ __global__ void k_ltab(const double* __restrict__ Lkd, int K, int Ws, double* __
   Lword[t] = total;
 }
 
+__global__ void k_ltab(const double* __restrict__ Lkd, int K, int Ws, double* __restrict__ Ltab, double* __restrict__ Lword) {
+  ltab_body(Lkd, K, Ws, Ltab, Lword);
+}
+
 // initial parameters: partition.py:65-85 (values) + nem_exe.c:1023-1040 (last proportion by subtraction)
-__global__ void k_init_params(Params P, float base_prop, const float* __restrict__ eps_k /*[K] host-computed*/) {
+__device__ __forceinline__ void init_params_body(const Params& P, float base_prop, const float* __restrict__ eps_k /*[K] host-computed*/) {
   const int K = P.K, D = P.D, Ws = P.Ws, Dpad = P.Dpad;
   const int k = blockIdx.x;
   const bool one = (double)(k + 1) <= (double)K / 2.0;
@@ -1495,6 +1573,8 @@ __global__ void k_init_params(Params P, float base_prop, const float* __restrict
     if (k == 0) { *P.has_half = 0; *P.status = 0; }
   }
 }
+
+__global__ void k_init_params(Params P, float base_prop, const float* __restrict__ eps_k) { init_params_body(P, base_prop, eps_k); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // Criteria (nem_alg.c:2764-2843), once per run.
@@ -1936,6 +2016,223 @@ __global__ void k_sum_partials(const double* __restrict__ p, int n, double* __re
   if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   const double t = ordered_sum(p, n, 1);
   if (threadIdx.x == 0) *out = t;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Batched, device-resident EM for small instances (the K-selection sweep of partition.py:482-514 and the chunk samples of
+// partition.py:837-846: thousands of instances of <= 100 000 x 500).  One launch per EM phase covers ALL instances of a
+// group (blockIdx.z = instance, operands from a descriptor array in device memory), the convergence test of
+// nem_alg.c:1868-1892 runs on the device (k_b_poll) and every kernel of a later iteration returns at once for an
+// instance that is no longer active -- so the host enqueues iterations without ever waiting for one, and only looks at an
+// "any instance still active" word one iteration late.  The arithmetic is the single-instance kernels' (same bodies).
+// ------------------------------------------------------------------------------------------------------------------
+enum { kStMaxdiff = 0, kStStatus = 1, kStActive = 2, kStIter = 3, kStConverged = 4, kStWords = 8 };
+
+struct BatchInst {
+  const uint32_t* bits;
+  long long N;
+  int D, Ws, Dpad, K, free_disp;
+  const int* rowptr; const int* col; const float* w;
+  const int* level_ptr; const int* level_rows; int n_levels;
+  int4* ell_hdr; int2* ell_nb;
+  float beta, cv_th;
+  int itermax, c0;             // c0: posterior buffer that holds the start posteriors (nem_alg.c:2023-2065)
+  int logspace, jacobi, full_recount;
+  Params P;
+  int* cnt; double* fsum; int* nk_cnt; double* nk_fz; int* hist; int* offsets; int* cursor; int* prev; int2* ent; int* perm;
+  double* Ltab; double* Lword; double* fin_partial; int* fin_tickets;
+  double* logf;
+  float* T[2];
+  unsigned* state;             // kSt* words; P.status aliases state + kStStatus
+  unsigned* barrier;           // InstBar counter of the sweep
+  char* zero_from; long long zero_bytes;   // statistics cleared before every M-step
+  float base_prop;
+  float eps_init[NEMB200_MAX_K];
+  // outputs of the run (device pointers of the caller, may be null)
+  float* T_out; float* mu_out; float* eps_out; float* pk_out;
+};
+
+__device__ __forceinline__ bool b_active(const BatchInst& I) { return I.state[kStActive] != 0u; }
+
+// start of a run: initial parameters, "nothing counted yet", zero posteriors (ClassifM is calloc'ed, nem_exe.c:533-536)
+__global__ void __launch_bounds__(256) k_b_start(const BatchInst* __restrict__ B) {
+  const BatchInst& I = B[blockIdx.z];
+  if (blockIdx.x < (unsigned)I.K) {
+    Params P = I.P;
+    // init_params_body works per class with blockIdx.x = class
+    init_params_body(P, I.base_prop, I.eps_init);
+  }
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long t = tid; t < I.N; t += nth) I.prev[t] = kNone;
+  const long long nkd = (long long)I.K * I.Dpad;
+  for (long long t = tid; t < nkd; t += nth) I.cnt[t] = 0;
+  const long long ntk = I.N * I.K;
+  float* T0 = I.T[0];
+  for (long long t = tid; t < ntk; t += nth) T0[t] = 0.0f;
+  for (long long t = tid; t < I.zero_bytes / 4; t += nth) reinterpret_cast<int*>(I.zero_from)[t] = 0;
+  if (tid == 0) {
+    I.state[kStMaxdiff] = 0u; I.state[kStActive] = I.itermax >= 1 ? 1u : 0u; I.state[kStIter] = 0u; I.state[kStConverged] = 0u;
+    *I.barrier = 0u;
+  }
+  if (tid < I.K) I.fin_tickets[tid] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_b_ltab(const BatchInst* __restrict__ B, int gate) {
+  const BatchInst& I = B[blockIdx.z];
+  if (gate && !b_active(I)) return;
+  ltab_body(I.P.L, I.K, I.Ws, I.Ltab, I.Lword);
+}
+
+__global__ void __launch_bounds__(256) k_b_ell_build(const BatchInst* __restrict__ B) {
+  const BatchInst& I = B[blockIdx.z];
+  if (I.ell_hdr == nullptr) return;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= I.N) return;
+  const int i = I.level_rows[idx];
+  const int n0 = I.rowptr[i], deg = I.rowptr[i + 1] - n0;
+  I.ell_hdr[idx] = make_int4(i, deg, n0, 0);
+#pragma unroll
+  for (int u = 0; u < kEllW; u++)
+    I.ell_nb[idx * kEllW + u] = u < deg ? make_int2(I.col[n0 + u], __float_as_int(I.w[n0 + u])) : make_int2(0, 0);
+}
+
+template <int KB>
+__global__ void __launch_bounds__(256) k_b_classify(const BatchInst* __restrict__ B, int s) {
+  const BatchInst& I = B[blockIdx.z];
+  if (!b_active(I) || (long long)blockIdx.x * 256 >= I.N) return;
+  classify_body<KB>(I.T[(I.c0 + s - 1) & 1], I.N, I.K, I.prev, I.ent, I.hist, I.nk_cnt, I.nk_fz, I.full_recount);
+}
+
+__global__ void __launch_bounds__(256) k_b_scatter(const BatchInst* __restrict__ B) {
+  const BatchInst& I = B[blockIdx.z];
+  if (!b_active(I) || (long long)blockIdx.x * 256 >= I.N) return;
+  scatter_body(I.ent, I.N, I.hist, 2 * I.K + 1, I.offsets, I.cursor, I.perm);
+}
+
+__global__ void __launch_bounds__(kMsTpb) k_b_onehot(const BatchInst* __restrict__ B, int tile_w) {
+  const BatchInst& I = B[blockIdx.z];
+  if (!b_active(I)) return;
+  mstep_onehot_body(reinterpret_cast<const uint2*>(I.bits), I.Ws / 2, tile_w, I.K, I.offsets, I.perm, I.cnt, I.Dpad);
+}
+
+template <int KB>
+__global__ void __launch_bounds__(256) k_b_fuzzy(const BatchInst* __restrict__ B, int s) {
+  const BatchInst& I = B[blockIdx.z];
+  if (!b_active(I)) return;
+  mstep_fuzzy_body<KB>(I.bits, I.Ws, I.K, I.D, I.offsets, I.perm, I.T[(I.c0 + s - 1) & 1], I.fsum, I.Dpad);
+}
+
+__global__ void __launch_bounds__(256) k_b_finalize(const BatchInst* __restrict__ B) {
+  const BatchInst& I = B[blockIdx.z];
+  if (!b_active(I) || blockIdx.y >= (unsigned)I.K) return;
+  PeerStats ps;
+  ps.n = 1; ps.iblock[0] = I.cnt; ps.dblock[0] = I.fsum;
+  mstep_finalize_body(I.P, ps, I.N, I.fin_partial, I.fin_tickets);
+}
+
+template <int KB, int KX, int RB>
+__global__ void __launch_bounds__(kDensTpb) k_b_density_sk(const BatchInst* __restrict__ B, int G, int gate) {
+  const BatchInst& I = B[blockIdx.z];
+  if (gate && !b_active(I)) return;
+  density_sk_cta<KB, KX, RB>(reinterpret_cast<const uint4*>(I.bits), I.N, I.Ws / 4, I.K, G, reinterpret_cast<const uint4*>(I.P.m1),
+                             reinterpret_cast<const uint4*>(I.P.valid), I.P.L, I.P.B, I.P.has_half, I.logf, 1);
+}
+
+template <int KB>
+__global__ void __launch_bounds__(256) k_b_density_skd(const BatchInst* __restrict__ B, int G, int gate) {
+  const BatchInst& I = B[blockIdx.z];
+  if (gate && !b_active(I)) return;
+  density_skd_body<KB>(I.bits, I.N, I.Ws, I.K, G, I.P.m1, I.P.valid, I.Ltab, I.Lword, I.P.B, I.logf);
+}
+
+// s >= 1: the sweep of EM iteration s (reads the posteriors of iteration s - 1); s == 0 / -1: the two start sweeps of
+// nem_alg.c:2043-2054 (blind beta = 0 from the zero posteriors in T[0] into T[1]; then with beta from T[1] into T[0])
+template <bool COOP, int GS>
+__global__ void __launch_bounds__(COOP ? 1024 : 256) k_b_sweep(const BatchInst* __restrict__ B, int s) {
+  const BatchInst& I = B[blockIdx.z];
+  if (s >= 1 && !b_active(I)) return;
+  int from, to;
+  float beta = I.beta;
+  if (s >= 1) { from = (I.c0 + s - 1) & 1; to = from ^ 1; }
+  else if (s == 0) { from = 0; to = 1; beta = 0.0f; }
+  else { if (I.beta == 0.0f) return; from = 1; to = 0; }
+  SweepArgs a;
+  a.N = I.N; a.K = I.K; a.logf = I.logf; a.pk = I.P.pk; a.logpk64 = I.P.logpk64; a.T_old = I.T[from]; a.T_new = I.T[to];
+  a.rowptr = I.rowptr; a.col = I.col; a.w = I.w; a.beta = beta; a.logspace = I.logspace; a.jacobi = I.jacobi;
+  a.maxdiff_bits = I.state + (s >= 1 ? kStMaxdiff : kStWords - 1);   // the start sweeps are not convergence-tested
+  a.ell_hdr = I.ell_hdr; a.ell_nb = I.ell_nb; a.stamps = nullptr;
+  a.wait_sig = nullptr; a.wait_n = 0; a.wait_epoch = 0; a.wait_err = nullptr;
+  const bool levels = COOP && beta != 0.0f && I.rowptr != nullptr && !I.jacobi && I.n_levels > 1;
+  a.level_ptr = levels ? I.level_ptr : nullptr; a.level_rows = levels ? I.level_rows : nullptr; a.n_levels = levels ? I.n_levels : 1;
+  InstBar bar{I.barrier, gridDim.x};
+  sweep_body<COOP, GS>(a, bar);
+}
+
+// nem_alg.c:1868-1892 on the device, after the sweep of iteration s: convergence / failure / iteration cap per instance,
+// the statistics of the next M-step cleared, and "is any instance of the group still running" for the host
+__global__ void __launch_bounds__(256) k_b_poll(const BatchInst* __restrict__ B, int s, volatile int* any_active /*[1] mapped host word*/,
+                                                int* __restrict__ group_active /*[1] device scratch*/) {
+  const BatchInst& I = B[blockIdx.z];
+  const bool was = b_active(I);
+  if (was) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    for (long long t = tid; t < I.zero_bytes / 4; t += nth) reinterpret_cast<int*>(I.zero_from)[t] = 0;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *I.P.has_half = 0;
+  }
+  __syncthreads();
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int still = 0;
+  if (was) {
+    const float maxdif = __uint_as_float(I.state[kStMaxdiff]);
+    const int status = (int)I.state[kStStatus];
+    I.state[kStIter] = (unsigned)s;
+    still = 1;
+    if (status != 0) still = 0;                                       // empty class: the reference stops (nem_alg.c:1873-1892)
+    else {
+      const int conv = maxdif < I.cv_th;                              // nem_alg.c:2160-2173
+      I.state[kStConverged] = (unsigned)conv;
+      if (conv || s >= I.itermax) still = 0;
+    }
+    I.state[kStMaxdiff] = 0u;
+    *I.barrier = 0u;
+    if (!still) I.state[kStActive] = 0u;
+  }
+  // last instance to report publishes the group's flag (the ticket counter is the scratch word's high half)
+  __threadfence();
+  const int n = (int)gridDim.z;
+  const int prevv = atomicAdd(group_active, (still ? 1 : 0) + (1 << 16));
+  if ((prevv >> 16) == n - 1) {
+    const int total = (prevv & 0xffff) + (still ? 1 : 0);
+    *group_active = 0;
+    __threadfence_system();
+    *any_active = total;
+    __threadfence_system();
+  }
+}
+
+// results of all instances of a group in one launch: final posteriors, parameters, and the scalar outcome
+// (out_scalars[inst] = {n_iter, converged, status, c_final})
+__global__ void __launch_bounds__(256) k_b_collect(const BatchInst* __restrict__ B, int* __restrict__ out_scalars /*[n][4]*/) {
+  const BatchInst& I = B[blockIdx.z];
+  const int n_iter = (int)I.state[kStIter], status = (int)I.state[kStStatus];
+  // a failed iteration does not replace the posteriors (nem_alg.c:1873-1892)
+  const int cfin = (I.c0 + n_iter - (status != 0 ? 1 : 0)) & 1;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (tid == 0) {
+    out_scalars[blockIdx.z * 4 + 0] = n_iter; out_scalars[blockIdx.z * 4 + 1] = (int)I.state[kStConverged];
+    out_scalars[blockIdx.z * 4 + 2] = status; out_scalars[blockIdx.z * 4 + 3] = cfin;
+  }
+  if (I.T_out != nullptr) {
+    const float* src = I.T[cfin];
+    const long long n = I.N * I.K;
+    for (long long t = tid; t < n; t += nth) I.T_out[t] = src[t];
+  }
+  const long long kd = (long long)I.K * I.D;
+  if (I.mu_out != nullptr) for (long long t = tid; t < kd; t += nth) I.mu_out[t] = I.P.mu[t];
+  if (I.eps_out != nullptr)
+    for (long long t = tid; t < kd; t += nth) I.eps_out[t] = I.free_disp ? I.P.eps[t] : I.P.eps_k[t / I.D];
+  if (I.pk_out != nullptr && tid < I.K) I.pk_out[tid] = I.P.pk[tid];
 }
 
 }  // namespace nemb200

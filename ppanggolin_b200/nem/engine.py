@@ -24,6 +24,7 @@ JACOBI = 2
 FULL_RECOUNT = 4
 PEER_EXCHANGE = 8
 MAX_K = 32
+MAX_PEERS = 8          # kMaxPeers of the peer-memory exchange (one NVSwitch box)
 
 STS_OK, STS_EMPTYCLASS, STS_INFINITE = 0, 1, 2
 

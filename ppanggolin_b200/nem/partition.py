@@ -112,13 +112,25 @@ def _run_sharded(inp, kval: int, beta: float, free_dispersion: bool, itermax: in
     beta32 = float(np.float32(beta))
     lo, hi = shard_rows(N, world, rank)
     graph = dev_in if beta32 != 0.0 else None
-    be = CudaBackend(dev_in.bits[lo:hi], inp.D, N, kval, free_dispersion, flags, graph, peer_group=dist.group.WORLD, row_offset=lo)
+    # the peer-memory exchange maps the other ranks' buffers through CUDA IPC: one host, at most engine.MAX_PEERS ranks;
+    # anything else exchanges through the NCCL collectives of ShardedEM (agreed on by all ranks: hostnames are gathered)
+    import socket
+    hosts = [None] * world
+    dist.all_gather_object(hosts, socket.gethostname())
+    peer_ok = world <= engine.MAX_PEERS and len(set(hosts)) == 1
+    be = CudaBackend(dev_in.bits[lo:hi], inp.D, N, kval, free_dispersion, flags, graph,
+                     peer_group=dist.group.WORLD if peer_ok else None, row_offset=lo)
     out = ShardedEM(be, N, kval, rank, world, dist.group.WORLD).run(beta32, itermax, 0.01)
     mu, eps, pk, _ = be.plan.get_params()
     run = engine.NemRun(out.T, mu, eps, pk, list(out.crit), out.n_iter, out.converged, out.status,
                         dev_in.n_levels if graph is not None else 1, 0.0)
     be.plan.close()
     return run
+
+
+def _f32(x: float) -> float:
+    """CriterT.M is a C float in the reference (nem_typ.h); the log-space epilogue sums it in fp64."""
+    return float(np.float32(x))
 
 
 def _g(x: float, spec: str) -> float:
@@ -168,7 +180,7 @@ def run_partitioning(
         logger.debug(f"NEM status={run.status} kval={kval} nb_org={nb_org} beta={beta} itermax={itermax}")
         return {}, None, None
 
-    log_likelihood = _g(run.crit[3], "%g")           # partition.py:187 reads criterion M from "%g" text
+    log_likelihood = _g(_f32(run.crit[3]), "%g")     # partition.py:187 reads criterion M (a C float) from "%g" text
     labels, entropy = engine.labels_device(run.T)    # partition.py:206-231 on " %5.3f " text
     if just_log_likelihood:
         return kval, log_likelihood, entropy
@@ -293,6 +305,10 @@ def evaluate_nb_partitions(
     # the K candidates are independent NEM instances over the same matrix (beta 0, 10 iterations, partition.py:482-496):
     # one batched call instead of the reference's fork pool; under torch.distributed the candidates are split over ranks
     ks = list(range(krange[0] - 1, krange[1] + 1))
+    if ks and ks[-1] > engine.MAX_K:
+        logging.getLogger("PPanGGOLiN").warning(f"K candidates above {engine.MAX_K} are not supported by the B200 path "
+                                                f"(NEMB200_MAX_K) and are skipped.")
+        ks = [k for k in ks if k <= engine.MAX_K]
     all_log_likelihood = run_k_candidates(newtmpdir, len(select_organisms), ks, free_dispersion)
     chosen_k, all_bics, all_icls, all_lls = select_k(all_log_likelihood, len(select_organisms), nb_fam,
                                                      free_dispersion, icl_margin)
@@ -322,7 +338,7 @@ def run_k_candidates(nem_dir_path: Path, nb_org: int, ks: List[int], free_disper
             results.append(({}, None, None))
             continue
         _, entropy = engine.labels_device(run.T)
-        results.append((k, _g(run.crit[3], "%g"), entropy))
+        results.append((k, _g(_f32(run.crit[3]), "%g"), entropy))
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, results)

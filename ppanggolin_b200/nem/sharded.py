@@ -184,4 +184,6 @@ class ShardedEM:
             md, status = self.iterate(beta)
             converged = md < cv_th
         crit = self.b.criteria(self.b.T[self.cur], beta) if status == 0 else [float("nan")] * 5
+        if status == 0 and crit[0] == float("-inf"):
+            status = 2   # NEMB200_STS_INFINITE: the reference returns STS_E_INFINITE and writes no .uf (nem_alg.c:2482-2487)
         return EmOutcome(self.b.T[self.cur], crit, it, converged, status)

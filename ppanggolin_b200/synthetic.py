@@ -203,3 +203,24 @@ def synth_pangenome_large(N: int, D: int, seed: int = 42, device="cuda", rows=No
         del x, words
     rowptr, col, w, ew = backbone_graph(N, p, rng)
     return SynthPangenome(None, bits, rowptr, col, w, ew, cls, N, D)
+
+
+def synth_pangenome_blocked(N: int, D: int, seed: int = 42, block: int = 1024, keep_X: bool = False) -> SynthPangenome:
+    """CPU generator for wide matrices (numpy only, so the same seed gives the same instance wherever it runs): the matrix
+    is drawn in row blocks seeded by their first row, so the float randoms of one block (block x D float32) are all that
+    is ever held; graph from :func:`backbone_graph`.  ``keep_X`` also returns the unpacked uint8 matrix (oracle input)."""
+    rng = np.random.default_rng(seed)
+    cls, p = _family_probs(N, rng)
+    W = row_stride_words(D)
+    bits = np.zeros((N, W), np.uint32)
+    X = np.zeros((N, D), np.uint8) if keep_X else None
+    for r0 in range(0, N, block):
+        r1 = min(N, r0 + block)
+        rb = np.random.default_rng([seed, r0])
+        xb = (rb.random((r1 - r0, D), dtype=np.float32) < p[r0:r1, None].astype(np.float32)).astype(np.uint8)
+        xb[xb.sum(1) == 0, 0] = 1
+        bits[r0:r1] = pack_rows(xb)
+        if keep_X:
+            X[r0:r1] = xb
+    rowptr, col, w, ew = backbone_graph(N, p, rng)
+    return SynthPangenome(X, bits, rowptr, col, w, ew, cls, N, D)

@@ -307,6 +307,41 @@ def partition_cases():
         print(name, Counter(v[0] if v else "?" for v in labels.values()), params)
 
 
+def chunked_replay_cases():
+    """Chunked partition() of the reference with every random.shuffle it performs recorded (genome names in shuffled order),
+    so that a test can feed the SAME chunk samples, in the same rounds, to the GPU path (SURVEY.md section 7,
+    "non-deterministic reference inputs"; partition.py:809-821)."""
+    ref_partition = import_reference_partition()
+    cases = [("chunked_replay", dict(n_fam=3000, n_org=150, seed=25), dict(kval=3, chunk_size=40, beta=2.5, free_dispersion=False)),
+             ("chunked_replay_fd", dict(n_fam=2000, n_org=120, seed=26), dict(kval=3, chunk_size=30, beta=2.5, free_dispersion=True))]
+    for name, g, kw in cases:
+        layouts = make_layouts(**g)
+        pan = build_reference_pangenome(layouts, g["n_fam"])
+        ref_partition.samples = []
+        recorded = []
+        real_shuffle = random.shuffle
+
+        def recording_shuffle(lst, *a):
+            real_shuffle(lst, *a)
+            recorded.append([o.name for o in lst])
+        random.seed(1234)
+        random.shuffle = recording_shuffle
+        try:
+            with tempfile.TemporaryDirectory() as td:
+                ref_partition.partition(pan, output=Path(td), tmpdir=Path(td), cpu=1, disable_bar=True, seed=42, **kw)
+        finally:
+            random.shuffle = real_shuffle
+        labels = {fam.name: fam.partition for fam in pan.gene_families}
+        names = sorted(labels, key=lambda s: int(s[3:]))
+        params = {k: (v if not isinstance(v, (np.floating, np.integer)) else v.item()) for k, v in pan.parameters["partition"].items()}
+        np.savez_compressed(OUT / f"partition_{name}.npz", n_fam=g["n_fam"], layouts=np.concatenate(layouts),
+                            layout_ptr=np.cumsum([0] + [len(l) for l in layouts]), fam_names=np.array(names),
+                            labels=np.array([labels[n] for n in names]), kwargs=json.dumps(kw), params=json.dumps(params),
+                            shuffles=json.dumps(recorded), n_samples=len(ref_partition.samples))
+        from collections import Counter
+        print(name, Counter(v[0] if v else "?" for v in labels.values()), len(recorded), "shuffles", len(ref_partition.samples), "samples")
+
+
 def rarefaction_case():
     """Reference raref_nem (rarefaction.py:36-189) on fixed genome samples of growing size: partition counts per sample."""
     ref_partition = import_reference_partition()
@@ -334,6 +369,10 @@ def rarefaction_case():
 
 if __name__ == "__main__":
     refnem.build()
+    if sys.argv[1:] == ["replay"]:
+        chunked_replay_cases()
+        sys.exit(0)
     nem_cases()
     partition_cases()
+    chunked_replay_cases()
     rarefaction_case()

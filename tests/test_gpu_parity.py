@@ -392,8 +392,7 @@ def test_partition_on_reference_genomes(eng, tmp_path):
     """BASELINE config 1 (surrogate): the reference's Chlamydia trachomatis GenBank genomes, families =
     identical translations, graph by gene order; `partition()` with the defaults of `ppanggolin all` (auto K in 3..20).
     The strict clustering makes the reference choose K = 19 here -- nineteen nearly identical shell classes -- so the
-    test asks for the partition letter (persistent / shell / cloud) of >= 99.9 % of the families and for a chosen K
-    within one of the reference's."""
+    test asks for the partition letter (persistent / shell / cloud) of >= 99.9 % of the families and for the same chosen K."""
     import random
     from collections import Counter
     import minipan
@@ -411,10 +410,8 @@ def test_partition_on_reference_genomes(eng, tmp_path):
     k_ours, k_ref = pan.parameters["partition"]["# final nb of partitions"], g["params"]["# final nb of partitions"]
     print("gbff surrogate: K", k_ours, "vs", k_ref, "letters", letters, "exact labels", exact,
           Counter(v[:1] for v in ours.values()), Counter(v[:1] for v in ref.values()))
-    assert abs(k_ours - k_ref) <= 1
-    assert letters >= 0.999
-    if k_ours == k_ref:
-        assert exact >= 0.999
+    assert k_ours == k_ref                  # north star: the same chosen K
+    assert letters >= 0.999 and exact >= 0.999
 
 
 def test_rarefaction_caller_matches_reference(eng, tmp_path):
