@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NEMB200_ABI_VERSION 1
+#define NEMB200_ABI_VERSION 2
 #define NEMB200_MAX_K 32
 
 enum { NEMB200_OK = 0, NEMB200_ERR_ARG = -1, NEMB200_ERR_CUDA = -2, NEMB200_ERR_NOMEM = -3 };
@@ -61,7 +61,9 @@ typedef struct nemb200_result {
   int32_t converged;
   int32_t status;     /* NEMB200_STS_* */
   int32_t n_levels;   /* depth of the Gauss-Seidel level schedule that was used */
-  float   elapsed_ms; /* device time of the EM loop (CUDA events), excluding copies */
+  float   elapsed_ms; /* device time of the run (CUDA events): start phase, EM iterations and criteria, excluding copies;
+                         for an instance of a batch: of its whole group */
+  float   em_ms;      /* of which: from the start phase to the end of the last EM iteration (no criteria) */
 } nemb200_result;
 
 int         nemb200_abi_version(void);
@@ -179,6 +181,9 @@ int nemb200_plan_graph_changed(nemb200_plan* plan);
  * implementation on caller-supplied terms (host arrays of n floats each) so that tests can compare them on adversarial
  * inputs: out2[0] = sum of d, out2[1] = sum of g, each accumulated in float32 from 0 in index order. */
 int nemb200_selftest_float_chain(const float* d, const float* g, int64_t n, int32_t parallel, double out2[2]);
+/* The criteria L and Z (nem_alg.c:2826-2827) are float32 accumulators that receive DOUBLE terms, acc = (float)((double)acc
+ * + x): the same two implementations for that kind of chain, on caller-supplied double terms. */
+int nemb200_selftest_double_chain(const double* l, const double* z, int64_t n, int32_t parallel, double out2[2]);
 
 /* nem_alg.c:2160-2173 (HasConverged, CVTEST_CLAS) needs max |T_new - T_old|; nem_alg.c:1873-1892 needs the empty-class
  * status.  Both in one 8-byte device->host read (synchronises the stream). */
@@ -195,6 +200,65 @@ int nemb200_get_params(nemb200_plan* plan, float* mu, float* eps, float* pk, int
 /* partition.py:206-231 on the "%5.3f" text of nem_exe.c:1682, on the device: labels[i] = class 0..K-1, or -1 for "S_"
  * (tie or max < 0.5); *entropy = sum p ln p over the 3-decimal posteriors (partition.py:212-220).  T: device. */
 int nemb200_labels(const float* T, int64_t N, int32_t K, int32_t* labels_dev, double* entropy_host, void* stream);
+
+/* ---- exporter: NEM instances derived on the device from the array form of a pangenome ---------------------------------
+ * Replaces write_nem_input_files (ppanggolin/nem/partition.py:344-436), which walks the Python objects again for every
+ * genome subset (the whole pangenome, the K-selection sample, every chunk of partition.py:809-821) and writes text.
+ * The pangenome is described ONCE by arrays in device memory; a call derives the instances of a batch of genome subsets:
+ * matrix rows of the families present in the subset (:381-391), neighbour lists weighted round(gene pairs in the subset /
+ * #genomes, 4) (:393-414) with the max-degree cut (:415-433) exactly as the C reader keeps them (NEM/nem_exe.c:1395-1451),
+ * sum of kept weights / 2 (:416,:436), and the Gauss-Seidel level schedule (nemb200_gs_schedule) -- without a host round
+ * trip of the arrays. */
+typedef struct nemb200_pangenome {
+  int64_t F, G, E, A;           /* families, genomes, edges, adjacency entries */
+  int64_t Wg;                   /* words per presence row, >= ceil(G / 32) */
+  const uint32_t* presence;     /* [F][Wg] bit g of row f: family f has a gene in genome g (geneFamily.py:296) */
+  const int32_t*  adj_ptr;      /* [F+1] adjacency rows, entries in fam.edges order (geneFamily.py:272) */
+  const int32_t*  adj_other;    /* [A]   the other family of the edge */
+  const int32_t*  adj_edge;     /* [A]   edge id */
+  const int32_t*  cov_ptr;      /* [E+1] gene pairs per (edge, genome) as CSR over edges (edge.py:75 get_organisms_dict), or NULL: */
+  const int32_t*  cov_org;      /* [M]   genome                                                                                   */
+  const int32_t*  cov_cnt;      /* [M]   number of gene pairs                                                                     */
+  const int32_t*  edge_fam;     /* [E][2] with cov_ptr == NULL: one gene pair in genome g iff both families are present in g
+                                   (synthetic pangenomes at scales where the explicit table does not fit)                        */
+} nemb200_pangenome;
+
+typedef struct nemb200_sample {
+  const int32_t* sel;           /* in  (device) genome columns of the subset, ascending: column j of the instance;
+                                   NULL = all genomes in order (then n_sel = G and row_stride_words = Wg)          */
+  int32_t  n_sel;
+  int64_t  row_stride_words;    /* in: words per instance row, multiple of 4 */
+  uint32_t* bits;               /* out (device, capacity F rows): matrix of the instance */
+  int32_t* fam_rows;            /* out (device, F): family index of every instance row */
+  int32_t* rowptr;              /* out (device, F + 1) */
+  int32_t* col;                 /* out (device, A) */
+  float*   w;                   /* out (device, A) */
+  int32_t* level_ptr;           /* out (device, F + 1): level schedule, may be NULL with want_levels == 0 */
+  int32_t* level_rows;          /* out (device, F) */
+  int64_t  N, nnz;              /* out (host): rows and neighbour entries of the instance */
+  int32_t  n_levels;
+  double   edges_weight;        /* out (host): partition.py:436, the caller scales beta with it (:324, :872) */
+} nemb200_sample;
+
+/* weight_lut (device, lut_len floats): lut[c] = (float) round(c / n_sel, 4) as Python computes it (partition.py:413), for
+ * every pair count c that can occur; all samples of a call share n_sel.  Synchronises `stream`. */
+int nemb200_export_samples(const nemb200_pangenome* pan, int32_t n_samples, nemb200_sample* samples, float sm_degree,
+                           const float* weight_lut, int32_t lut_len, int32_t want_levels, void* stream);
+
+/* validate_family (partition.py:784-802) on the device, in two steps.  nemb200_chunk_codes, per finished chunk: the label
+ * rule of partition.py:206-231 on the posteriors T (N x K) reduced to the letter that is voted with (0 = P, 1 = S, 2 = C),
+ * scattered into codes[F] (int8, filled with -1 by the caller: family not in the chunk).  nemb200_apply_votes, per round:
+ * every family applies the votes of the round's chunks in sample order (codes[n_chunks][F]) to votes[F][4] (P, S, C, U);
+ * families that become validated are marked in validated[F] and counted in *n_validated (device int).
+ * ratio = n_org / chunk_size. */
+int nemb200_chunk_codes(const float* T, int64_t N, int32_t K, const int32_t* fam_rows, int8_t* codes, void* stream);
+int nemb200_apply_votes(const int8_t* codes, int32_t n_chunks, int64_t F, int32_t* votes, uint8_t* validated,
+                        int32_t* n_validated, double ratio, int32_t n_org, void* stream);
+
+/* rarefaction.py:657-684 (core / soft-core counts of a genome sample, gmpy2 bitarrays there): counts[f] = number of the
+ * selected genomes that hold family f.  mask_scratch: Wg words (device). */
+int nemb200_subset_counts(const nemb200_pangenome* pan, const int32_t* sel, int32_t n_sel, uint32_t* mask_scratch,
+                          int32_t* counts, void* stream);
 
 #ifdef __cplusplus
 }

@@ -183,9 +183,14 @@ struct nemb200_plan {
   int* crit_counts = nullptr;     // [crit_blocks * 8] terms per region
   int* crit_offsets = nullptr;    // [crit_blocks * 8 + 1]
   float* crit_dense = nullptr;    // the regions' terms, contiguous and in order
-  long long* crit_rec = nullptr;  // k_crit_chain_par: per (chunk, chain) records, 3 x int64 + flag
+  double* crit_lz = nullptr;      // [N_total][2] per-row (log f_i, -log z_i): terms of the float32 L and Z sums
+  int* crit_nrows = nullptr;      // [1] number of rows of the last criteria call (term count of the L / Z chains)
+  long long* crit_rec = nullptr;  // k_crit_chain_par, D / G chains: per (chunk, chain) records, 3 x int64 + flag
   int* crit_recbad = nullptr;
   CcState* crit_state = nullptr;
+  long long* crit_rec_lz = nullptr;   // the same for the L / Z chains (their CTA runs beside the D / G one)
+  int* crit_recbad_lz = nullptr;
+  CcState* crit_state_lz = nullptr;
   // run buffers of the whole-run drivers (nem_host / nem_device / batch); not used by the stepwise interface
   bool stepwise_used = false;     // work was enqueued through the stepwise entry points on a stream this library does not own
   bool with_run_buffers = false;
@@ -227,9 +232,13 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   pl->crit_counts = ar.take<int>((size_t)pl->crit_blocks * 8);
   pl->crit_offsets = ar.take<int>((size_t)pl->crit_blocks * 8 + 1);
   pl->crit_dense = ar.take<float>(((size_t)pl->N_total * K + 64) * 2);
+  pl->crit_lz = ar.take<double>(((size_t)pl->N_total + 64) * 2);
+  pl->crit_nrows = ar.take<int>(1);
   {
     const size_t nch = ((size_t)pl->N_total * K + kCcChunk - 1) / kCcChunk + 1;
     pl->crit_rec = ar.take<long long>(nch * 2 * 3); pl->crit_recbad = ar.take<int>(nch * 2); pl->crit_state = ar.take<CcState>(1);
+    const size_t nch_lz = ((size_t)pl->N_total + kCcChunk - 1) / kCcChunk + 1;
+    pl->crit_rec_lz = ar.take<long long>(nch_lz * 2 * 3); pl->crit_recbad_lz = ar.take<int>(nch_lz * 2); pl->crit_state_lz = ar.take<CcState>(1);
   }
   if (pl->with_run_buffers) {
     pl->run_logf = ar.take<double>(N * K); pl->run_Ta = ar.take<float>(N * K); pl->run_Tb = ar.take<float>(N * K);
@@ -852,6 +861,18 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
   return NEMB200_OK;
 }
 
+// the two chain jobs of a plan's criteria: D / G over the compacted float terms, L / Z over the per-row double terms
+static void chain_jobs(nemb200_plan* pl, int64_t N, int n_regions, const unsigned* run_state, CcJob* dg, CcJob* lz) {
+  const size_t nch = ((size_t)N * pl->K + kCcChunk - 1) / kCcChunk + 1;
+  const size_t nch_lz = ((size_t)N + kCcChunk - 1) / kCcChunk + 1;
+  dg->terms = pl->crit_dense; dg->total_ptr = pl->crit_offsets + n_regions;
+  dg->recR = pl->crit_rec; dg->recMn = pl->crit_rec + nch * 2; dg->recMx = pl->crit_rec + nch * 4; dg->recFlag = pl->crit_recbad;
+  dg->state = pl->crit_state; dg->out2 = pl->crit4; dg->run_state = run_state;
+  lz->terms = pl->crit_lz; lz->total_ptr = pl->crit_nrows;
+  lz->recR = pl->crit_rec_lz; lz->recMn = pl->crit_rec_lz + nch_lz * 2; lz->recMx = pl->crit_rec_lz + nch_lz * 4; lz->recFlag = pl->crit_recbad_lz;
+  lz->state = pl->crit_state_lz; lz->out2 = pl->crit4 + 2; lz->run_state = run_state;
+}
+
 static int criteria_enqueue(nemb200_plan* pl, int64_t N, const double* logf, const float* T, const int32_t* rowptr,
                             const int32_t* col, const float* w, float beta, cudaStream_t st) {
   CritArgs a;
@@ -863,6 +884,7 @@ static int criteria_enqueue(nemb200_plan* pl, int64_t N, const double* logf, con
   a.rows_per_warp = (N + n_warps - 1) / n_warps;
   a.terms = a.logspace ? nullptr : (float2*)pl->crit_terms;
   a.counts = a.logspace ? nullptr : pl->crit_counts;
+  a.row_lz = a.logspace ? nullptr : (double2*)pl->crit_lz;
   const int GS = pl->K <= 4 ? 4 : (pl->K <= 8 ? 8 : (pl->K <= 16 ? 16 : 32));
   if (GS == 4) k_criteria<4><<<pl->crit_blocks, 256, 0, st>>>(a);
   else if (GS == 8) k_criteria<8><<<pl->crit_blocks, 256, 0, st>>>(a);
@@ -873,40 +895,32 @@ static int criteria_enqueue(nemb200_plan* pl, int64_t N, const double* logf, con
     k_crit_reduce<<<1, 128, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4, 0);
     CK(cudaGetLastError());
   } else {
-    k_crit_reduce<<<1, 128, 0, st>>>(pl->crit_partial, pl->crit_blocks, pl->crit4, 2);       // L, Z: fp64 sums
-    CK(cudaGetLastError());
-    k_crit_offsets<<<1, 32, 0, st>>>(pl->crit_counts, n_warps, pl->crit_offsets);
+    k_crit_offsets<<<1, 32, 0, st>>>(pl->crit_counts, n_warps, pl->crit_offsets, pl->crit_nrows, (int)N);
     CK(cudaGetLastError());
     k_crit_compact<<<(n_warps + 7) / 8, 256, 0, st>>>((const float2*)pl->crit_terms, pl->crit_counts, pl->crit_offsets, n_warps,
                                                     a.rows_per_warp, pl->K, (float2*)pl->crit_dense);
     CK(cudaGetLastError());
-    // D, G: float32 sums in the reference's order -- sequential chain for small instances, the exact parallel scheme above it
-    const size_t nch = ((size_t)N * pl->K + kCcChunk - 1) / kCcChunk + 1;
+    // all four sums are float32 accumulators walked in the reference's order (nem_alg.c:2813-2827): D, G over the compacted
+    // non-zero (d_ik, g_ik) terms, L, Z over the per-row double terms -- a sequential chain for small instances, the exact
+    // parallel scheme above it
     const char* force = getenv("NEMB200_CRIT_SEQ");
-    if (force ? atoi(force) != 0 : (size_t)N * pl->K < 32768) {
-      k_crit_chain<<<1, 64, 0, st>>>((const float2*)pl->crit_dense, pl->crit_offsets, n_warps, pl->crit4);
-      CK(cudaGetLastError());
+    CcJob dg, lz;
+    chain_jobs(pl, N, n_warps, nullptr, &dg, &lz);
+    if (force ? atoi(force) != 0 : (size_t)N * pl->K < 8192) {
+      k_crit_chain<TermsF2><<<1, 64, 0, st>>>(TermsF2{(const float2*)dg.terms}, dg.total_ptr, dg.out2);
+      k_crit_chain<TermsD2><<<1, 64, 0, st>>>(TermsD2{(const double2*)lz.terms}, lz.total_ptr, lz.out2);
     } else {
-      const float2* dense = (const float2*)pl->crit_dense;
-      const int* offs = pl->crit_offsets;
-      int nreg = n_warps;
-      long long *rR = pl->crit_rec, *rMn = pl->crit_rec + nch * 2, *rMx = pl->crit_rec + nch * 4;
-      int* rBad = pl->crit_recbad;
-      CcState* stp = pl->crit_state;
-      double* out = pl->crit4;
-      void* args[] = {&dense, &offs, &nreg, &rR, &rMn, &rMx, &rBad, &stp, &out};
-      const int blocks = (int)std::min<size_t>(std::max<size_t>(nch / 8, 1), (size_t)32);   // few CTAs: cheap barriers, batched instances side by side
-      CK(cudaLaunchCooperativeKernel((void*)k_crit_chain_par, dim3(blocks), dim3(256), args, 0, st));
+      k_crit_chain_par<TermsF2><<<1, 1024, 0, st>>>(nullptr, dg);
+      k_crit_chain_par<TermsD2><<<1, 1024, 0, st>>>(nullptr, lz);
     }
+    CK(cudaGetLastError());
   }
   return 0;
 }
 
-static int criteria_collect(nemb200_plan* pl, float beta, double crit_out[5], cudaStream_t st) {
-  double h[4];
-  CK(cudaMemcpyAsync(h, pl->crit4, sizeof h, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (pl->flags & NEMB200_EPI_LOGSPACE) {
+// the four sums -> U, D, L, M, Z with the reference's expression types (nem_alg.c:2834-2835)
+static void crit_combine(const double h[4], float beta, bool logspace, double crit_out[5]) {
+  if (logspace) {
     const double cD = h[0], cG = h[1], cL = h[2], cZ = h[3];
     crit_out[0] = cD + 0.5 * (double)beta * cG;  // U  (nem_alg.c:2834)
     crit_out[1] = cD;
@@ -914,7 +928,6 @@ static int criteria_collect(nemb200_plan* pl, float beta, double crit_out[5], cu
     crit_out[3] = cD + (double)beta * cG + cZ;    // M  (nem_alg.c:2835)
     crit_out[4] = cZ;
   } else {
-    // float32 fields combined with the reference's expression types (nem_alg.c:2834-2835)
     const float cD = (float)h[0], cG = (float)h[1], cL = (float)h[2], cZ = (float)h[3];
     const float cU = (float)((double)cD + 0.5 * (double)beta * (double)cG);
     volatile float t1 = beta * cG;
@@ -922,6 +935,13 @@ static int criteria_collect(nemb200_plan* pl, float beta, double crit_out[5], cu
     const float cM = t2 + cZ;
     crit_out[0] = cU; crit_out[1] = cD; crit_out[2] = cL; crit_out[3] = cM; crit_out[4] = cZ;
   }
+}
+
+static int criteria_collect(nemb200_plan* pl, float beta, double crit_out[5], cudaStream_t st) {
+  double h[4];
+  CK(cudaMemcpyAsync(h, pl->crit4, sizeof h, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  crit_combine(h, beta, (pl->flags & NEMB200_EPI_LOGSPACE) != 0, crit_out);
   return NEMB200_OK;
 }
 
@@ -954,19 +974,16 @@ extern "C" int nemb200_selftest_float_chain(const float* d, const float* g, int6
   cudaError_t e = cudaMemcpy(p_dense, h.data(), b_dense, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(offs, hoffs, sizeof hoffs, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    const float2* dense = (const float2*)p_dense;
-    const int* co = offs;
-    int nreg = 1;
+    TermsF2 dense{(const float2*)p_dense};
+    const int* tot = offs + 1;
     if (parallel) {
-      long long *rR = (long long*)p_rec, *rMn = rR + nch * 2, *rMx = rR + nch * 4;
-      int* rBad = (int*)p_bad;
-      void* args[] = {&dense, &co, &nreg, &rR, &rMn, &rMx, &rBad, &stp, &out};
-      const int blocks = (int)std::min<size_t>(std::max<size_t>(nch / 8, 1), (size_t)32);
-      e = cudaLaunchCooperativeKernel((void*)k_crit_chain_par, dim3(blocks), dim3(256), args, 0, nullptr);
+      long long *rR = (long long*)p_rec;
+      CcJob job{p_dense, tot, rR, rR + nch * 2, rR + nch * 4, (int*)p_bad, stp, out, nullptr};
+      k_crit_chain_par<TermsF2><<<1, 1024>>>(nullptr, job);
     } else {
-      k_crit_chain<<<1, 64>>>(dense, co, nreg, out);
-      e = cudaGetLastError();
+      k_crit_chain<TermsF2><<<1, 64>>>(dense, tot, out);
     }
+    e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(out2, out, 2 * sizeof(double), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && parallel && getenv("NEMB200_CHAIN_DEBUG")) {
@@ -977,6 +994,44 @@ extern "C" int nemb200_selftest_float_chain(const float* d, const float* g, int6
   }
   release();
   if (e != cudaSuccess) return fail(NEMB200_ERR_CUDA, "selftest_float_chain: %s", cudaGetErrorString(e));
+  return NEMB200_OK;
+}
+
+/* the same for the L / Z kind of chain: double terms added to a float accumulator, acc = (float)((double)acc + x) */
+extern "C" int nemb200_selftest_double_chain(const double* l, const double* z, int64_t n, int32_t parallel, double out2[2]) {
+  if (!l || !z || n < 0 || n > 0x7fffffffLL || !out2) return fail(NEMB200_ERR_ARG, "selftest_double_chain: bad argument");
+  std::vector<double2> h((size_t)std::max<int64_t>(n, 1));
+  for (int64_t i = 0; i < n; i++) h[(size_t)i] = make_double2(l[i], z[i]);
+  const size_t nch = ((size_t)n + kCcChunk - 1) / kCcChunk + 1;
+  const size_t b_dense = h.size() * sizeof(double2), b_rec = nch * 2 * 3 * sizeof(long long), b_bad = nch * 2 * sizeof(int);
+  void *p_dense = nullptr, *p_rec = nullptr, *p_bad = nullptr, *p_misc = nullptr;
+  int rc;
+  if ((rc = cached_malloc(&p_dense, b_dense))) return rc;
+  if ((rc = cached_malloc(&p_rec, b_rec))) { cached_free(p_dense, b_dense); return rc; }
+  if ((rc = cached_malloc(&p_bad, b_bad))) { cached_free(p_dense, b_dense); cached_free(p_rec, b_rec); return rc; }
+  if ((rc = cached_malloc(&p_misc, 256))) { cached_free(p_dense, b_dense); cached_free(p_rec, b_rec); cached_free(p_bad, b_bad); return rc; }
+  auto release = [&]() { cached_free(p_dense, b_dense); cached_free(p_rec, b_rec); cached_free(p_bad, b_bad); cached_free(p_misc, 256); };
+  int* tot = (int*)p_misc;
+  CcState* stp = (CcState*)((char*)p_misc + 64);
+  double* out = (double*)((char*)p_misc + 128);
+  const int hn = (int)n;
+  cudaError_t e = cudaMemcpy(p_dense, h.data(), b_dense, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(tot, &hn, sizeof hn, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    TermsD2 dense{(const double2*)p_dense};
+    const int* totp = tot;
+    if (parallel) {
+      long long *rR = (long long*)p_rec;
+      CcJob job{p_dense, totp, rR, rR + nch * 2, rR + nch * 4, (int*)p_bad, stp, out, nullptr};
+      k_crit_chain_par<TermsD2><<<1, 1024>>>(nullptr, job);
+    } else {
+      k_crit_chain<TermsD2><<<1, 64>>>(dense, totp, out);
+    }
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out2, out, 2 * sizeof(double), cudaMemcpyDeviceToHost);
+  release();
+  if (e != cudaSuccess) return fail(NEMB200_ERR_CUDA, "selftest_double_chain: %s", cudaGetErrorString(e));
   return NEMB200_OK;
 }
 
@@ -1151,6 +1206,7 @@ struct EmRun {
     if (res) {
       for (int q = 0; q < 5; q++) res->crit[q] = crit[q];
       res->n_iter = iter; res->converged = converged; res->status = status; res->n_levels = n_levels; res->elapsed_ms = ms;
+      res->em_ms = ms;
     }
     return NEMB200_OK;
   }
@@ -1197,7 +1253,7 @@ extern "C" int nemb200_nem_device(const uint32_t* bits, int64_t N, int64_t D, in
   if (beta != 0.0f && (!rowptr || !col || !w)) return fail(NEMB200_ERR_ARG, "nem_device: beta != 0 needs the neighbour graph");
   if (K < 1 || K > NEMB200_MAX_K || row_stride_words % 4 != 0 || row_stride_words * 32 < D || D < 1)
     return fail(NEMB200_ERR_ARG, "nem_device: bad shape D=%lld stride=%lld K=%d", (long long)D, (long long)row_stride_words, K);
-  if (batch_eligible(N, row_stride_words, K)) {   // small instance: the device-resident loop (a batch of one)
+  if (batch_enabled()) {   // the device-resident loop (a batch of one)
     nemb200_result tmp;
     const std::vector<int> one{0};
     return batch_run(one, &bits, &N, &D, &row_stride_words, &rowptr, &col, &w, &sched_level_ptr, &sched_rows, &n_levels, &K, &beta,
@@ -1226,8 +1282,8 @@ extern "C" int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* b
                                         float* const* pk_out, nemb200_result* results) {
   if (n_inst < 1 || !bits || !N || !D || !row_stride_words || !K || !beta || !free_disp || !itermax || !results)
     return fail(NEMB200_ERR_ARG, "nem_device_batch: null argument");
-  // small instances (every K candidate, every chunk sample): grouped, one launch per EM phase and group, convergence on
-  // the device; the others (matrices that want the streaming kernels) keep one stream each below
+  // grouped by kernel shape, one launch per EM phase and group, convergence on the device (nemb200_batch.inc); the
+  // host-polled driver below only runs with NEMB200_NO_BATCH=1 (cross-check in the tests)
   std::vector<int> small;
   std::vector<char> is_small(n_inst, 0);
   for (int i = 0; i < n_inst; i++) {
@@ -1236,7 +1292,7 @@ extern "C" int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* b
       return fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d needs its neighbour graph", i);
     if (K[i] < 1 || K[i] > NEMB200_MAX_K || row_stride_words[i] % 4 != 0 || row_stride_words[i] * 32 < D[i] || D[i] < 1)
       return fail(NEMB200_ERR_ARG, "nem_device_batch: instance %d has a bad shape", i);
-    if (batch_eligible(N[i], row_stride_words[i], K[i])) { small.push_back(i); is_small[i] = 1; }
+    if (batch_enabled()) { small.push_back(i); is_small[i] = 1; }
   }
   if (!small.empty()) {
     const int brc = batch_run(small, bits, N, D, row_stride_words, rowptr, col, w, sched_level_ptr, sched_rows, n_levels, K, beta,
@@ -1337,7 +1393,7 @@ extern "C" int nemb200_nem_host(const uint32_t* bits, int64_t N, int64_t D, int6
     CK(cudaStreamSynchronize(st));  // lp / lr are locals
   }
   if ((rc = dmal((void**)&d_T, (size_t)N * K * sizeof(float)))) return rc;
-  if (K >= 1 && K <= NEMB200_MAX_K && row_stride_words % 4 == 0 && batch_eligible(N, row_stride_words, K)) {
+  if (K >= 1 && K <= NEMB200_MAX_K && row_stride_words % 4 == 0 && batch_enabled()) {
     float *d_mu = nullptr, *d_eps = nullptr, *d_pk = nullptr;
     const size_t kd = (size_t)K * D * sizeof(float);
     if (mu_out && (rc = dmal((void**)&d_mu, kd))) return rc;
@@ -1371,4 +1427,5 @@ extern "C" int nemb200_nem_host(const uint32_t* bits, int64_t N, int64_t D, int6
   return rc;
 }
 
+#include "nemb200_export.inc"
 #include "nem_shim.inc"

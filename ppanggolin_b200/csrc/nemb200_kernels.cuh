@@ -24,6 +24,8 @@ namespace nemb200 {
 namespace cg = cooperative_groups;
 
 constexpr double kEps = 1e-20;  // NEM/nem_typ.h:65 EPSILON
+// state words of a run (device): convergence word, status (NEMB200_STS_*), and the bookkeeping of the device-resident loop
+enum { kStMaxdiff = 0, kStStatus = 1, kStActive = 2, kStIter = 3, kStConverged = 4, kStWords = 8 };
 constexpr int kFuzzy = -1;
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
@@ -425,10 +427,10 @@ __device__ __forceinline__ void density_sk_ring(const uint4* __restrict__ bits, 
 }
 
 template <int KB, int KX, int RB, int P, int TPB>
-__global__ void __launch_bounds__(TPB, 1)
-k_density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
-                  const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
-                  const int* __restrict__ has_half, double* __restrict__ logf, int Kstride) {
+__device__ __forceinline__ void
+density_sk_ring_cta(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
+                    const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
+                    const int* __restrict__ has_half, double* __restrict__ logf, int Kstride) {
   // K classes starting at the pointers given (a launch may cover a chunk of the model's classes); logf rows hold Kstride
   extern __shared__ uint4 smem4[];
   const bool half = (*has_half != 0);
@@ -443,6 +445,14 @@ k_density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int K, in
   __syncthreads();
   if (half) density_sk_ring<KB, KX, RB, P, TPB, true>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf, Kstride);
   else      density_sk_ring<KB, KX, RB, P, TPB, false>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf, Kstride);
+}
+
+template <int KB, int KX, int RB, int P, int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+k_density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
+                  const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
+                  const int* __restrict__ has_half, double* __restrict__ logf, int Kstride) {
+  density_sk_ring_cta<KB, KX, RB, P, TPB>(bits, N, W4, K, G, m1g, validg, L, B, has_half, logf, Kstride);
 }
 
 // free dispersion ("skd"): per-column log-odds, logf_ik = B_k - sum over mismatching columns d of L_kd.  The sum walks
@@ -1143,9 +1153,9 @@ __host__ __device__ inline size_t onehot_ring_smem() {
   return (size_t)kOhGroups * kOhRows * kOhTpb * 16 + (size_t)kMaxRun * 4;
 }
 
-__global__ void __launch_bounds__(kOhTpb, 1)
-k_mstep_onehot_ring(const uint4* __restrict__ bits4, int W4, int tile_w /*<= kOhTpb*/, int K, const int* __restrict__ offsets,
-                    const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad) {
+__device__ __forceinline__ void
+mstep_onehot_ring_body(const uint4* __restrict__ bits4, int W4, int tile_w /*<= kOhTpb*/, int K, const int* __restrict__ offsets,
+                       const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad) {
   extern __shared__ uint4 smem4[];
   uint4* ring = smem4;                                            // [kOhGroups][kOhRows][kOhTpb]
   int* s_rows = reinterpret_cast<int*>(ring + kOhGroups * kOhRows * kOhTpb);
@@ -1244,6 +1254,12 @@ k_mstep_onehot_ring(const uint4* __restrict__ bits4, int W4, int tile_w /*<= kOh
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(kOhTpb, 1)
+k_mstep_onehot_ring(const uint4* __restrict__ bits4, int W4, int tile_w, int K, const int* __restrict__ offsets,
+                    const int* __restrict__ perm, int* __restrict__ cnt, int Dpad) {
+  mstep_onehot_ring_body(bits4, W4, tile_w, K, offsets, perm, cnt, Dpad);
 }
 
 // Fuzzy rows: fsum[k][d] += T[i][k] for every set bit (i, d) of a fuzzy row.  A thread owns bit `lane` of WPT consecutive
@@ -1604,10 +1620,11 @@ struct CritArgs {
   float2* terms;     // reference arithmetic: per-warp regions of compacted (d_ik, g_ik), region w at w * rows_per_warp * K
   int* counts;       // [total warps] terms in each region
   long long rows_per_warp;
+  double2* row_lz;   // reference arithmetic: per row (log f_i, -log z_i), the terms of the float32 L and Z sums
 };
 
 template <int GS>
-__global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
+__device__ __forceinline__ void criteria_body(const CritArgs& a) {
   __shared__ double s_part[8][4];
   constexpr int RPW = 32 / GS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1686,7 +1703,10 @@ __global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
       rowL = (m > -INFINITY) ? m + log(sum) : -INFINITY;
       rowZ = -log(zi);
     }
-    if (valid && sub == 0) { accD += rowD; accG += rowG; accL += rowL; accZ += rowZ; }
+    if (valid && sub == 0) {
+      accD += rowD; accG += rowG; accL += rowL; accZ += rowZ;
+      if (a.row_lz != nullptr) a.row_lz[i] = make_double2(rowL, rowZ);
+    }
   }
   if (a.counts != nullptr && lane == 0) a.counts[warp_global] = cnt;
   // the group leaders' partial sums -> warp -> block (fixed order)
@@ -1705,9 +1725,14 @@ __global__ void __launch_bounds__(256) k_criteria(CritArgs a) {
   }
 }
 
+template <int GS>
+__global__ void __launch_bounds__(256) k_criteria(CritArgs a) { criteria_body<GS>(a); }
+
 // exclusive prefix sum of the region counts (one warp; a few thousand regions)
-__global__ void __launch_bounds__(32) k_crit_offsets(const int* __restrict__ counts, int n, int* __restrict__ offsets /*[n+1]*/) {
+__device__ __forceinline__ void crit_offsets_body(const int* __restrict__ counts, int n, int* __restrict__ offsets /*[n+1]*/,
+                                                  int* __restrict__ n_rows_out, int n_rows) {
   const int lane = threadIdx.x;
+  if (lane == 0) *n_rows_out = n_rows;
   int carry = 0;
   for (int base = 0; base < n; base += 32) {
     const int v = base + lane < n ? counts[base + lane] : 0;
@@ -1722,10 +1747,15 @@ __global__ void __launch_bounds__(32) k_crit_offsets(const int* __restrict__ cou
   if (lane == 0) offsets[n] = carry;
 }
 
+__global__ void __launch_bounds__(32) k_crit_offsets(const int* __restrict__ counts, int n, int* __restrict__ offsets,
+                                                     int* __restrict__ n_rows_out, int n_rows) {
+  crit_offsets_body(counts, n, offsets, n_rows_out, n_rows);
+}
+
 // regions -> one dense array, order preserved (one warp per region)
-__global__ void __launch_bounds__(256)
-k_crit_compact(const float2* __restrict__ terms, const int* __restrict__ counts, const int* __restrict__ offsets, int n_regions,
-               long long rows_per_warp, int K, float2* __restrict__ dense) {
+__device__ __forceinline__ void
+crit_compact_body(const float2* __restrict__ terms, const int* __restrict__ counts, const int* __restrict__ offsets, int n_regions,
+                  long long rows_per_warp, int K, float2* __restrict__ dense) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_regions) return;
   const int lane = threadIdx.x & 31;
@@ -1733,6 +1763,12 @@ k_crit_compact(const float2* __restrict__ terms, const int* __restrict__ counts,
   const float2* src = terms + (size_t)r * rows_per_warp * K;
   float2* dst = dense + offsets[r];
   for (int t = lane; t < n; t += 32) dst[t] = src[t];
+}
+
+__global__ void __launch_bounds__(256)
+k_crit_compact(const float2* __restrict__ terms, const int* __restrict__ counts, const int* __restrict__ offsets, int n_regions,
+               long long rows_per_warp, int K, float2* __restrict__ dense) {
+  crit_compact_body(terms, counts, offsets, n_regions, rows_per_warp, K, dense);
 }
 
 // ---- the same float32 sequential sums, computed in parallel and still bit-exact ------------------------------------------
@@ -1747,8 +1783,26 @@ k_crit_compact(const float2* __restrict__ terms, const int* __restrict__ counts,
 // or a zero / subnormal state) the chunk is added sequentially, and the following chunks are redone with the new u.
 // Cooperative kernel, rounds separated by grid barriers; in the worst case it degrades to plain sequential adds chunk
 // by chunk, never to a different result (tests compare it bit for bit with k_crit_chain on adversarial inputs).
+// Two kinds of chains.  D and G (nem_alg.c:2813-2823) add FLOAT terms to a float accumulator: fl32(s + x).  L and Z
+// (nem_alg.c:2826-2827: `cL = cL + log(fi)`, `cZ = cZ - log(zi)`) add DOUBLE terms: the sum is formed in double and stored
+// to the float accumulator, fl32(fl64(s + x)) -- at 50 000 rows the drift of that float accumulator is 1.2e-5 of M
+// (measured against the reference on BASELINE configs[2]), so it is reproduced as well.  For double terms the integer
+// shortcut also excludes terms within 2^-26 u of a rounding tie (where the double rounding could matter).
+struct TermsF2 {
+  const float2* p;
+  static constexpr bool kDouble = false;
+  __device__ __forceinline__ void get(int t, double& a, double& b) const { const float2 v = p[t]; a = (double)v.x; b = (double)v.y; }
+  static __device__ __forceinline__ float add(float acc, double x) { return __fadd_rn(acc, (float)x); }
+};
+struct TermsD2 {
+  const double2* p;
+  static constexpr bool kDouble = true;
+  __device__ __forceinline__ void get(int t, double& a, double& b) const { const double2 v = p[t]; a = v.x; b = v.y; }
+  static __device__ __forceinline__ float add(float acc, double x) { return (float)__dadd_rn((double)acc, x); }
+};
+
 constexpr int kCcChunk = 512;
-constexpr int kCcMinTerms = 50000;   // below this many terms the plain chain wins
+constexpr int kCcMinTerms = 8192;    // below this many terms the plain chain wins
 struct CcState { float s[2]; int cur[2]; int rounds; int seq_chunks[2]; };   // per chain (0: D, 1: G): exact running sum, next chunk
 
 __device__ __forceinline__ bool cc_binade(float s, int& E) {   // normal, non-zero, finite
@@ -1757,42 +1811,56 @@ __device__ __forceinline__ bool cc_binade(float s, int& E) {   // normal, non-ze
   return true;
 }
 
-__global__ void __launch_bounds__(256)
-k_crit_chain_par(const float2* __restrict__ dense, const int* __restrict__ offsets, int n_regions,
-                 long long* __restrict__ recR, long long* __restrict__ recMn, long long* __restrict__ recMx,
-                 int* __restrict__ recFlag /*each [nchunks][2]; flag bit 0: needs the sequential path, bit 1: all terms zero*/,
-                 CcState* state, double* __restrict__ out4) {
-  cg::grid_group grid = cg::this_grid();
-  const int total = offsets[n_regions];
+// One CTA (32 warps) per pair of chains: the rounds are separated by block barriers, so a batch of instances (blockIdx.x =
+// job) runs all its chains side by side, and a round costs the window's records (32 chunks per pass of the CTA) plus the walk.
+struct CcJob {
+  const void* terms;            // float2* (D, G: compacted terms) or double2* (L, Z: one pair per row)
+  const int* total_ptr;         // number of terms
+  long long* recR; long long* recMn; long long* recMx;   // [nchunks][2]
+  int* recFlag;                 // [nchunks][2]; bit 0: needs the sequential path, bit 1: all terms zero
+  CcState* state;
+  double* out2;                 // the two sums
+  const unsigned* run_state;    // batched runs: kSt* words of the instance (a failed run is skipped); may be null
+};
+
+template <class Terms>
+__global__ void __launch_bounds__(1024)
+k_crit_chain_par(const CcJob* __restrict__ jobs, CcJob job0) {
+  const CcJob job = jobs != nullptr ? jobs[blockIdx.x] : job0;
+  if (job.run_state != nullptr && job.run_state[kStStatus] != 0u) return;
+  Terms dense{reinterpret_cast<decltype(Terms::p)>(job.terms)};
+  long long* __restrict__ recR = job.recR; long long* __restrict__ recMn = job.recMn; long long* __restrict__ recMx = job.recMx;
+  int* __restrict__ recFlag = job.recFlag;
+  double* out4 = job.out2;
+  const int total = *job.total_ptr;
   const int nchunks = (total + kCcChunk - 1) / kCcChunk;
   const int lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
-  volatile CcState* vs = state;
+  const int warp_global = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  volatile CcState* vs = job.state;
   if (total < kCcMinTerms) {   // short sums: the plain chain is quicker than a dozen rounds (uniform branch: no barrier is skipped)
-    if (blockIdx.x == 0 && (threadIdx.x >> 5) < 2) {
+    if ((threadIdx.x >> 5) < 2) {
       const int which = threadIdx.x >> 5;
-      auto fetch = [&](int t) -> float {
-        if (t < total) { const float2 v = dense[t]; return which == 0 ? v.x : v.y; }
-        return 0.0f;
+      auto fetch = [&](int t) -> double {
+        if (t < total) { double a, b; dense.get(t, a, b); return which == 0 ? a : b; }
+        return 0.0;
       };
       float acc = 0.0f;
-      float x = fetch(lane), x1 = fetch(32 + lane);
+      double x = fetch(lane), x1 = fetch(32 + lane);
       for (int t0 = 0; t0 < total; t0 += 32) {
-        const float x2 = fetch(t0 + 64 + lane);
-#pragma unroll
-        for (int q = 0; q < 32; q++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x, q));
+        const double x2 = fetch(t0 + 64 + lane);
+        const int m = min(32, total - t0);               // terms past the end are not added (a double 0.0 is not the identity of -0.0f)
+        for (int q = 0; q < m; q++) acc = Terms::add(acc, __shfl_sync(0xffffffffu, x, q));
         x = x1; x1 = x2;
       }
       if (lane == 0) out4[which] = (double)acc;
     }
     return;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
     vs->s[0] = 0.0f; vs->s[1] = 0.0f; vs->cur[0] = 0; vs->cur[1] = 0; vs->rounds = 0; vs->seq_chunks[0] = 0; vs->seq_chunks[1] = 0;
   }
-  __threadfence();
-  grid.sync();
+  __syncthreads();
   for (int round = 0; round < 2 * nchunks + 4; round++) {
     const int cur0 = vs->cur[0], cur1 = vs->cur[1];
     if (cur0 >= nchunks && cur1 >= nchunks) break;
@@ -1809,9 +1877,9 @@ k_crit_chain_par(const float2* __restrict__ dense, const int* __restrict__ offse
       constexpr int kPer = kCcChunk / 32;
       const int t_end = min(total, (c + 1) * kCcChunk);
       const int t_lane = c * kCcChunk + lane * kPer;
-      float2 vv[kPer];
+      double vx[kPer], vy[kPer];
 #pragma unroll
-      for (int j = 0; j < kPer; j++) vv[j] = (t_lane + j < t_end) ? dense[t_lane + j] : make_float2(0.0f, 0.0f);
+      for (int j = 0; j < kPer; j++) { vx[j] = 0.0; vy[j] = 0.0; if (t_lane + j < t_end) dense.get(t_lane + j, vx[j], vy[j]); }
       long long run[2] = {0, 0}, mn[2] = {LLONG_MAX, LLONG_MAX}, mx[2] = {LLONG_MIN, LLONG_MIN};
       int flag[2] = {2, 2};
 #pragma unroll
@@ -1823,11 +1891,13 @@ k_crit_chain_par(const float2* __restrict__ dense, const int* __restrict__ offse
         const int sh = 23 - (ch ? E1 : E0);
 #pragma unroll
         for (int j = 0; j < kPer; j++) {
-          const float x = ch ? vv[j].y : vv[j].x;
-          nz = nz || (x != 0.0f);
+          const double x = ch ? vy[j] : vx[j];
+          nz = nz || (x != 0.0);
           if (okc) {
-            const double q = scalbn((double)x, sh);                        // x / u, exact
-            needseq = needseq || (fabs(q - trunc(q)) == 0.5) || !(fabs(q) < 1073741824.0);   // tie; huge, inf or nan term
+            const double q = scalbn(x, sh);                                // x / u, exact
+            const double fr = fabs(q - trunc(q));
+            const bool tie = Terms::kDouble ? (fabs(fr - 0.5) < 1.4901161193847656e-08) : (fr == 0.5);   // 2^-26 around the tie
+            needseq = needseq || tie || !(fabs(q) < 1073741824.0);         // tie; huge, inf or nan term
             pre += (fabs(q) < 1073741824.0) ? (long long)rint(q) : 0;
             if (t_lane + j < t_end) { lmn = min(lmn, pre); lmx = max(lmx, pre); }
           }
@@ -1858,11 +1928,10 @@ k_crit_chain_par(const float2* __restrict__ dense, const int* __restrict__ offse
         }
       }
     }
-    __threadfence();
-    grid.sync();
+    __syncthreads();
     // ---- B: CTA 0, warp ch walks chain ch over the prepared chunks; a chunk that cannot be taken by integer arithmetic
     // is added the plain way, and the walk goes on as long as the records still fit the state
-    if (blockIdx.x == 0 && (threadIdx.x >> 5) < 2) {
+    if ((threadIdx.x >> 5) < 2) {
       const int ch = threadIdx.x >> 5;
       int cur = ch ? cur1 : cur0;
       if (cur < nchunks) {
@@ -1908,18 +1977,18 @@ k_crit_chain_par(const float2* __restrict__ dense, const int* __restrict__ offse
           if (cur >= last) break;
           {   // chunk `cur` the plain way
             const int t_begin = cur * kCcChunk, t_end = min(total, t_begin + kCcChunk);
-            float xs[kCcChunk / 32];                                          // 16 independent loads, then the chain
+            double xs[kCcChunk / 32];                                         // 16 independent loads, then the chain
 #pragma unroll
             for (int b = 0; b < kCcChunk / 32; b++) {
               const int t = t_begin + b * 32 + lane;
-              xs[b] = 0.0f;
-              if (t < t_end) { const float2 v = dense[t]; xs[b] = ch ? v.y : v.x; }
+              xs[b] = 0.0;
+              if (t < t_end) { double a, bb; dense.get(t, a, bb); xs[b] = ch ? bb : a; }
             }
             float acc = sacc;
 #pragma unroll
             for (int b = 0; b < kCcChunk / 32; b++) {
-#pragma unroll
-              for (int q = 0; q < 32; q++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, xs[b], q));   // 0.0f past the end: identity
+              const int m = min(32, t_end - (t_begin + b * 32));              // warp-uniform; <= 0 past the end
+              for (int q = 0; q < m; q++) acc = Terms::add(acc, __shfl_sync(0xffffffffu, xs[b], q));
             }
             sacc = acc;
             cur++; nseq++;
@@ -1931,33 +2000,32 @@ k_crit_chain_par(const float2* __restrict__ dense, const int* __restrict__ offse
         if (lane == 0) { vs->s[ch] = sacc; vs->cur[ch] = cur; vs->seq_chunks[ch] += nseq; }
       }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 64) vs->rounds = round + 1;
-    __threadfence();
-    grid.sync();
+    if (threadIdx.x == 64) vs->rounds = round + 1;
+    __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { out4[0] = (double)vs->s[0]; out4[1] = (double)vs->s[1]; }
+  if (threadIdx.x == 0) { out4[0] = (double)vs->s[0]; out4[1] = (double)vs->s[1]; }
 }
 
 // D (warp 0) and G (warp 1) re-accumulated in float32 in the reference's order.  The warp loads 32 terms at a time
 // (coalesced, one block ahead of the adds) and hands them to the dependent chain of adds through shuffles.
+template <class Terms>
 __global__ void __launch_bounds__(64)
-k_crit_chain(const float2* __restrict__ dense, const int* __restrict__ offsets, int n_regions, double* __restrict__ out4) {
-  const int lane = threadIdx.x & 31, which = threadIdx.x >> 5;   // 0: D, 1: G
-  const int total = offsets[n_regions];
-  auto fetch = [&](int t) -> float {
-    if (t < total) { const float2 v = dense[t]; return which == 0 ? v.x : v.y; }
-    return 0.0f;
+k_crit_chain(Terms dense, const int* __restrict__ total_ptr, double* __restrict__ out2) {
+  const int lane = threadIdx.x & 31, which = threadIdx.x >> 5;   // 0: D (L), 1: G (Z)
+  const int total = *total_ptr;
+  auto fetch = [&](int t) -> double {
+    if (t < total) { double a, b; dense.get(t, a, b); return which == 0 ? a : b; }
+    return 0.0;
   };
   float acc = 0.0f;
-  float x = fetch(lane), x1 = fetch(32 + lane);
+  double x = fetch(lane), x1 = fetch(32 + lane);
   for (int t0 = 0; t0 < total; t0 += 32) {
-    const float x2 = fetch(t0 + 64 + lane);       // two blocks ahead of the chain
-    // terms past `total` were fetched as 0.0f: adding them is the identity
-#pragma unroll
-    for (int q = 0; q < 32; q++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x, q));
+    const double x2 = fetch(t0 + 64 + lane);      // two blocks ahead of the chain
+    const int m = min(32, total - t0);
+    for (int q = 0; q < m; q++) acc = Terms::add(acc, __shfl_sync(0xffffffffu, x, q));
     x = x1; x1 = x2;
   }
-  if (lane == 0) out4[which] = (double)acc;
+  if (lane == 0) out2[which] = (double)acc;
 }
 
 // fp64 sum of n values (stride apart) in index order: a warp loads 32 at a time, lane 0's adds take them by shuffle --
@@ -2027,7 +2095,6 @@ __global__ void k_sum_partials(const double* __restrict__ p, int n, double* __re
 // instance that is no longer active -- so the host enqueues iterations without ever waiting for one, and only looks at an
 // "any instance still active" word one iteration late.  The arithmetic is the single-instance kernels' (same bodies).
 // ------------------------------------------------------------------------------------------------------------------
-enum { kStMaxdiff = 0, kStStatus = 1, kStActive = 2, kStIter = 3, kStConverged = 4, kStWords = 8 };
 
 struct BatchInst {
   const uint32_t* bits;
@@ -2049,9 +2116,18 @@ struct BatchInst {
   char* zero_from; long long zero_bytes;   // statistics cleared before every M-step
   float base_prop;
   float eps_init[NEMB200_MAX_K];
+  // criteria (nem_alg.c:2764-2843), computed once at the end of the run
+  float* logpk32_unused;       // (P carries logpk32 / logpk64)
+  double* crit_partial; float* crit_terms; int* crit_counts; int* crit_offsets; float* crit_dense; double* crit_lz;
+  int* crit_nrows; double* crit4;
   // outputs of the run (device pointers of the caller, may be null)
   float* T_out; float* mu_out; float* eps_out; float* pk_out;
 };
+
+__device__ __forceinline__ int b_final_buffer(const BatchInst& I) {
+  // a failed iteration does not replace the posteriors (nem_alg.c:1873-1892)
+  return (I.c0 + (int)I.state[kStIter] - (I.state[kStStatus] != 0u ? 1 : 0)) & 1;
+}
 
 __device__ __forceinline__ bool b_active(const BatchInst& I) { return I.state[kStActive] != 0u; }
 
@@ -2132,11 +2208,29 @@ __global__ void __launch_bounds__(256) k_b_finalize(const BatchInst* __restrict_
 }
 
 template <int KB, int KX, int RB>
-__global__ void __launch_bounds__(kDensTpb) k_b_density_sk(const BatchInst* __restrict__ B, int G, int gate) {
+__global__ void __launch_bounds__(kDensTpb) k_b_density_sk(const BatchInst* __restrict__ B, int G, int gate, int planes_in_smem) {
   const BatchInst& I = B[blockIdx.z];
   if (gate && !b_active(I)) return;
   density_sk_cta<KB, KX, RB>(reinterpret_cast<const uint4*>(I.bits), I.N, I.Ws / 4, I.K, G, reinterpret_cast<const uint4*>(I.P.m1),
-                             reinterpret_cast<const uint4*>(I.P.valid), I.P.L, I.P.B, I.P.has_half, I.logf, 1);
+                             reinterpret_cast<const uint4*>(I.P.valid), I.P.L, I.P.B, I.P.has_half, I.logf, planes_in_smem);
+}
+
+// large matrices: the streaming (shared-memory ring) kernels, classes [k0, k0 + kc) per launch
+template <int KB, int KX, int RB, int P, int TPB>
+__global__ void __launch_bounds__(TPB, 1) k_b_density_ring(const BatchInst* __restrict__ B, int G, int gate, int k0, int kc) {
+  const BatchInst& I = B[blockIdx.z];
+  if (gate && !b_active(I)) return;
+  const int W4 = I.Ws / 4;
+  density_sk_ring_cta<KB, KX, RB, P, TPB>(reinterpret_cast<const uint4*>(I.bits), I.N, W4, kc, G,
+                                          reinterpret_cast<const uint4*>(I.P.m1) + (size_t)k0 * W4,
+                                          reinterpret_cast<const uint4*>(I.P.valid) + (size_t)k0 * W4, I.P.L + k0, I.P.B + k0,
+                                          I.P.has_half, I.logf + k0, I.K);
+}
+
+__global__ void __launch_bounds__(kOhTpb, 1) k_b_onehot_ring(const BatchInst* __restrict__ B, int tile_w) {
+  const BatchInst& I = B[blockIdx.z];
+  if (!b_active(I)) return;
+  mstep_onehot_ring_body(reinterpret_cast<const uint4*>(I.bits), I.Ws / 4, tile_w, I.K, I.offsets, I.perm, I.cnt, I.Dpad);
 }
 
 template <int KB>
@@ -2211,17 +2305,56 @@ __global__ void __launch_bounds__(256) k_b_poll(const BatchInst* __restrict__ B,
   }
 }
 
+// criteria of all instances of a group (nem_alg.c:1906): per-row terms, then the float32 sums in the reference's order
+template <int GS>
+__global__ void __launch_bounds__(256) k_b_criteria(const BatchInst* __restrict__ B) {
+  const BatchInst& I = B[blockIdx.z];
+  if (I.state[kStStatus] != 0u) return;
+  CritArgs a;
+  a.N = I.N; a.K = I.K; a.logf = I.logf; a.pk = I.P.pk; a.logpk32 = I.P.logpk32; a.logpk64 = I.P.logpk64;
+  a.T = I.T[b_final_buffer(I)];
+  a.rowptr = I.rowptr; a.col = I.col; a.w = I.w; a.beta = I.beta; a.logspace = I.logspace;
+  a.partial = I.crit_partial;
+  const int n_warps = gridDim.x * 8;
+  a.rows_per_warp = (I.N + n_warps - 1) / n_warps;
+  a.terms = I.logspace ? nullptr : reinterpret_cast<float2*>(I.crit_terms);
+  a.counts = I.logspace ? nullptr : I.crit_counts;
+  a.row_lz = I.logspace ? nullptr : reinterpret_cast<double2*>(I.crit_lz);
+  criteria_body<GS>(a);
+}
+// reference arithmetic: region offsets (one warp per instance) ...
+__global__ void __launch_bounds__(32) k_b_crit_offsets(const BatchInst* __restrict__ B, int n_regions) {
+  const BatchInst& I = B[blockIdx.z];
+  if (I.state[kStStatus] != 0u || I.logspace) return;
+  crit_offsets_body(I.crit_counts, n_regions, I.crit_offsets, I.crit_nrows, (int)I.N);
+}
+// ... and the compaction of the regions' terms
+__global__ void __launch_bounds__(256) k_b_crit_compact(const BatchInst* __restrict__ B, int n_regions) {
+  const BatchInst& I = B[blockIdx.z];
+  if (I.state[kStStatus] != 0u || I.logspace) return;
+  crit_compact_body(reinterpret_cast<const float2*>(I.crit_terms), I.crit_counts, I.crit_offsets, n_regions,
+                    (I.N + n_regions - 1) / n_regions, I.K, reinterpret_cast<float2*>(I.crit_dense));
+}
+// log-space mode: fp64 sums of the block partials, in block order
+__global__ void __launch_bounds__(128) k_b_crit_reduce(const BatchInst* __restrict__ B, int nblocks) {
+  const BatchInst& I = B[blockIdx.z];
+  if (I.state[kStStatus] != 0u || !I.logspace) return;
+  const int w = threadIdx.x >> 5;
+  const double t = ordered_sum(I.crit_partial + w, nblocks, 4);
+  if ((threadIdx.x & 31) == 0) I.crit4[w] = t;
+}
+
 // results of all instances of a group in one launch: final posteriors, parameters, and the scalar outcome
 // (out_scalars[inst] = {n_iter, converged, status, c_final})
-__global__ void __launch_bounds__(256) k_b_collect(const BatchInst* __restrict__ B, int* __restrict__ out_scalars /*[n][4]*/) {
+__global__ void __launch_bounds__(256) k_b_collect(const BatchInst* __restrict__ B, double* __restrict__ out_scalars /*[n][8]*/) {
   const BatchInst& I = B[blockIdx.z];
   const int n_iter = (int)I.state[kStIter], status = (int)I.state[kStStatus];
-  // a failed iteration does not replace the posteriors (nem_alg.c:1873-1892)
-  const int cfin = (I.c0 + n_iter - (status != 0 ? 1 : 0)) & 1;
+  const int cfin = b_final_buffer(I);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   if (tid == 0) {
-    out_scalars[blockIdx.z * 4 + 0] = n_iter; out_scalars[blockIdx.z * 4 + 1] = (int)I.state[kStConverged];
-    out_scalars[blockIdx.z * 4 + 2] = status; out_scalars[blockIdx.z * 4 + 3] = cfin;
+    double* o = out_scalars + (size_t)blockIdx.z * 8;
+    o[0] = n_iter; o[1] = (double)I.state[kStConverged]; o[2] = status; o[3] = cfin;
+    for (int q = 0; q < 4; q++) o[4 + q] = status == 0 ? I.crit4[q] : 0.0;
   }
   if (I.T_out != nullptr) {
     const float* src = I.T[cfin];

@@ -35,7 +35,8 @@ class NemB200Error(RuntimeError):
 
 class _Result(ctypes.Structure):
     _fields_ = [("crit", ctypes.c_double * 5), ("n_iter", ctypes.c_int32), ("converged", ctypes.c_int32),
-                ("status", ctypes.c_int32), ("n_levels", ctypes.c_int32), ("elapsed_ms", ctypes.c_float)]
+                ("status", ctypes.c_int32), ("n_levels", ctypes.c_int32), ("elapsed_ms", ctypes.c_float),
+                ("em_ms", ctypes.c_float)]
 
 
 _lib = None
@@ -71,6 +72,11 @@ SIGNATURES = {
     "nemb200_sweep": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp]),
     "nemb200_plan_graph_changed": (ctypes.c_int, [_vp]),
     "nemb200_selftest_float_chain": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "nemb200_selftest_double_chain": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "nemb200_export_samples": (ctypes.c_int, [_vp, _i32, _vp, _f32, _vp, _i32, _i32, _vp]),
+    "nemb200_chunk_codes": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "nemb200_apply_votes": (ctypes.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, ctypes.c_double, _i32, _vp]),
+    "nemb200_subset_counts": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "nemb200_read_flags": (ctypes.c_int, [_vp, ctypes.POINTER(_f32), ctypes.POINTER(_i32), _vp]),
     "nemb200_criteria": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f32, ctypes.POINTER(ctypes.c_double * 5), _vp]),
     "nemb200_get_params": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.POINTER(_i32), _vp]),
@@ -133,6 +139,7 @@ class NemRun:
     status: int
     n_levels: int
     elapsed_ms: float
+    em_ms: float = 0.0
 
     @property
     def ok(self) -> bool:
@@ -171,7 +178,8 @@ def nem_run_host(bits: np.ndarray, D: int, rowptr, col, w, K: int, beta: float, 
                                 itermax, cv_th, flags, T.ctypes.data, mu.ctypes.data, eps.ctypes.data, pk.ctypes.data,
                                 ctypes.byref(res))
     _check(rc, "nemb200_nem_host")
-    return NemRun(T, mu, eps, pk, list(res.crit), res.n_iter, bool(res.converged), res.status, res.n_levels, res.elapsed_ms)
+    return NemRun(T, mu, eps, pk, list(res.crit), res.n_iter, bool(res.converged), res.status, res.n_levels, res.elapsed_ms,
+                  res.em_ms)
 
 
 @dataclass
@@ -223,21 +231,23 @@ class DeviceInput:
 
 
 def _nem_run_device_impl(bits, rowptr, col, w, sched_ptr, sched_rows, D: int, n_levels: int, K: int, beta: float,
-                         free_disp: int, itermax: int, cv_th: float, flags: int):
+                         free_disp: int, itermax: int, cv_th: float, flags: int, want_params: bool = True):
     torch = _torch()
     N, Ws = bits.shape
     dev = bits.device
     T = torch.empty((N, K), dtype=torch.float32, device=dev)
-    mu = torch.empty((K, D), dtype=torch.float32, device=dev)
-    eps = torch.empty((K, D), dtype=torch.float32, device=dev)
-    pk = torch.empty((K,), dtype=torch.float32, device=dev)
+    kd = (K, D) if want_params else (0, 0)
+    mu = torch.empty(kd, dtype=torch.float32, device=dev)
+    eps = torch.empty(kd, dtype=torch.float32, device=dev)
+    pk = torch.empty((K if want_params else 0,), dtype=torch.float32, device=dev)
     res = _Result()
     with torch.cuda.device(dev):
         rc = lib().nemb200_nem_device(_ptr(bits), N, D, Ws, _ptr(rowptr), _ptr(col), _ptr(w), _ptr(sched_ptr),
                                       _ptr(sched_rows), n_levels, K, beta, free_disp, itermax, cv_th, flags, _ptr(T),
-                                      _ptr(mu), _ptr(eps), _ptr(pk), ctypes.byref(res), _stream())
+                                      _ptr(mu) if want_params else 0, _ptr(eps) if want_params else 0,
+                                      _ptr(pk) if want_params else 0, ctypes.byref(res), _stream())
     _check(rc, "nemb200_nem_device")
-    stats = torch.tensor(list(res.crit) + [res.n_iter, res.converged, res.status, res.n_levels, res.elapsed_ms],
+    stats = torch.tensor(list(res.crit) + [res.n_iter, res.converged, res.status, res.n_levels, res.elapsed_ms, res.em_ms],
                          dtype=torch.float64)
     return T, mu, eps, pk, stats
 
@@ -254,20 +264,22 @@ def _register_op():
     torch.library.define(
         "ppanggolin_b200::nem_run",
         "(Tensor bits, Tensor? rowptr, Tensor? col, Tensor? w, Tensor? sched_ptr, Tensor? sched_rows, int D, "
-        "int n_levels, int K, float beta, int free_disp, int itermax, float cv_th, int flags) "
+        "int n_levels, int K, float beta, int free_disp, int itermax, float cv_th, int flags, bool want_params=True) "
         "-> (Tensor, Tensor, Tensor, Tensor, Tensor)")
 
     @torch.library.impl("ppanggolin_b200::nem_run", "CUDA")
-    def nem_run(bits, rowptr, col, w, sched_ptr, sched_rows, D, n_levels, K, beta, free_disp, itermax, cv_th, flags):
+    def nem_run(bits, rowptr, col, w, sched_ptr, sched_rows, D, n_levels, K, beta, free_disp, itermax, cv_th, flags,
+                want_params=True):
         return _nem_run_device_impl(bits, rowptr, col, w, sched_ptr, sched_rows, D, n_levels, K, beta, free_disp,
-                                    itermax, cv_th, flags)
+                                    itermax, cv_th, flags, want_params)
 
     _op_registered = True
 
 
 def nem_run_device(inp: DeviceInput, K: int, beta: float, free_dispersion: bool = False, itermax: int = 100,
-                   cv_th: float = 0.01, flags: int = EPI_REF) -> NemRun:
-    """Whole run with the instance already resident in HBM (the custom op)."""
+                   cv_th: float = 0.01, flags: int = EPI_REF, want_params: bool = True) -> NemRun:
+    """Whole run with the instance already resident in HBM (the custom op).  ``want_params=False`` skips the K x D
+    centres / dispersions (callers that only need posteriors and criteria: K selection, chunk votes)."""
     torch = _require_cuda()
     if not (1 <= K <= MAX_K):
         raise NemB200Error(f"K={K} outside 1..{MAX_K}")
@@ -279,16 +291,20 @@ def nem_run_device(inp: DeviceInput, K: int, beta: float, free_dispersion: bool 
     T, mu, eps, pk, stats = torch.ops.ppanggolin_b200.nem_run(
         inp.bits, inp.rowptr if use_graph else None, inp.col if use_graph else None, inp.w if use_graph else None,
         inp.sched_ptr if use_graph else None, inp.sched_rows if use_graph else None, inp.D,
-        inp.n_levels if use_graph else 1, K, beta32, int(free_dispersion), itermax, cv_th, flags)
+        inp.n_levels if use_graph else 1, K, beta32, int(free_dispersion), itermax, cv_th, flags, want_params)
     s = stats.tolist()
-    return NemRun(T, mu.cpu().numpy(), eps.cpu().numpy(), pk.cpu().numpy(), s[:5], int(s[5]), bool(s[6]), int(s[7]),
-                  int(s[8]), float(s[9]))
+    if want_params:
+        mu, eps, pk = mu.cpu().numpy(), eps.cpu().numpy(), pk.cpu().numpy()
+    else:
+        mu = eps = pk = None
+    return NemRun(T, mu, eps, pk, s[:5], int(s[5]), bool(s[6]), int(s[7]), int(s[8]), float(s[9]), float(s[10]))
 
 
-def nem_run_batch(instances, cv_th: float = 0.01, flags: int = EPI_REF):
+def nem_run_batch(instances, cv_th: float = 0.01, flags: int = EPI_REF, want_params: bool = True):
     """Independent NEM instances in one call (``nemb200_nem_device_batch``): the K-selection sweep or chunk samples.
 
-    ``instances``: list of ``(DeviceInput, K, beta, free_dispersion, itermax)``.  Returns a list of :class:`NemRun`."""
+    ``instances``: list of ``(DeviceInput, K, beta, free_dispersion, itermax)``.  Returns a list of :class:`NemRun`
+    (``mu`` / ``eps`` / ``pk`` are None with ``want_params=False``)."""
     torch = _require_cuda()
     n = len(instances)
     if n == 0:
@@ -311,9 +327,11 @@ def nem_run_batch(instances, cv_th: float = 0.01, flags: int = EPI_REF):
             raise NemB200Error("beta != 0 needs the neighbour graph")
         N, W = inp.bits.shape
         T = torch.empty((N, K), dtype=torch.float32, device=dev)
-        mu = torch.empty((K, inp.D), dtype=torch.float32, device=dev)
-        eps = torch.empty((K, inp.D), dtype=torch.float32, device=dev)
-        pk = torch.empty((K,), dtype=torch.float32, device=dev)
+        mu = eps = pk = None
+        if want_params:
+            mu = torch.empty((K, inp.D), dtype=torch.float32, device=dev)
+            eps = torch.empty((K, inp.D), dtype=torch.float32, device=dev)
+            pk = torch.empty((K,), dtype=torch.float32, device=dev)
         outs.append((T, mu, eps, pk))
         bits[i], Ns[i], Ds[i], Ws[i] = _ptr(inp.bits), N, inp.D, W
         rp[i], cl[i], ww[i] = (_ptr(inp.rowptr), _ptr(inp.col), _ptr(inp.w)) if g else (0, 0, 0)
@@ -330,8 +348,9 @@ def nem_run_batch(instances, cv_th: float = 0.01, flags: int = EPI_REF):
     runs = []
     for i, (T, mu, eps, pk) in enumerate(outs):
         r = res[i]
-        runs.append(NemRun(T, mu.cpu().numpy(), eps.cpu().numpy(), pk.cpu().numpy(), list(r.crit), r.n_iter, bool(r.converged),
-                           r.status, r.n_levels, r.elapsed_ms))
+        if want_params:
+            mu, eps, pk = mu.cpu().numpy(), eps.cpu().numpy(), pk.cpu().numpy()
+        runs.append(NemRun(T, mu, eps, pk, list(r.crit), r.n_iter, bool(r.converged), r.status, r.n_levels, r.elapsed_ms, r.em_ms))
     return runs
 
 
@@ -344,6 +363,17 @@ def float_chain(d: np.ndarray, g: np.ndarray, parallel: bool):
     out = (ctypes.c_double * 2)()
     _check(lib().nemb200_selftest_float_chain(d.ctypes.data, g.ctypes.data, d.shape[0], int(parallel), ctypes.cast(out, _vp)),
            "selftest_float_chain")
+    return np.float32(out[0]), np.float32(out[1])
+
+
+def double_chain(l: np.ndarray, z: np.ndarray, parallel: bool):
+    """Diagnostics: float32 accumulators receiving double terms (the L / Z criteria), sequential chain or exact parallel scheme."""
+    _require_cuda()
+    l = np.ascontiguousarray(l, np.float64); z = np.ascontiguousarray(z, np.float64)
+    assert l.shape == z.shape and l.ndim == 1
+    out = (ctypes.c_double * 2)()
+    _check(lib().nemb200_selftest_double_chain(l.ctypes.data, z.ctypes.data, l.shape[0], int(parallel), ctypes.cast(out, _vp)),
+           "selftest_double_chain")
     return np.float32(out[0]), np.float32(out[1])
 
 

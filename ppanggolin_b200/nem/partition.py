@@ -84,12 +84,11 @@ def _device_input(inp):
 SHARD_MIN_BYTES = int(os.environ.get("PPANGGOLIN_B200_SHARD_MIN_BYTES", str(256 << 20)))
 
 
-def _run_sharded(inp, kval: int, beta: float, free_dispersion: bool, itermax: int, flags: int):
+def _run_sharded(dev_in, D: int, names, kval: int, beta: float, free_dispersion: bool, itermax: int, flags: int):
     """The instance through ``nem/sharded.py`` when a process group is active and the matrix is large: every rank keeps a
     contiguous block of families, the exchange runs over NVLink peer memory inside the kernels, and every rank ends with
     the same posteriors as a single-GPU run.  Returns None when the instance should run on one GPU."""
     rank, world, dist = _rank_world()
-    dev_in = inp.device
     N, Ws = dev_in.bits.shape
     if world == 1 or N * Ws * 4 < SHARD_MIN_BYTES or N < 2 * world:
         return None
@@ -101,7 +100,8 @@ def _run_sharded(inp, kval: int, beta: float, free_dispersion: bool, itermax: in
     colsum = torch.zeros(Ws, dtype=torch.int64, device=dev_in.bits.device)     # per 32-column word: sum of the rows' words
     for r0 in range(0, N, 8192):
         colsum += (dev_in.bits[r0:r0 + 8192].to(torch.int64) & 0xFFFFFFFF).sum(0)
-    digest = hashlib.sha256(colsum.cpu().numpy().tobytes() + "|".join(inp.fam_names[:64] + inp.fam_names[-64:]).encode()).hexdigest()
+    tail = "|".join(list(names[:64]) + list(names[-64:])) if names is not None else ""
+    digest = hashlib.sha256(colsum.cpu().numpy().tobytes() + tail.encode()).hexdigest()
     seen = [None] * world
     dist.all_gather_object(seen, digest)
     if len(set(seen)) != 1:
@@ -118,13 +118,23 @@ def _run_sharded(inp, kval: int, beta: float, free_dispersion: bool, itermax: in
     hosts = [None] * world
     dist.all_gather_object(hosts, socket.gethostname())
     peer_ok = world <= engine.MAX_PEERS and len(set(hosts)) == 1
-    be = CudaBackend(dev_in.bits[lo:hi], inp.D, N, kval, free_dispersion, flags, graph,
+    be = CudaBackend(dev_in.bits[lo:hi], D, N, kval, free_dispersion, flags, graph,
                      peer_group=dist.group.WORLD if peer_ok else None, row_offset=lo)
     out = ShardedEM(be, N, kval, rank, world, dist.group.WORLD).run(beta32, itermax, 0.01)
     mu, eps, pk, _ = be.plan.get_params()
     run = engine.NemRun(out.T, mu, eps, pk, list(out.crit), out.n_iter, out.converged, out.status,
                         dev_in.n_levels if graph is not None else 1, 0.0)
     be.plan.close()
+    return run
+
+
+def _run_instance(dev_in, kval: int, beta: float, free_dispersion: bool, itermax: int, flags: int, want_params: bool = True,
+                  names=None):
+    """One NEM instance resident in HBM: row-sharded over the process group when it is large, else on this rank's GPU."""
+    run = _run_sharded(dev_in, dev_in.D, names, kval, beta, free_dispersion, itermax, flags)
+    if run is None:
+        run = engine.nem_run_device(dev_in, kval, beta, free_dispersion, itermax=itermax, cv_th=0.01, flags=flags,
+                                    want_params=want_params)
     return run
 
 
@@ -164,10 +174,7 @@ def run_partitioning(
         raise FileNotFoundError(f"no exported NEM instance registered for {nem_dir_path}: call write_nem_input_files first")
     if inp.device is None:
         inp.device = _device_input(inp)
-    run = _run_sharded(inp, kval, beta, free_dispersion, itermax, _epilogue_flags(nb_org))
-    if run is None:
-        run = engine.nem_run_device(inp.device, kval, beta, free_dispersion, itermax=itermax, cv_th=0.01,
-                                    flags=_epilogue_flags(nb_org))
+    run = _run_instance(inp.device, kval, beta, free_dispersion, itermax, _epilogue_flags(nb_org), names=inp.fam_names)
     if not run.ok:
         # the reference writes no .uf in this case and partition.py:233-265 returns empty objects
         if just_log_likelihood:
@@ -242,35 +249,33 @@ _ARRAYS = {"pan": None, "arrays": None}
 
 
 def _arrays_for(pangenome):
-    """Array form of ``pangenome`` (export_arrays.PangenomeArrays), built once per partition() call; None when the
-    fast exporter is switched off (PPANGGOLIN_B200_FAST_EXPORT=0) or no CUDA device is present."""
-    if os.environ.get("PPANGGOLIN_B200_FAST_EXPORT", "1") == "0":
-        return None
+    """Device-resident array form of ``pangenome`` (export_device.DevicePangenome), built once per partition() call; None
+    when it was not prepared (keep_tmp_files: the object traversal that also produces the text files is used)."""
     if _ARRAYS["pan"] is pangenome:
         return _ARRAYS["arrays"]
     return None
 
 
 def prepare_arrays(pangenome, device=None):
-    """Read the pangenome objects once into tensors; every later write_nem_input_files(...) for this pangenome derives
-    its instance from them.  Called by partition(); callers that drive write_nem_input_files themselves (rarefaction)
-    may call it too."""
-    if os.environ.get("PPANGGOLIN_B200_FAST_EXPORT", "1") == "0":
-        return None
-    from .export_arrays import PangenomeArrays
-    if device is None:
-        import torch
-        device = "cuda" if torch.cuda.is_available() else "cpu"
-    _ARRAYS["pan"], _ARRAYS["arrays"] = pangenome, PangenomeArrays.from_pangenome(pangenome, device)
+    """Read the pangenome objects once into arrays in HBM; every later write_nem_input_files(...) for this pangenome derives
+    its instance from them on the device.  Called by partition(); callers that drive write_nem_input_files themselves
+    (rarefaction) call it too."""
+    from .export_device import DevicePangenome
+    _ARRAYS["pan"], _ARRAYS["arrays"] = pangenome, DevicePangenome.from_pangenome(pangenome, device or "cuda")
     return _ARRAYS["arrays"]
 
 
 def write_nem_input_files(tmpdir: Path, organisms: set, sm_degree: int = 10, keep_tmp_files: bool = False) -> Tuple[float, int]:
     """partition.py:344-436.  Exports the sub-pangenome of ``organisms`` (global ``pan``) and registers it under
     ``tmpdir``; returns (total edge weight / 2, number of families) exactly like the reference."""
-    arrays = _arrays_for(pan)
-    if arrays is not None and not keep_tmp_files:
-        inp = arrays.instance(organisms, sm_degree)          # tensor ops on the cached array form of the pangenome
+    dp = _arrays_for(pan)
+    if dp is not None and not keep_tmp_files:
+        cols = dp.columns(organisms)
+        inst = dp.export([cols], sm_degree)[0]               # CUDA exporter on the cached array form of the pangenome
+        rows = inst.fam_rows.cpu().numpy()
+        inp = export.NemInput(None, inst.D, None, None, None, [dp.fam_names[i] for i in rows], [dp.org_names[c] for c in cols],
+                              inst.edges_weight)
+        inp.device, inp.fam_rows, inp.bits_tensor = inst.inp, inst.fam_rows, inst.inp.bits
     else:
         inp = export.export_from_pangenome(pan, organisms, sm_degree, keep_text=keep_tmp_files)
     export.register(tmpdir, inp)
@@ -296,6 +301,14 @@ def evaluate_nb_partitions(
     """partition.py:439-634: BIC/ICL sweep over K = krange[0]-1 .. krange[1] with beta = 0 and 10 iterations."""
     tmpdir = Path(tempfile.gettempdir()) if tmpdir is None else tmpdir
     newtmpdir = tmpdir / "eval_partitions"
+    dp = _arrays_for(pan)
+    if dp is not None:      # the whole sweep on arrays (nem/workflow.py): same draws, same rule
+        from . import workflow
+        chosen_k, all_bics, all_icls, all_lls = workflow.evaluate_nb_partitions_arrays(
+            dp, [dp.org_index[o] for o in organisms], free_dispersion, chunk_size, krange, icl_margin, sm_degree)
+        if len(all_bics) > 0 and draw_icl:
+            _draw_icl(output, all_bics, all_icls, all_lls, chosen_k)
+        return chosen_k
     if len(organisms) > chunk_size:
         select_organisms = _same_on_all_ranks(set(random.sample(list(organisms), chunk_size)), organisms)
     else:
@@ -425,8 +438,9 @@ def partition(
     check_pangenome_former_partition(pangenome, force)
     check_pangenome_info(pangenome, need_annotations=True, need_families=True, need_graph=True, disable_bar=disable_bar)
     organisms = set(pangenome.organisms)
+    dp = None
     if not keep_tmp_files:
-        prepare_arrays(pangenome)   # one traversal of the objects; every sample / chunk below is derived from tensors
+        dp = prepare_arrays(pangenome)   # one traversal of the objects; every sample / chunk below is derived on the device
 
     if keep_tmp_files:
         tmp_dir = tempfile.mkdtemp(dir=tmpdir)
@@ -461,26 +475,23 @@ def partition(
     init = "param_file"
 
     partitioning_results = {}
-    families = set()
-    cpt = 0
-    cpt_partition = {}
-    random.seed(seed)
-
-    for fam in pangenome.gene_families:
-        families.add(fam)
-        if chunk_size < len(organisms):
-            cpt_partition[fam.name] = {"P": 0, "S": 0, "C": 0, "U": 0}
-
     start_partitioning = time.time()
     logger.info("Partitioning...")
-    pansize = len(families)
-    arrays = _arrays_for(pangenome)
-    if chunk_size < len(organisms) and arrays is not None:
-        partitioning_results = [_partition_chunked_arrays(arrays, organisms, chunk_size, kval, beta, sm_degree,
-                                                          free_dispersion, pansize), []]
-        logger.info(f"Did {len(samples)} partitioning with chunks of size {chunk_size} among "
-                    f"{len(organisms)} genomes in {round(time.time() - start_partitioning, 2)} seconds.")
+    if dp is not None:
+        # the workflow on arrays (nem/workflow.py): chunk samples / the single instance exported and run on the GPU in batches
+        from . import workflow
+        order = list(organisms)                                  # what the reference shuffles: list(set of organisms)
+        outcome = workflow.partition_arrays(dp, beta, sm_degree, free_dispersion, chunk_size, kval, kmm, icl_margin, seed,
+                                            cols_in_order=[dp.org_index[o] for o in order])
+        by_col = {dp.org_index[o]: o for o in order}
+        samples.extend({by_col[c] for c in smp} for smp in outcome.samples)
+        partitioning_results = [{name: lab for name, lab in zip(dp.fam_names, outcome.labels) if lab != ""}, []]
     elif chunk_size < len(organisms):
+        # keep_tmp_files: every chunk through write_nem_input_files / run_partitioning, which also write the reference's files
+        families = list(pangenome.gene_families)
+        pansize = len(families)
+        cpt_partition = {fam.name: {"P": 0, "S": 0, "C": 0, "U": 0} for fam in families}
+        random.seed(seed)
         validated = set()
 
         def validate_family(res):  # partition.py:784-802
@@ -512,15 +523,13 @@ def partition(
         logger.info(f"Did {len(samples)} partitioning with chunks of size {chunk_size} among "
                     f"{len(organisms)} genomes in {round(time.time() - start_partitioning, 2)} seconds.")
     else:
-        edges_weight, nb_fam = write_nem_input_files(tmp_path / f"{str(cpt)}", organisms, sm_degree=sm_degree,
-                                                     keep_tmp_files=keep_tmp_files)
-        partitioning_results = run_partitioning(tmp_path / f"{str(cpt)}", len(organisms),
-                                                beta * (nb_fam / edges_weight), free_dispersion, kval=kval, seed=seed,
-                                                init=init, keep_files=keep_tmp_files)
+        random.seed(seed)
+        edges_weight, nb_fam = write_nem_input_files(tmp_path / "0", organisms, sm_degree=sm_degree, keep_tmp_files=keep_tmp_files)
+        partitioning_results = run_partitioning(tmp_path / "0", len(organisms), beta * (nb_fam / edges_weight), free_dispersion,
+                                                kval=kval, seed=seed, init=init, keep_files=keep_tmp_files)
         if partitioning_results == [{}, None, None]:  # never true in the reference either (tuple vs list)
             raise Exception("Statistical partitioning does not work on your data. "
                             "This usually happens because you used very few (<15) genomes.")
-        cpt += 1
         logger.info(f"Partitioned {len(organisms)} genomes in {round(time.time() - start_partitioning, 2)} seconds.")
 
     for fam_name, part in partitioning_results[0].items():
@@ -548,9 +557,6 @@ def _draw_samples(organisms, chunk_size, org_nb_sample, condition):
             shuffled_orgs = shuffled_orgs[chunk_size:]
 
 
-CHUNK_BATCH = 16   # chunk instances per batched GPU call
-
-
 def _same_on_all_ranks(chosen: set, organisms) -> set:
     """Random genome samples must be the same on every rank of a process group, but they are drawn from sets of objects whose
     iteration order depends on object addresses (SURVEY.md Appendix A #11): rank 0's draw is broadcast by genome name."""
@@ -563,26 +569,6 @@ def _same_on_all_ranks(chosen: set, organisms) -> set:
         return chosen
     by_name = {o.name: o for o in organisms}
     return {by_name[n] for n in payload[0]}
-
-
-def _draw_samples_synced(organisms, chunk_size, org_nb_sample, condition):
-    """``_draw_samples`` on rank 0; the other ranks take over its new samples (by genome name) and counters."""
-    rank, world, dist = _rank_world()
-    if world == 1:
-        _draw_samples(organisms, chunk_size, org_nb_sample, condition)
-        return
-    prev = len(samples)
-    if rank == 0:
-        _draw_samples(organisms, chunk_size, org_nb_sample, condition)
-    payload = [[sorted(o.name for o in smp) for smp in samples[prev:]] if rank == 0 else None]
-    dist.broadcast_object_list(payload, src=0)
-    if rank != 0:
-        by_name = {o.name: o for o in organisms}
-        for names in payload[0]:
-            smp = {by_name[n] for n in names}
-            samples.append(smp)
-            for org in smp:
-                org_nb_sample[org] += 1
 
 
 _local_only = 0
@@ -615,104 +601,6 @@ def _rank_world():
     except ImportError:
         pass
     return 0, 1, None
-
-
-def _run_chunk_batch(arrays, sample_ids, kval, beta, sm_degree, free_dispersion, chunk_size):
-    """One batched GPU call for the chunk samples ``sample_ids``; returns per sample a code vector over ALL families of the
-    pangenome (int8: 0 = P, 1 = S, 2 = C, -1 = family absent from the chunk or run failed)."""
-    import torch
-    logger = logging.getLogger("PPanGGOLiN")
-    F = len(arrays.fam_names)
-    out = torch.full((len(sample_ids), F), -1, dtype=torch.int8, device=arrays.device)
-    if not sample_ids:
-        return out
-    insts = [arrays.instance(samples[i], sm_degree) for i in sample_ids]
-    jobs = [(_device_input(inp), kval, beta * (inp.N / inp.edges_weight), free_dispersion, 100) for inp in insts]
-    runs = engine.nem_run_batch(jobs, flags=_epilogue_flags(chunk_size))
-    for j, (inp, run) in enumerate(zip(insts, runs)):
-        if not run.ok:
-            logger.warning("A NEM run failed for this dataset/chunk and was skipped. In chunked mode, other chunks "
-                           "can still complete and final partitioning may still succeed.")
-            continue
-        lab, _ = engine.labels_device(run.T)
-        lab = lab.to(torch.long)
-        code = torch.where(lab == 0, 0, torch.where(lab == kval - 1, 2, 1))    # first letter: P / S (S1.., S_) / C
-        out[j, inp.fam_rows] = code.to(torch.int8)
-    return out
-
-
-def _apply_chunk_votes(votes, validated, codevec, n_org: int, chunk_size: int):
-    """``validate_family`` (partition.py:784-802) for one finished chunk, element-wise: ``codevec`` holds the chunk's label
-    per family (-1 = not in the chunk).  A family occurs at most once per chunk, so this is the reference's per-node rule."""
-    import torch
-    rows = (codevec >= 0).nonzero().squeeze(1)
-    if rows.numel() == 0:
-        return
-    code = codevec[rows].to(torch.long)
-    votes.index_put_((rows, code), torch.ones_like(code), accumulate=True)
-    v = votes[rows]
-    s = v.sum(1)
-    mx = v.max(1).values
-    cond = ((s > n_org / chunk_size) & (mx.to(torch.float64) >= s.to(torch.float64) * 0.5)) | (s > n_org)
-    newly = cond & ~validated[rows]
-    undecided = newly & (mx.to(torch.float64) < s.to(torch.float64) * 0.5)
-    if bool(undecided.any()):
-        votes[rows[undecided], 3] = n_org
-    validated[rows[newly]] = True
-
-
-def _chunk_round(sample_ids, F: int, device, run_batch, votes, validated, n_org: int, chunk_size: int):
-    """The chunk samples of one draw: dealt out round-robin to the ranks in groups of CHUNK_BATCH per rank, run, and the
-    per-chunk label vectors all-gathered, so that every rank applies every chunk's votes in sample order -- the same
-    votes, in the same order, as a single process."""
-    import torch
-    rank, world, dist = _rank_world()
-    for g0 in range(0, len(sample_ids), CHUNK_BATCH * world):
-        group = sample_ids[g0:g0 + CHUNK_BATCH * world]
-        mine = group[rank::world]
-        local = run_batch(mine)
-        if world > 1:
-            per_rank = (len(group) + world - 1) // world            # pad: ranks may hold one sample less
-            buf = torch.full((per_rank, F), -1, dtype=torch.int8, device=device)
-            buf[:local.shape[0]] = local
-            gathered = [torch.empty_like(buf) for _ in range(world)]
-            dist.all_gather(gathered, buf)
-            for pos in range(len(group)):                            # sample `pos` of the group ran on rank pos % world
-                _apply_chunk_votes(votes, validated, gathered[pos % world][pos // world], n_org, chunk_size)
-        else:
-            for j in range(local.shape[0]):
-                _apply_chunk_votes(votes, validated, local[j], n_org, chunk_size)
-
-
-def _partition_chunked_arrays(arrays, organisms, chunk_size, kval, beta, sm_degree, free_dispersion, pansize):
-    """The chunked mode of partition.py:781-864 on tensors: every chunk instance is derived from the cached arrays,
-    instances run in batches on the GPU (spread over the ranks of a process group, if one is initialised), and
-    ``validate_family`` (partition.py:784-802) is applied to the whole result of a chunk at once."""
-    import torch
-    logger = logging.getLogger("PPanGGOLiN")
-    dev = arrays.device
-    F = len(arrays.fam_names)
-    n_org = len(organisms)
-    votes = torch.zeros((F, 4), dtype=torch.long, device=dev)          # columns: P, S, C, U
-    validated = torch.zeros(F, dtype=torch.bool, device=dev)
-    org_nb_sample = Counter()
-    for org in organisms:
-        org_nb_sample[org] = 0
-    condition = n_org / chunk_size
-
-    def run_batch(ids):
-        return _run_chunk_batch(arrays, ids, kval, beta, sm_degree, free_dispersion, chunk_size)
-
-    while int(validated.sum().item()) < pansize:
-        prev = len(samples)
-        _draw_samples_synced(organisms, chunk_size, org_nb_sample, condition)
-        logger.info("Launching NEM")
-        _chunk_round(list(range(prev, len(samples))), F, dev, run_batch, votes, validated, n_org, chunk_size)
-        condition += 1
-        logger.debug(f"There are {int(validated.sum().item())} validated families out of {pansize} families.")
-    best = votes.argmax(1).cpu().numpy()                                  # ties -> first of P, S, C, U like max(dict)
-    letters = np.array(["P", "S", "C", "U"])
-    return dict(zip(arrays.fam_names, letters[best].tolist()))
 
 
 def launch(args: argparse.Namespace):

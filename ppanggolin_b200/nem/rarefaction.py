@@ -27,6 +27,8 @@ from . import partition as ppp
 
 samples: List[set] = []
 
+RAREF_BATCH = 16          # samples per exporter / EM call
+
 CSV_COLUMNS = ["genomes_count", "persistent", "shell", "cloud", "undefined", "exact_core", "exact_accessory", "soft_core",
                "soft_accessory", "pangenome", "K"]
 
@@ -114,24 +116,50 @@ def launch_raref_nem(args) -> Tuple[Dict[str, int], int]:
     return raref_nem(*args)
 
 
-def sample_family_stats(arrays, all_samples: List[set], soft_core: float = 0.95) -> List[Counter]:
-    """rarefaction.py:657-684 on the presence tensor: per sample, families present in all / in >= soft_core of the
-    sample's genomes (exact / soft core) and the others that occur at least once (exact / soft accessory)."""
+def sample_family_stats(dp, all_samples: List[set], soft_core: float = 0.95) -> List[Counter]:
+    """rarefaction.py:657-684: per sample, families present in all / in >= soft_core of the sample's genomes (exact / soft
+    core) and the others that occur at least once (exact / soft accessory).  The reference ANDs gmpy2 bitarrays per family;
+    here one popcount kernel over the bit-packed presence matrix gives every family's count in the sample
+    (``nemb200_subset_counts``)."""
     import torch
     out = []
     for samp in all_samples:
-        cols = torch.tensor(sorted(arrays.org_index[o] for o in samp), dtype=torch.long, device=arrays.device)
-        nb = arrays.presence.index_select(1, cols).sum(1)
+        nb = dp.subset_counts(dp.columns(samp)).to(torch.int64)
         present = nb > 0
         n = len(samp)
+        soft = present & (nb.to(torch.float64) >= n * soft_core)
+        stats = torch.stack([(nb == n).sum(), (present & (nb != n)).sum(), soft.sum(), (present & ~soft).sum()]).cpu().tolist()
         part = Counter()
         part["nborgs"] = n
-        part["exact_core"] = int((nb == n).sum().item())
-        part["exact_accessory"] = int((present & (nb != n)).sum().item())
-        soft = present & (nb.to(torch.float64) >= n * soft_core)
-        part["soft_core"] = int(soft.sum().item())
-        part["soft_accessory"] = int((present & ~soft).sum().item())
+        part["exact_core"], part["exact_accessory"], part["soft_core"], part["soft_accessory"] = (int(v) for v in stats)
         out.append(part)
+    return out
+
+
+def _counts_from_labels(lab, kval: int) -> Dict[str, int]:
+    """Partition counts of one un-chunked run (rarefaction.py:163-177): label 0 = persistent, K - 1 = cloud, the rest
+    (shell classes and the undecided "S_") = shell."""
+    import torch
+    n = int(lab.numel())
+    pers = int((lab == 0).sum().item())
+    cloud = int((lab == kval - 1).sum().item())
+    return {"persistent": pers, "shell": n - pers - cloud, "cloud": cloud, "undefined": 0, "K": kval}
+
+
+def raref_batch(dp, indices: List[int], beta: float, sm_degree: float, free_dispersion: bool, kval: int) -> Dict[int, Dict[str, int]]:
+    """The samples ``indices`` (all of the same size, none above the chunk size, K fixed) as ONE exporter call and ONE batched
+    EM call instead of one fork-pool task each (rarefaction.py:707-716)."""
+    from . import engine
+    insts = dp.export([dp.columns(samples[i]) for i in indices], sm_degree)
+    jobs = [(it.inp, kval, it.beta_eff(beta), free_dispersion, 100) for it in insts]
+    runs = engine.nem_run_batch(jobs, flags=ppp._epilogue_flags(insts[0].D), want_params=False)
+    out = {}
+    for i, run in zip(indices, runs):
+        if not run.ok:
+            out[i] = {"persistent": "NA", "shell": "NA", "cloud": "NA", "undefined": "NA", "K": kval}
+            continue
+        lab, _ = engine.labels_device(run.T)
+        out[i] = _counts_from_labels(lab, kval)
     return out
 
 
@@ -194,12 +222,7 @@ def make_rarefaction_curve(pangenome, output: Path, tmpdir: Path = None, beta: f
             all_samples = [{by_name[n] for n in names} for names in payload[0]]
     logger.info(f"Done sampling genomes in the pan, there are {len(all_samples)} samples")
 
-    if arrays is None:
-        from .export_arrays import PangenomeArrays
-        stats_arrays = PangenomeArrays.from_pangenome(pangenome, "cpu")
-    else:
-        stats_arrays = arrays
-    samp_nb_per_part = sample_family_stats(stats_arrays, all_samples, soft_core)
+    samp_nb_per_part = sample_family_stats(arrays, all_samples, soft_core)
 
     global samples
     samples = all_samples
@@ -208,7 +231,19 @@ def make_rarefaction_curve(pangenome, output: Path, tmpdir: Path = None, beta: f
     # the per-sample counts are gathered at the end (the reference spreads them over a fork pool, rarefaction.py:707)
     mine = {}
     with ppp.local_instances():
-        for index in range(rank, len(samples), world):
+        my_indices = list(range(rank, len(samples), world))
+        if kval >= 3:
+            # K is fixed: samples of one size that fit a single NEM instance are exported and run as batches
+            by_size = {}
+            for index in my_indices:
+                if len(samples[index]) <= chunk_size:
+                    by_size.setdefault(len(samples[index]), []).append(index)
+            for size, idxs in by_size.items():
+                for b0 in range(0, len(idxs), RAREF_BATCH):
+                    mine.update(raref_batch(arrays, idxs[b0:b0 + RAREF_BATCH], beta, sm_degree, free_dispersion, kval))
+        for index in my_indices:
+            if index in mine:
+                continue
             counts, idx = launch_raref_nem((index, tmp_path, beta, sm_degree, free_dispersion, chunk_size, kval, krange, seed))
             mine[idx] = counts
     if world > 1:

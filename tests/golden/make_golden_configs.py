@@ -35,26 +35,7 @@ def digest(sp) -> str:
     return h.hexdigest()[:32]
 
 
-def write_files_fast(d: Path, X, rowptr, col, w):
-    """Same bytes as refnem.write_nem_files (partition.py:344-436 formats), vectorised for 10^7..10^8 cells."""
-    d.mkdir(parents=True, exist_ok=True)
-    N, D = X.shape
-    (d / "nem_file.str").write_text(f"S\t{N}\t{D}\n")
-    buf = np.full((N, 2 * D), ord("\t"), np.uint8)
-    buf[:, 0::2] = X + ord("0")
-    buf[:, -1] = ord("\n")
-    (d / "nem_file.dat").write_bytes(buf.tobytes())
-    with open(d / "nem_file.index", "w") as f:
-        f.write("".join(f"{i + 1}\tfam{i}\n" for i in range(N)))
-    w_text = [repr(round(float(v), 4)) for v in np.asarray(w, np.float64)]
-    with open(d / "nem_file.nei", "w") as f:
-        f.write("1\n")
-        for i in range(N):
-            a, b = int(rowptr[i]), int(rowptr[i + 1])
-            if b > a:
-                f.write("\t".join([str(i + 1), str(b - a)] + [str(int(j) + 1) for j in col[a:b]] + w_text[a:b]) + "\n")
-            else:
-                f.write(f"{i + 1}\t0\n")
+write_files_fast = refnem.write_nem_files_fast
 
 
 def _ref_one(args):

@@ -66,3 +66,18 @@ def mstep(X, T, free_disp):
         eps = np.repeat((iner.sum(1) / (D * nk)).astype(np.float32)[:, None], D, 1)
     pk = (nk / N).astype(np.float32)
     return mu, eps, pk, s1, nk
+
+
+def apply_votes_ref(codes, votes, validated, n_org, chunk_size):
+    """validate_family (partition.py:784-802) for a sequence of chunk label vectors ``codes`` [n_chunks, F] (0 = P, 1 = S,
+    2 = C, -1 = not in the chunk), chunk after chunk; ``votes`` [F, 4] (P, S, C, U) and ``validated`` [F] are updated in place."""
+    for row in codes:
+        for f in np.flatnonzero(row >= 0):
+            votes[f, row[f]] += 1
+            s_ = votes[f].sum()
+            m_ = votes[f].max()
+            if (s_ > n_org / chunk_size and m_ >= s_ * 0.5) or s_ > n_org:
+                if not validated[f]:
+                    if m_ < s_ * 0.5:
+                        votes[f, 3] = n_org
+                    validated[f] = True

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(raw, s), f"{s} declared in include/nemb200.h but not exported by libnemb200.so"
         assert s in engine.SIGNATURES, f"{s} has no ctypes signature in engine.SIGNATURES"
     assert set(engine.SIGNATURES) == set(syms)
-    assert engine.lib().nemb200_abi_version() == 1
+    assert engine.lib().nemb200_abi_version() == 2
 
 
 def test_gs_schedule_levels_respect_dependencies():

@@ -701,6 +701,43 @@ def test_parallel_float_chain_is_bit_exact(eng):
 
 
 @pytest.mark.gpu
+def test_parallel_double_term_chain_is_bit_exact(eng):
+    """The L and Z criteria (nem_alg.c:2826-2827) are float32 accumulators that receive DOUBLE terms, acc =
+    (float)((double)acc + x): parallel scheme against the sequential chain kernel and a numpy loop -- the constant term
+    -log K of the beta = 0 runs (systematic drift of the float accumulator), log-density sized terms, terms sitting next
+    to rounding ties, mixed signs, absorbed terms, infinities."""
+    rng = np.random.default_rng(12)
+
+    def seq(x):
+        acc = np.float32(0)
+        for v in x:
+            acc = np.float32(np.float64(acc) + v)
+        return acc
+
+    n = 70_000
+    tie = (rng.integers(1, 2 ** 20, n) + 0.5) * 2.0 ** -10          # exact half-ulp positions for sums around 2^13..2^14
+    cases = {
+        "constant -log 3": np.full(n, -np.log(3.0)),
+        "constant -log 20": np.full(n, -np.log(20.0)),
+        "log densities": -np.abs(rng.normal(300, 150, n)),
+        "near ties": np.where(rng.random(n) < 0.5, tie, tie * (1 + 2.0 ** -40)),
+        "mixed signs": rng.normal(0, 5, n),
+        "absorbed": rng.random(n) * 1e-9 + np.where(np.arange(n) == 0, 1e6, 0.0),
+        "minus infinity inside": np.where(np.arange(n) == 40_000, -np.inf, -rng.random(n)),
+        "zeros": np.zeros(n),
+        "one term": np.array([0.1]),
+    }
+    for name, x in cases.items():
+        x = x.astype(np.float64)
+        y = np.roll(x, 5) if len(x) > 5 else x
+        with np.errstate(invalid="ignore", over="ignore"):
+            a = eng.double_chain(x, y, parallel=False)
+            b = eng.double_chain(x, y, parallel=True)
+            assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes(), name
+            assert seq(x).tobytes() == b[0].tobytes(), name
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("K,fd", [(3, False), (6, True)])
 def test_high_degree_rows_match_strict_oracle(eng, K, fd):
     """Neighbour lists longer than the 8 entries the schedule-ordered graph copy keeps inline (sm_degree = 60: up to ~40
@@ -720,3 +757,35 @@ def test_high_degree_rows_match_strict_oracle(eng, K, fd):
         olab, _, _ = refnem.oracle_labels(o["T"])
         assert (lab.cpu().numpy() == olab).mean() >= 0.999
         assert abs(run.crit[3] - o["crit"][3]) <= 1e-5 * abs(o["crit"][3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", ["graph_K3", "graph_skd", "sweep_K7", "sweep_K20", "large_ring", "large_K12"])
+def test_device_resident_loop_equals_host_polled_driver(eng, shape, monkeypatch):
+    """The device-resident EM loop (nemb200_batch.inc: one launch per phase, convergence decided on the device, the host
+    one iteration behind) against the host-polled driver (NEMB200_NO_BATCH=1: one flag read per iteration): same kernels'
+    arithmetic, so posteriors, parameters, iteration counts and criteria must be identical."""
+    from ppanggolin_b200.synthetic import synth_pangenome_blocked
+    if shape.startswith("large"):
+        sp = synth_pangenome_blocked(12000, 50000, seed=3)      # 75 MB of bits: the streaming (ring) kernels
+        K, beta, fd, itermax, flags = (3 if shape == "large_ring" else 12), sp.beta_eff(2.5), False, 6, eng.EPI_LOGSPACE
+    else:
+        sp = synth_pangenome(4000, 300, seed=77)
+        K, beta, fd, itermax, flags = {"graph_K3": (3, sp.beta_eff(2.5), False, 100, eng.EPI_REF),
+                                       "graph_skd": (4, sp.beta_eff(2.5), True, 100, eng.EPI_REF),
+                                       "sweep_K7": (7, 0.0, False, 10, eng.EPI_REF),
+                                       "sweep_K20": (20, 0.0, False, 10, eng.EPI_REF)}[shape]
+    inp = eng.DeviceInput.from_numpy(sp.bits, sp.D, sp.rowptr, sp.col, sp.w)
+    monkeypatch.setenv("NEMB200_NO_BATCH", "1")
+    a = eng.nem_run_device(inp, K, beta, fd, itermax, flags=flags)
+    monkeypatch.delenv("NEMB200_NO_BATCH")
+    b = eng.nem_run_device(inp, K, beta, fd, itermax, flags=flags)
+    assert (a.status, a.n_iter, a.converged, a.n_levels) == (b.status, b.n_iter, b.converged, b.n_levels)
+    assert a.status == 0
+    Ta, Tb = a.T.cpu().numpy(), b.T.cpu().numpy()
+    if K <= 4:
+        assert np.array_equal(Ta, Tb)
+    else:   # fuzzy-row column sums are fp64 atomics over row slices: the slicing differs between the drivers
+        assert np.abs(Ta - Tb).max() <= 1e-6
+    assert np.array_equal(a.mu, b.mu) and np.allclose(a.eps, b.eps, rtol=1e-6) and np.allclose(a.pk, b.pk, rtol=1e-6)
+    assert a.crit[3] == pytest.approx(b.crit[3], rel=1e-9)

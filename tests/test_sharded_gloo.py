@@ -68,11 +68,12 @@ def test_two_rank_gloo_run_equals_single_process(tmp_path, N):
 
 
 def _chunk_votes(rank, world, port, F, n_samples, out):
-    """Chunk samples dealt out to the ranks (partition._chunk_round) with a deterministic stand-in for the GPU runs."""
+    """Chunk samples dealt out to the ranks (workflow.deal_round) with a deterministic stand-in for the GPU runs."""
     for p in (str(ROOT), str(ROOT / "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
-    from ppanggolin_b200.nem import partition as ppp
+    import npref
+    from ppanggolin_b200.nem import workflow
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     if world > 1:
@@ -89,16 +90,17 @@ def _chunk_votes(rank, world, port, F, n_samples, out):
                 res[j] = torch.where(present, code, torch.tensor(-1, dtype=torch.int8))
         return res
 
-    votes = torch.zeros((F, 4), dtype=torch.long)
-    validated = torch.zeros(F, dtype=torch.bool)
-    old = ppp.CHUNK_BATCH
-    ppp.CHUNK_BATCH = 3          # several groups, the last one ragged
+    votes = np.zeros((F, 4), np.int64)
+    validated = np.zeros(F, bool)
+    old = workflow.CHUNK_BATCH
+    workflow.CHUNK_BATCH = 3          # several groups, the last one ragged
     try:
-        ppp._chunk_round(list(range(n_samples)), F, torch.device("cpu"), fake_batch, votes, validated, n_org, chunk_size)
+        workflow.deal_round(list(range(n_samples)), F, torch.device("cpu"), fake_batch,
+                            lambda codes: npref.apply_votes_ref(codes.numpy(), votes, validated, n_org, chunk_size))
     finally:
-        ppp.CHUNK_BATCH = old
-    np.save(f"{out}/votes_{world}_{rank}.npy", votes.numpy())
-    np.save(f"{out}/validated_{world}_{rank}.npy", validated.numpy())
+        workflow.CHUNK_BATCH = old
+    np.save(f"{out}/votes_{world}_{rank}.npy", votes)
+    np.save(f"{out}/validated_{world}_{rank}.npy", validated)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -133,6 +135,7 @@ def _sample_sync(rank, world, port, out):
     import random
     from collections import Counter
     from ppanggolin_b200.nem import partition as ppp
+    from ppanggolin_b200.nem import workflow
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -141,11 +144,15 @@ def _sample_sync(rank, world, port, out):
     random.shuffle(orgs)
     chosen = ppp._same_on_all_ranks(set(random.sample(orgs, 20)), orgs)
     assert all(o in orgs for o in chosen)     # this rank's own objects, not unpickled copies
-    ppp.samples = []
-    counts = Counter({o: 0 for o in orgs})
-    ppp._draw_samples_synced(orgs, 10, counts, 2)
-    rec = {"chosen": sorted(o.name for o in chosen), "samples": [sorted(o.name for o in s) for s in ppp.samples],
-           "counts": sorted((o.name, c) for o, c in counts.items())}
+    # the array workflow draws genome COLUMNS: the K-selection sample and the chunk samples of rank 0 reach every rank
+    cols = list(range(57))
+    random.shuffle(cols)
+    k_sample = workflow._bcast_from_rank0(random.sample(cols, 20))
+    samples = []
+    counts = {c: 0 for c in cols}
+    workflow.draw_chunks(cols, 10, counts, 2, samples)
+    rec = {"chosen": sorted(o.name for o in chosen), "k_sample": sorted(k_sample), "samples": samples,
+           "counts": sorted(counts.items())}
     with open(f"{out}/sync_{rank}.json", "w") as f:
         json.dump(rec, f)
     with ppp.local_instances():               # nested callers switch the dealing-out off
@@ -160,5 +167,6 @@ def test_random_genome_samples_are_the_same_on_every_rank(tmp_path):
     mp.spawn(_sample_sync, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     a = json.load(open(tmp_path / "sync_0.json")); b = json.load(open(tmp_path / "sync_1.json"))
     assert a == b
-    assert len(a["chosen"]) == 20 and len(a["samples"]) >= 10 and all(len(s) == 10 for s in a["samples"])
+    assert len(a["chosen"]) == 20 and len(a["k_sample"]) == 20
+    assert len(a["samples"]) >= 10 and all(len(s) == 10 and s == sorted(s) for s in a["samples"])
     assert all(c >= 2 for _, c in a["counts"])
