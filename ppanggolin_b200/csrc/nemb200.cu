@@ -355,6 +355,14 @@ static int launch_classify(nemb200_plan* pl, const float* T, cudaStream_t st) {
 }
 template <int KB>
 static int launch_fuzzy(nemb200_plan* pl, const uint32_t* bits, const float* T, cudaStream_t st) {
+  const char* mma_env = getenv("NEMB200_FUZZY_MMA");
+  if (KB >= 8 && !(mma_env && atoi(mma_env) == 0)) {   // more than 4 classes: fp64 tensor cores (k_mstep_fuzzy_mma)
+    constexpr int KT = KB / 8 < 1 ? 1 : KB / 8;
+    const int col_tiles = (pl->Ws + 7) / 8;
+    k_mstep_fuzzy_mma<KT><<<dim3(col_tiles, 128), 256, 0, st>>>(bits, pl->Ws, pl->K, pl->D, pl->offsets, pl->perm, T, pl->fsum, pl->Dpad);
+    CK(cudaGetLastError());
+    return 0;
+  }
   const int cols_per_cta = 256 * FuzzyCfg<KB>::WPT;
   const int col_tiles = (pl->Dpad + cols_per_cta - 1) / cols_per_cta;
   int per_sm = 0;
@@ -867,10 +875,10 @@ static void chain_jobs(nemb200_plan* pl, int64_t N, int n_regions, const unsigne
   const size_t nch_lz = ((size_t)N + kCcChunk - 1) / kCcChunk + 1;
   dg->terms = pl->crit_dense; dg->total_ptr = pl->crit_offsets + n_regions;
   dg->recR = pl->crit_rec; dg->recMn = pl->crit_rec + nch * 2; dg->recMx = pl->crit_rec + nch * 4; dg->recFlag = pl->crit_recbad;
-  dg->state = pl->crit_state; dg->out2 = pl->crit4; dg->run_state = run_state;
+  dg->state = pl->crit_state; dg->out2 = pl->crit4; dg->run_state = run_state; dg->double_terms = 0;
   lz->terms = pl->crit_lz; lz->total_ptr = pl->crit_nrows;
   lz->recR = pl->crit_rec_lz; lz->recMn = pl->crit_rec_lz + nch_lz * 2; lz->recMx = pl->crit_rec_lz + nch_lz * 4; lz->recFlag = pl->crit_recbad_lz;
-  lz->state = pl->crit_state_lz; lz->out2 = pl->crit4 + 2; lz->run_state = run_state;
+  lz->state = pl->crit_state_lz; lz->out2 = pl->crit4 + 2; lz->run_state = run_state; lz->double_terms = 1;
 }
 
 static int criteria_enqueue(nemb200_plan* pl, int64_t N, const double* logf, const float* T, const int32_t* rowptr,
@@ -910,8 +918,8 @@ static int criteria_enqueue(nemb200_plan* pl, int64_t N, const double* logf, con
       k_crit_chain<TermsF2><<<1, 64, 0, st>>>(TermsF2{(const float2*)dg.terms}, dg.total_ptr, dg.out2);
       k_crit_chain<TermsD2><<<1, 64, 0, st>>>(TermsD2{(const double2*)lz.terms}, lz.total_ptr, lz.out2);
     } else {
-      k_crit_chain_par<TermsF2><<<1, 1024, 0, st>>>(nullptr, dg);
-      k_crit_chain_par<TermsD2><<<1, 1024, 0, st>>>(nullptr, lz);
+      k_crit_chain_par<<<1, kCcTpb, 0, st>>>(nullptr, dg);     // (batched runs put both jobs of all instances in one launch)
+      k_crit_chain_par<<<1, kCcTpb, 0, st>>>(nullptr, lz);
     }
     CK(cudaGetLastError());
   }
@@ -978,8 +986,8 @@ extern "C" int nemb200_selftest_float_chain(const float* d, const float* g, int6
     const int* tot = offs + 1;
     if (parallel) {
       long long *rR = (long long*)p_rec;
-      CcJob job{p_dense, tot, rR, rR + nch * 2, rR + nch * 4, (int*)p_bad, stp, out, nullptr};
-      k_crit_chain_par<TermsF2><<<1, 1024>>>(nullptr, job);
+      CcJob job{p_dense, tot, rR, rR + nch * 2, rR + nch * 4, (int*)p_bad, stp, out, nullptr, 0};
+      k_crit_chain_par<<<1, kCcTpb>>>(nullptr, job);
     } else {
       k_crit_chain<TermsF2><<<1, 64>>>(dense, tot, out);
     }
@@ -1022,8 +1030,8 @@ extern "C" int nemb200_selftest_double_chain(const double* l, const double* z, i
     const int* totp = tot;
     if (parallel) {
       long long *rR = (long long*)p_rec;
-      CcJob job{p_dense, totp, rR, rR + nch * 2, rR + nch * 4, (int*)p_bad, stp, out, nullptr};
-      k_crit_chain_par<TermsD2><<<1, 1024>>>(nullptr, job);
+      CcJob job{p_dense, totp, rR, rR + nch * 2, rR + nch * 4, (int*)p_bad, stp, out, nullptr, 1};
+      k_crit_chain_par<<<1, kCcTpb>>>(nullptr, job);
     } else {
       k_crit_chain<TermsD2><<<1, 64>>>(dense, totp, out);
     }

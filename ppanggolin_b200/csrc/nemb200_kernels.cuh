@@ -786,9 +786,18 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
           if (b + gtotal < e) sweep_finish<GS>(a, p1, sub, wmax);   // grid-uniform condition
           idx += 2 * gtotal;
         }
-        for (long long idx0 = idx - grp; idx0 < e; idx0 += gtotal) {   // idx0: the warp's first slot (warp-uniform loop)
-          const SweepPre<GS> p = sweep_preload_slot<GS>(a, idx0 + grp, idx0 + grp < e, sub);
-          sweep_finish<GS>(a, p, sub, wmax);
+        // the rest of the level, software-pipelined: the graph side of the group's next row (one L2 round trip that does
+        // not depend on anything this sweep writes) is in flight while the current row's posteriors are gathered
+        long long idx0 = idx - grp;                                    // the warp's first slot (warp-uniform loop)
+        if (idx0 < e) {
+          SweepPre<GS> cur = sweep_preload_slot<GS>(a, idx0 + grp, idx0 + grp < e, sub);
+          for (; idx0 < e; idx0 += gtotal) {
+            const long long nx = idx0 + gtotal;
+            SweepPre<GS> nxt = cur;
+            if (nx < e) nxt = sweep_preload_slot<GS>(a, nx + grp, nx + grp < e, sub);
+            sweep_finish<GS>(a, cur, sub, wmax);
+            cur = nxt;
+          }
         }
         L++; b = e; e = e_next;
       }
@@ -1381,6 +1390,106 @@ k_mstep_fuzzy(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int
   mstep_fuzzy_body<KB>(bits, Ws, K, D, offsets, perm, T, fsum, Dpad);
 }
 
+// ---- fuzzy-row sums on the FP64 tensor cores ---------------------------------------------------------------------------
+// fsum[k][d] = sum_i T[i][k] x[i][d] over the fuzzy rows is a (K x n_fuzzy) . (n_fuzzy x D) product; in the K-selection
+// sweep nearly every row is fuzzy and K goes up to 20, where the predicated-add kernel above issues K fp64 adds per
+// (row, column) whether the bit is set or not -- 4x the fp64 pipe's bound (measured: 392 us per iteration for the four
+// K = 17..20 candidates of BASELINE configs[2], half of the whole sweep).  DMMA (mma.sync m8n8k4, f64: the only FP64
+// tensor-core instruction -- tcgen05 has no f64 kind) keeps the exact fp64 accumulation: A = 8 classes x 4 rows of
+// posteriors, B = 4 rows x 8 columns of matrix bits expanded to 0.0 / 1.0, C = 8 x 8 fp64.  A warp owns one 32-column
+// word (4 column tiles) and all class tiles; rows are staged in shared memory 64 at a time like in the kernel above.
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int KT /*class tiles of 8*/>
+__device__ __forceinline__ void
+mstep_fuzzy_mma_body(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int* __restrict__ offsets,
+                     const int* __restrict__ perm, const float* __restrict__ T, double* __restrict__ fsum /*[K][Dpad]*/, int Dpad) {
+  constexpr int KP = KT * 8 + ((KT & 1) ? 12 : 4);   // row pitch in doubles, = 4 mod 16: the 16 lanes of a half-warp hit 16 banks
+  constexpr int XW = 8;                              // 32-bit words per row that the CTA's 8 warps look at
+  __shared__ __align__(16) double s_t[kFzRows][KP];
+  __shared__ __align__(16) uint32_t s_x[kFzRows][XW];
+  const int f0 = offsets[2 * K], f1 = offsets[2 * K + 1];   // the fuzzy bucket
+  const int nf = f1 - f0;
+  const long long S = min((long long)gridDim.y, max(1LL, ((long long)nf + kFzRows - 1) / kFzRows));
+  if (blockIdx.y >= S) return;
+  const int lo = f0 + (int)((long long)nf * blockIdx.y / S), hi = f0 + (int)((long long)nf * (blockIdx.y + 1) / S);
+  if (lo >= hi) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;            // fragment coordinates: g = class (A) / column (B) index, t4 = row of the quad
+  const int cta_word0 = blockIdx.x * XW;
+  const int word = cta_word0 + wid;
+  const int ktiles = min(KT, (K + 7) >> 3);
+  double acc[KT][4][2];
+#pragma unroll
+  for (int mt = 0; mt < KT; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+  for (int base = lo; base < hi; base += kFzRows) {
+    const int n = min(kFzRows, hi - base);
+    const int n4 = (n + 3) & ~3;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n4 * (KT * 8 + XW); t += blockDim.x) {
+      if (t < n4 * KT * 8) {
+        const int r = t / (KT * 8), k = t - r * (KT * 8);
+        double v = 0.0;
+        if (r < n && k < K) v = (double)T[(size_t)perm[base + r] * K + k];
+        s_t[r][k] = v;                                // rows past n are zero: they add nothing
+      } else {
+        const int u = t - n4 * KT * 8;
+        const int r = u / XW, q = u - r * XW;
+        const int wq = cta_word0 + q;
+        s_x[r][q] = (r < n && wq < Ws) ? __ldg(bits + (size_t)perm[base + r] * Ws + wq) : 0u;
+      }
+    }
+    __syncthreads();
+    if (word < Ws) {
+#pragma unroll 2
+      for (int r0 = 0; r0 < n4; r0 += 4) {
+        const uint32_t x = s_x[r0 + t4][wid];
+        if (__any_sync(0xffffffffu, x != 0u)) {        // an all-zero quad of this word adds nothing
+          double b[4];
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) b[nt] = ((x >> (nt * 8 + g)) & 1u) ? 1.0 : 0.0;
+#pragma unroll
+          for (int mt = 0; mt < KT; mt++) {
+            if (mt < ktiles) {
+              const double a = s_t[r0 + t4][mt * 8 + g];
+#pragma unroll
+              for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a, b[nt]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (word < Ws) {
+#pragma unroll
+    for (int mt = 0; mt < KT; mt++) {
+      const int k = mt * 8 + g;                         // C fragment: row = class g, columns 2 t4, 2 t4 + 1 of the tile
+      if (mt < ktiles && k < K) {
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int d = word * 32 + nt * 8 + t4 * 2 + c;
+            const double v = acc[mt][nt][c];
+            if (d < D && v != 0.0) atomicAdd(&fsum[(size_t)k * Dpad + d], v);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256)
+k_mstep_fuzzy_mma(const uint32_t* __restrict__ bits, int Ws, int K, int D, const int* __restrict__ offsets,
+                  const int* __restrict__ perm, const float* __restrict__ T, double* __restrict__ fsum, int Dpad) {
+  mstep_fuzzy_mma_body<KT>(bits, Ws, K, D, offsets, perm, T, fsum, Dpad);
+}
+
 // Parameters from the column statistics.  grid = (column chunks, K); every CTA handles kFinCols columns of one class:
 // centres (weighted median of a 0/1 column, nem_mod.c:1417-1474), inertia (nem_mod.c:1641-1699), centre bit planes and,
 // for "skd", the per-column dispersion and log-odds.  The last CTA of a class to finish (ticket counter) adds the chunk
@@ -1811,7 +1920,36 @@ __device__ __forceinline__ bool cc_binade(float s, int& E) {   // normal, non-ze
   return true;
 }
 
-// One CTA (32 warps) per pair of chains: the rounds are separated by block barriers, so a batch of instances (blockIdx.x =
+// rn_u(x) / u for u = 2^Eu, as an integer, by integer arithmetic on the bits of x (a double; float terms are exact in it):
+// x = +-M 2^e with a 53-bit M.  `needseq` is raised for what the integer shortcut must not decide: an exact rounding tie
+// (round-to-even looks at the running sum), for double terms also anything within 2^-26 u of a tie (where the double
+// rounding of fl32(fl64(s + x)) could matter), a term of 2^30 u or more, an infinity or a NaN.
+__device__ __forceinline__ long long cc_round_units(double x, int Eu, bool double_terms, bool& needseq) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+  const int ex = (int)((bits >> 52) & 0x7ffu);
+  const unsigned long long frac = bits & 0xfffffffffffffULL;
+  if (ex == 0x7ff) { needseq = true; return 0; }
+  if (ex == 0 && frac == 0) return 0;
+  const unsigned long long M = ex ? (frac | (1ULL << 52)) : frac;
+  const int e = (ex ? ex : 1) - 1075;                    // x = +-M 2^e
+  if (ex - 1023 - Eu >= 30) { needseq = true; return 0; }
+  const int sh = e - Eu;
+  long long r;
+  if (sh >= 0) {
+    r = (long long)(M << sh);
+  } else {
+    const int sdown = -sh;
+    if (sdown >= 63) return 0;                           // |x| < u / 2^9: rounds to zero, far from a tie
+    const unsigned long long fl = M >> sdown, rem = M & ((1ULL << sdown) - 1ULL), half = 1ULL << (sdown - 1);
+    const unsigned long long dist = rem > half ? rem - half : half - rem;
+    const unsigned long long window = double_terms ? (half >> 25) : 0ULL;
+    if (dist <= window && (dist == 0 || double_terms)) needseq = true;
+    r = (long long)(fl + (rem > half ? 1ULL : 0ULL));
+  }
+  return (bits >> 63) ? -r : r;
+}
+
+// One CTA (16 warps) per pair of chains: the rounds are separated by block barriers, so a batch of instances (blockIdx.x =
 // job) runs all its chains side by side, and a round costs the window's records (32 chunks per pass of the CTA) plus the walk.
 struct CcJob {
   const void* terms;            // float2* (D, G: compacted terms) or double2* (L, Z: one pair per row)
@@ -1821,13 +1959,11 @@ struct CcJob {
   CcState* state;
   double* out2;                 // the two sums
   const unsigned* run_state;    // batched runs: kSt* words of the instance (a failed run is skipped); may be null
+  int double_terms;             // 0: float2 terms (D, G), 1: double2 terms (L, Z)
 };
 
 template <class Terms>
-__global__ void __launch_bounds__(1024)
-k_crit_chain_par(const CcJob* __restrict__ jobs, CcJob job0) {
-  const CcJob job = jobs != nullptr ? jobs[blockIdx.x] : job0;
-  if (job.run_state != nullptr && job.run_state[kStStatus] != 0u) return;
+__device__ __forceinline__ void cc_chain_cta(const CcJob& job) {
   Terms dense{reinterpret_cast<decltype(Terms::p)>(job.terms)};
   long long* __restrict__ recR = job.recR; long long* __restrict__ recMn = job.recMn; long long* __restrict__ recMx = job.recMx;
   int* __restrict__ recFlag = job.recFlag;
@@ -1870,7 +2006,7 @@ k_crit_chain_par(const CcJob* __restrict__ jobs, CcJob job0) {
     int E0 = 0, E1 = 0;
     const bool ok0 = cc_binade(s0, E0), ok1 = cc_binade(s1, E1);
     const int first = min(cur0, cur1);
-    const int last = min(nchunks, max(cur0 < nchunks ? 2 * cur0 + 64 : 0, cur1 < nchunks ? 2 * cur1 + 64 : 0));
+    const int last = min(nchunks, max(cur0 < nchunks ? 2 * cur0 + 32 : 0, cur1 < nchunks ? 2 * cur1 + 32 : 0));
     for (int c = first + warp_global; c < last; c += nwarps) {
       // lane l owns the 16 consecutive terms [16 l, 16 l + 16) of the chunk: a lane-local running sum with its extremes,
       // then one scan over the 32 lane totals
@@ -1894,11 +2030,7 @@ k_crit_chain_par(const CcJob* __restrict__ jobs, CcJob job0) {
           const double x = ch ? vy[j] : vx[j];
           nz = nz || (x != 0.0);
           if (okc) {
-            const double q = scalbn(x, sh);                                // x / u, exact
-            const double fr = fabs(q - trunc(q));
-            const bool tie = Terms::kDouble ? (fabs(fr - 0.5) < 1.4901161193847656e-08) : (fr == 0.5);   // 2^-26 around the tie
-            needseq = needseq || tie || !(fabs(q) < 1073741824.0);         // tie; huge, inf or nan term
-            pre += (fabs(q) < 1073741824.0) ? (long long)rint(q) : 0;
+            pre += cc_round_units(x, -sh, Terms::kDouble, needseq);        // u = 2^(E - 23)
             if (t_lane + j < t_end) { lmn = min(lmn, pre); lmx = max(lmx, pre); }
           }
         }
@@ -2004,6 +2136,15 @@ k_crit_chain_par(const CcJob* __restrict__ jobs, CcJob job0) {
     __syncthreads();
   }
   if (threadIdx.x == 0) { out4[0] = (double)vs->s[0]; out4[1] = (double)vs->s[1]; }
+}
+
+constexpr int kCcTpb = 512;      // 16 warps: the records of a chunk hold 32 doubles per lane, 1024 threads would spill
+__global__ void __launch_bounds__(kCcTpb)
+k_crit_chain_par(const CcJob* __restrict__ jobs, CcJob job0) {
+  const CcJob job = jobs != nullptr ? jobs[blockIdx.x] : job0;
+  if (job.run_state != nullptr && job.run_state[kStStatus] != 0u) return;
+  if (job.double_terms) cc_chain_cta<TermsD2>(job);
+  else cc_chain_cta<TermsF2>(job);
 }
 
 // D (warp 0) and G (warp 1) re-accumulated in float32 in the reference's order.  The warp loads 32 terms at a time
@@ -2197,6 +2338,13 @@ __global__ void __launch_bounds__(256) k_b_fuzzy(const BatchInst* __restrict__ B
   const BatchInst& I = B[blockIdx.z];
   if (!b_active(I)) return;
   mstep_fuzzy_body<KB>(I.bits, I.Ws, I.K, I.D, I.offsets, I.perm, I.T[(I.c0 + s - 1) & 1], I.fsum, I.Dpad);
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256) k_b_fuzzy_mma(const BatchInst* __restrict__ B, int s) {
+  const BatchInst& I = B[blockIdx.z];
+  if (!b_active(I)) return;
+  mstep_fuzzy_mma_body<KT>(I.bits, I.Ws, I.K, I.D, I.offsets, I.perm, I.T[(I.c0 + s - 1) & 1], I.fsum, I.Dpad);
 }
 
 __global__ void __launch_bounds__(256) k_b_finalize(const BatchInst* __restrict__ B) {

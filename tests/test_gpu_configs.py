@@ -186,8 +186,8 @@ def test_keep_tmp_files_chunked_path_equals_array_workflow(eng, tmp_path):
     from ppanggolin_b200.nem import partition as part
     g = load_partition("chunked")
     res = []
+    pan = minipan.build_from_layouts(g["layouts"], g["n_fam"])   # ONE object graph: the genome set iterates in the same order
     for keep in (False, True):
-        pan = minipan.build_from_layouts(g["layouts"], g["n_fam"])
         part.samples = []
         random.seed(99)
         out = tmp_path / f"out{int(keep)}"
