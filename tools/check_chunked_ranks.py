@@ -5,6 +5,7 @@ draws other samples, so its class counts are close, not identical).
   python tools/check_chunked_ranks.py                      # single process: prints the reference digest
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_chunked_ranks.py"""
 import hashlib
+import json
 import os
 import random
 import sys
@@ -25,18 +26,6 @@ rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE",
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
-if os.environ.get("CHUNK_DEBUG"):
-    _orig = part._apply_chunk_votes
-    _n = [0]
-
-    def _logged(votes, validated, codevec, n_org, chunk_size):
-        h = hashlib.sha256(codevec.cpu().numpy().tobytes()).hexdigest()[:10]
-        if rank == 0:
-            print(f"DBG world {world} chunk {_n[0]} codevec {h} present {int((codevec >= 0).sum())}", flush=True)
-        _n[0] += 1
-        return _orig(votes, validated, codevec, n_org, chunk_size)
-
-    part._apply_chunk_votes = _logged
 junk = [object() for _ in range(rank * 100003)]   # different heap layouts per rank: set iteration orders of objects differ
 layouts = mg.make_layouts(3000, 240, 31)
 pan = minipan.build_from_layouts(layouts, 3000)
@@ -54,6 +43,7 @@ for name, kw in cases:
         part.partition(pan, output=Path(td), tmpdir=Path(td), cpu=1, disable_bar=True, seed=42, beta=2.5, **kw)
     labels = "".join(f"{f.name}:{f.partition};" for f in sorted(pan.gene_families, key=lambda f: f.name))
     digest = hashlib.sha256(labels.encode()).hexdigest()[:16]
+    print("CHECK " + json.dumps({"world": world, "rank": rank, "case": name, "digest": digest}), flush=True)
     print(f"world {world} rank {rank} {name}: instances {len(part.samples)} K {pan.parameters['partition']['# final nb of partitions']} "
           f"counts {dict(Counter(f.partition[:1] for f in pan.gene_families))} digest {digest}", flush=True)
 from ppanggolin_b200.nem import rarefaction as raref
@@ -64,6 +54,7 @@ with tempfile.TemporaryDirectory() as td:
     recs = raref.make_rarefaction_curve(pan, output=None, tmpdir=Path(td), depth=2, min_sampling=20, max_sampling=40, chunk_size=30,
                                         kval=3, disable_bar=True)
 text = ";".join(",".join(f"{k}={r[k]}" for k in sorted(r)) for r in recs)
+print("CHECK " + json.dumps({"world": world, "rank": rank, "case": "rarefaction", "digest": hashlib.sha256(text.encode()).hexdigest()[:16]}), flush=True)
 print(f"world {world} rank {rank} rarefaction: {len(recs)} samples digest {hashlib.sha256(text.encode()).hexdigest()[:16]}", flush=True)
 if world > 1:
     dist.barrier()
