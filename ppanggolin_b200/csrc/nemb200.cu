@@ -185,7 +185,7 @@ struct nemb200_plan {
   float* crit_dense = nullptr;    // the regions' terms, contiguous and in order
   double* crit_lz = nullptr;      // [N_total][2] per-row (log f_i, -log z_i): terms of the float32 L and Z sums
   int* crit_nrows = nullptr;      // [1] number of rows of the last criteria call (term count of the L / Z chains)
-  long long* crit_rec = nullptr;  // k_crit_chain_par, D / G chains: per (chunk, chain) records, 3 x int64 + flag
+  long long* crit_rec = nullptr;  // k_cc_*, D / G chains: per (chunk, chain) records (3 x int64 + fp64 chunk sum; flag + predicted binade)
   int* crit_recbad = nullptr;
   CcState* crit_state = nullptr;
   long long* crit_rec_lz = nullptr;   // the same for the L / Z chains (their CTA runs beside the D / G one)
@@ -236,9 +236,9 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   pl->crit_nrows = ar.take<int>(1);
   {
     const size_t nch = ((size_t)pl->N_total * K + kCcChunk - 1) / kCcChunk + 1;
-    pl->crit_rec = ar.take<long long>(nch * 2 * 3); pl->crit_recbad = ar.take<int>(nch * 2); pl->crit_state = ar.take<CcState>(1);
+    pl->crit_rec = ar.take<long long>(nch * 2 * 4); pl->crit_recbad = ar.take<int>(nch * 2 * 2); pl->crit_state = ar.take<CcState>(1);
     const size_t nch_lz = ((size_t)pl->N_total + kCcChunk - 1) / kCcChunk + 1;
-    pl->crit_rec_lz = ar.take<long long>(nch_lz * 2 * 3); pl->crit_recbad_lz = ar.take<int>(nch_lz * 2); pl->crit_state_lz = ar.take<CcState>(1);
+    pl->crit_rec_lz = ar.take<long long>(nch_lz * 2 * 4); pl->crit_recbad_lz = ar.take<int>(nch_lz * 2 * 2); pl->crit_state_lz = ar.take<CcState>(1);
   }
   if (pl->with_run_buffers) {
     pl->run_logf = ar.take<double>(N * K); pl->run_Ta = ar.take<float>(N * K); pl->run_Tb = ar.take<float>(N * K);
@@ -590,7 +590,7 @@ static int launch_density_ring(nemb200_plan* pl, const uint32_t* bits, double* l
   if (blocks < 1) blocks = 1;
   kern<<<(unsigned)blocks, TPB, smem, st>>>((const uint4*)bits, pl->N_local, W4, kc, G, (const uint4*)pl->P.m1 + (size_t)k0 * W4,
                                             (const uint4*)pl->P.valid + (size_t)k0 * W4, pl->P.L + k0, pl->P.B + k0, pl->P.has_half,
-                                            logf + k0, pl->K);
+                                            logf + k0, pl->K, pl->D);
   CK(cudaGetLastError());
   *done = true;
   return 0;
@@ -869,15 +869,27 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
   return NEMB200_OK;
 }
 
+// the four launches of the exact parallel float chains (nemb200_kernels.cuh, k_cc_*) for `njobs` jobs of at most max_terms terms
+static void chain_launch(const CcJob* jobs_dev, const CcJob& job0, int njobs, size_t max_terms, cudaStream_t st) {
+  const size_t nch = (max_terms + kCcChunk - 1) / kCcChunk + 1;
+  const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((nch + 7) / 8, (size_t)std::max(1, num_sms() * 4 / njobs)));
+  k_cc_sums<<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev, job0);
+  k_cc_predict<<<dim3(1, njobs), 64, 0, st>>>(jobs_dev, job0);
+  k_cc_records<<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev, job0);
+  k_cc_walk<<<dim3(1, njobs), 64, 0, st>>>(jobs_dev, job0);
+}
+
 // the two chain jobs of a plan's criteria: D / G over the compacted float terms, L / Z over the per-row double terms
 static void chain_jobs(nemb200_plan* pl, int64_t N, int n_regions, const unsigned* run_state, CcJob* dg, CcJob* lz) {
   const size_t nch = ((size_t)N * pl->K + kCcChunk - 1) / kCcChunk + 1;
   const size_t nch_lz = ((size_t)N + kCcChunk - 1) / kCcChunk + 1;
   dg->terms = pl->crit_dense; dg->total_ptr = pl->crit_offsets + n_regions;
   dg->recR = pl->crit_rec; dg->recMn = pl->crit_rec + nch * 2; dg->recMx = pl->crit_rec + nch * 4; dg->recFlag = pl->crit_recbad;
+  dg->csum = (double*)(pl->crit_rec + nch * 6); dg->epred = pl->crit_recbad + nch * 2;
   dg->state = pl->crit_state; dg->out2 = pl->crit4; dg->run_state = run_state; dg->double_terms = 0;
   lz->terms = pl->crit_lz; lz->total_ptr = pl->crit_nrows;
   lz->recR = pl->crit_rec_lz; lz->recMn = pl->crit_rec_lz + nch_lz * 2; lz->recMx = pl->crit_rec_lz + nch_lz * 4; lz->recFlag = pl->crit_recbad_lz;
+  lz->csum = (double*)(pl->crit_rec_lz + nch_lz * 6); lz->epred = pl->crit_recbad_lz + nch_lz * 2;
   lz->state = pl->crit_state_lz; lz->out2 = pl->crit4 + 2; lz->run_state = run_state; lz->double_terms = 1;
 }
 
@@ -918,8 +930,8 @@ static int criteria_enqueue(nemb200_plan* pl, int64_t N, const double* logf, con
       k_crit_chain<TermsF2><<<1, 64, 0, st>>>(TermsF2{(const float2*)dg.terms}, dg.total_ptr, dg.out2);
       k_crit_chain<TermsD2><<<1, 64, 0, st>>>(TermsD2{(const double2*)lz.terms}, lz.total_ptr, lz.out2);
     } else {
-      k_crit_chain_par<<<1, kCcTpb, 0, st>>>(nullptr, dg);     // (batched runs put both jobs of all instances in one launch)
-      k_crit_chain_par<<<1, kCcTpb, 0, st>>>(nullptr, lz);
+      chain_launch(nullptr, dg, 1, (size_t)N * pl->K, st);     // (batched runs put both jobs of all instances in one launch)
+      chain_launch(nullptr, lz, 1, (size_t)N, st);
     }
     CK(cudaGetLastError());
   }
@@ -967,7 +979,7 @@ extern "C" int nemb200_selftest_float_chain(const float* d, const float* g, int6
   std::vector<float2> h((size_t)std::max<int64_t>(n, 1));
   for (int64_t i = 0; i < n; i++) h[(size_t)i] = make_float2(d[i], g[i]);
   const size_t nch = ((size_t)n + kCcChunk - 1) / kCcChunk + 1;
-  const size_t b_dense = h.size() * sizeof(float2), b_rec = nch * 2 * 3 * sizeof(long long), b_bad = nch * 2 * sizeof(int);
+  const size_t b_dense = h.size() * sizeof(float2), b_rec = nch * 2 * 4 * sizeof(long long), b_bad = nch * 2 * 2 * sizeof(int);
   void *p_dense = nullptr, *p_rec = nullptr, *p_bad = nullptr, *p_misc = nullptr;
   int rc;
   if ((rc = cached_malloc(&p_dense, b_dense))) return rc;
@@ -986,8 +998,8 @@ extern "C" int nemb200_selftest_float_chain(const float* d, const float* g, int6
     const int* tot = offs + 1;
     if (parallel) {
       long long *rR = (long long*)p_rec;
-      CcJob job{p_dense, tot, rR, rR + nch * 2, rR + nch * 4, (int*)p_bad, stp, out, nullptr, 0};
-      k_crit_chain_par<<<1, kCcTpb>>>(nullptr, job);
+      CcJob job{p_dense, tot, rR, rR + nch * 2, rR + nch * 4, (double*)(rR + nch * 6), (int*)p_bad, (int*)p_bad + nch * 2, stp, out, nullptr, 0};
+      chain_launch(nullptr, job, 1, (size_t)n, nullptr);
     } else {
       k_crit_chain<TermsF2><<<1, 64>>>(dense, tot, out);
     }
@@ -997,7 +1009,7 @@ extern "C" int nemb200_selftest_float_chain(const float* d, const float* g, int6
   if (e == cudaSuccess && parallel && getenv("NEMB200_CHAIN_DEBUG")) {
     CcState hs;
     if (cudaMemcpy(&hs, stp, sizeof hs, cudaMemcpyDeviceToHost) == cudaSuccess)
-      fprintf(stderr, "float chain: %lld terms, %zu chunks, %d rounds, chunks added sequentially: %d / %d\n", (long long)n, nch - 1, hs.rounds,
+      fprintf(stderr, "float chain: %lld terms, %zu chunks, chunks added sequentially: %d / %d\n", (long long)n, nch - 1,
               hs.seq_chunks[0], hs.seq_chunks[1]);
   }
   release();
@@ -1011,7 +1023,7 @@ extern "C" int nemb200_selftest_double_chain(const double* l, const double* z, i
   std::vector<double2> h((size_t)std::max<int64_t>(n, 1));
   for (int64_t i = 0; i < n; i++) h[(size_t)i] = make_double2(l[i], z[i]);
   const size_t nch = ((size_t)n + kCcChunk - 1) / kCcChunk + 1;
-  const size_t b_dense = h.size() * sizeof(double2), b_rec = nch * 2 * 3 * sizeof(long long), b_bad = nch * 2 * sizeof(int);
+  const size_t b_dense = h.size() * sizeof(double2), b_rec = nch * 2 * 4 * sizeof(long long), b_bad = nch * 2 * 2 * sizeof(int);
   void *p_dense = nullptr, *p_rec = nullptr, *p_bad = nullptr, *p_misc = nullptr;
   int rc;
   if ((rc = cached_malloc(&p_dense, b_dense))) return rc;
@@ -1030,8 +1042,8 @@ extern "C" int nemb200_selftest_double_chain(const double* l, const double* z, i
     const int* totp = tot;
     if (parallel) {
       long long *rR = (long long*)p_rec;
-      CcJob job{p_dense, totp, rR, rR + nch * 2, rR + nch * 4, (int*)p_bad, stp, out, nullptr, 1};
-      k_crit_chain_par<<<1, kCcTpb>>>(nullptr, job);
+      CcJob job{p_dense, totp, rR, rR + nch * 2, rR + nch * 4, (double*)(rR + nch * 6), (int*)p_bad, (int*)p_bad + nch * 2, stp, out, nullptr, 1};
+      chain_launch(nullptr, job, 1, (size_t)n, nullptr);
     } else {
       k_crit_chain<TermsD2><<<1, 64>>>(dense, totp, out);
     }

@@ -309,11 +309,16 @@ __device__ __forceinline__ const uint4* ptr_plus16(const uint4* base, uint32_t i
   return reinterpret_cast<const uint4*>(r);
 }
 
-template <int KB, int KX, int RB, int P, int TPB, bool HALF>
+// PC (with KB = KX = 2): the three-class case whose first centre is all ones and whose last centre is all zeros -- the
+// persistent and the cloud class of nearly every iteration of a K = 3 run.  Their mismatch counts are D - popc(x) and
+// popc(x), so only two accumulations run per matrix word instead of three (plane 0 is a zero plane: "mismatches" against
+// it are the row's set bits; plane 1 is the middle class), which takes the kernel from ALU-bound to HBM-bound; the
+// epilogue writes the three log-densities (L, B of the three classes; Dcols = number of genome columns).
+template <int KB, int KX, int RB, int P, int TPB, bool HALF, bool PC = false>
 __device__ __forceinline__ void density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int Krt, int G,
                                                 const uint4* m1, const uint4* valid, uint4* ring /*[P][RB][TPB]*/,
                                                 const double* __restrict__ L, const double* __restrict__ B,
-                                                double* __restrict__ logf, int Kstride /*classes per row of logf*/) {
+                                                double* __restrict__ logf, int Kstride /*classes per row of logf*/, int Dcols = 0) {
   const int K = KX > 0 ? KX : Krt;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
@@ -409,15 +414,31 @@ __device__ __forceinline__ void density_sk_ring(const uint4* __restrict__ bits, 
 #pragma unroll
         for (int k = 0; k < KB; k++) h[r][k] += __shfl_xor_sync(0xffffffffu, h[r][k], off);
     }
+    if (PC) {
 #pragma unroll
-    for (int k = 0; k < KB; k++) {
-      if (k < K && (k & (G - 1)) == sub) {
-        const double Lk = L[k], Bk = B[k];
+      for (int k = 0; k < 3; k++) {
+        if ((k & (G - 1)) == sub) {
+          const double Lk = L[k], Bk = B[k];
 #pragma unroll
-        for (int r = 0; r < RB; r++) {
-          if (r0 + r < N) {
-            const double v = (h[r][k] == 0) ? Bk : (Bk - (double)h[r][k] * Lk);   // see density_sk_body
-            logf[(r0 + r) * Kstride + k] = v;
+          for (int r = 0; r < RB; r++) {
+            if (r0 + r < N) {
+              const int hk = k == 0 ? Dcols - h[r][0] : (k == 1 ? h[r][KB - 1] : h[r][0]);
+              logf[(r0 + r) * Kstride + k] = (hk == 0) ? Bk : (Bk - (double)hk * Lk);
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < KB; k++) {
+        if (k < K && (k & (G - 1)) == sub) {
+          const double Lk = L[k], Bk = B[k];
+#pragma unroll
+          for (int r = 0; r < RB; r++) {
+            if (r0 + r < N) {
+              const double v = (h[r][k] == 0) ? Bk : (Bk - (double)h[r][k] * Lk);   // see density_sk_body
+              logf[(r0 + r) * Kstride + k] = v;
+            }
           }
         }
       }
@@ -426,11 +447,16 @@ __device__ __forceinline__ void density_sk_ring(const uint4* __restrict__ bits, 
   cp_async_wait<0>();
 }
 
+__device__ __forceinline__ uint32_t columns_mask(int w, int D) {   // bits of 32-column word w that are genome columns
+  const int n = D - w * 32;
+  return n >= 32 ? 0xffffffffu : (n > 0 ? ((1u << n) - 1u) : 0u);
+}
+
 template <int KB, int KX, int RB, int P, int TPB>
 __device__ __forceinline__ void
 density_sk_ring_cta(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
                     const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
-                    const int* __restrict__ has_half, double* __restrict__ logf, int Kstride) {
+                    const int* __restrict__ has_half, double* __restrict__ logf, int Kstride, int D) {
   // K classes starting at the pointers given (a launch may cover a chunk of the model's classes); logf rows hold Kstride
   extern __shared__ uint4 smem4[];
   const bool half = (*has_half != 0);
@@ -442,6 +468,21 @@ density_sk_ring_cta(const uint4* __restrict__ bits, long long N, int W4, int K, 
     sm1[t] = m1g[t];
     if (half) sval[t] = validg[t];
   }
+  if (KX == 3 && Kstride == 3 && D > 0) {
+    // first centre all ones, last centre all zeros, no centre at 0.5?  (block-uniform decision)
+    bool mine = !half;
+    for (int t = threadIdx.x; t < W4 && mine; t += TPB) {
+      const uint4 a = m1g[t], c = m1g[2 * W4 + t];
+      mine = a.x == columns_mask(4 * t, D) && a.y == columns_mask(4 * t + 1, D) && a.z == columns_mask(4 * t + 2, D) &&
+             a.w == columns_mask(4 * t + 3, D) && (c.x | c.y | c.z | c.w) == 0u;
+    }
+    if (__syncthreads_and(mine)) {
+      for (int t = threadIdx.x; t < W4; t += TPB) sm1[t] = make_uint4(0u, 0u, 0u, 0u);   // plane 0: the row's own bits
+      __syncthreads();
+      density_sk_ring<2, 2, RB, P, TPB, false, true>(bits, N, W4, 2, G, sm1, sval, ring, L, B, logf, Kstride, D);
+      return;
+    }
+  }
   __syncthreads();
   if (half) density_sk_ring<KB, KX, RB, P, TPB, true>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf, Kstride);
   else      density_sk_ring<KB, KX, RB, P, TPB, false>(bits, N, W4, K, G, sm1, sval, ring, L, B, logf, Kstride);
@@ -451,8 +492,8 @@ template <int KB, int KX, int RB, int P, int TPB>
 __global__ void __launch_bounds__(TPB, 1)
 k_density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int K, int G, const uint4* __restrict__ m1g,
                   const uint4* __restrict__ validg, const double* __restrict__ L, const double* __restrict__ B,
-                  const int* __restrict__ has_half, double* __restrict__ logf, int Kstride) {
-  density_sk_ring_cta<KB, KX, RB, P, TPB>(bits, N, W4, K, G, m1g, validg, L, B, has_half, logf, Kstride);
+                  const int* __restrict__ has_half, double* __restrict__ logf, int Kstride, int D) {
+  density_sk_ring_cta<KB, KX, RB, P, TPB>(bits, N, W4, K, G, m1g, validg, L, B, has_half, logf, Kstride, D);
 }
 
 // free dispersion ("skd"): per-column log-odds, logf_ik = B_k - sum over mismatching columns d of L_kd.  The sum walks
@@ -1172,7 +1213,10 @@ mstep_onehot_ring_body(const uint4* __restrict__ bits4, int W4, int tile_w /*<= 
   constexpr uint32_t kGroupBytes = kOhRows * kOhTpb * 16;
 
   const int total = offsets[2 * K];
-  const long long S = min((long long)gridDim.y, max(1LL, ((long long)total + 63) / 64));
+  // few listed rows (steady state of the incremental update): fewer, fuller slices.  A CTA's counter flush (one RED per
+  // non-zero column of its tile and bucket, ~53 000 of them) costs as much as streaming ~200 rows, and with 64-row slices
+  // it was the whole M-step of a converging run (measured: ~70 us per iteration at 2 000 changed rows)
+  const long long S = min((long long)gridDim.y, max(1LL, ((long long)total + 255) / 256));
   if (blockIdx.y >= S) return;
   const int lo = (int)((long long)total * blockIdx.y / S), hi = (int)((long long)total * (blockIdx.y + 1) / S);
   if (lo >= hi) return;
@@ -1884,14 +1928,10 @@ k_crit_compact(const float2* __restrict__ terms, const int* __restrict__ counts,
 // A dependent chain of float adds runs at one add per 2-3 ns: 3.2 ms for the 10^6 terms of a K = 20 instance, more than
 // its ten EM iterations.  But while the running sum s stays inside one binade [2^E, 2^(E+1)), every partial sum is a
 // multiple of u = ulp(s) = 2^(E-23), and fl(s + x) = s + rn_u(x): the rounded addend rn_u(x) (x rounded to the nearest
-// multiple of u) does not depend on s -- except on an exact tie, where round-to-even looks at s.  So, given the exact
-// state s at some term, the integers r_i = rn_u(x_i) / u of ALL following terms can be computed in parallel, summed per
-// chunk with integer prefix sums (which also give the smallest and largest partial sum inside the chunk), and the state
-// advances over whole chunks by integer addition for as long as the partial sums stay inside the binade and no tie
-// occurs.  At the first chunk where that fails (a binade crossing -- about log2(n) of them for sums that grow -- a tie,
-// or a zero / subnormal state) the chunk is added sequentially, and the following chunks are redone with the new u.
-// Cooperative kernel, rounds separated by grid barriers; in the worst case it degrades to plain sequential adds chunk
-// by chunk, never to a different result (tests compare it bit for bit with k_crit_chain on adversarial inputs).
+// multiple of u) does not depend on s -- except on an exact tie, where round-to-even looks at s.  So, for the binade the
+// accumulator is in, the integers r_i = rn_u(x_i) / u of the terms can be computed in parallel, summed per chunk with
+// integer prefix sums (which also give the smallest and largest partial sum inside the chunk), and the state advances
+// over whole chunks by integer addition for as long as the partial sums stay inside the binade and no tie occurs.
 // Two kinds of chains.  D and G (nem_alg.c:2813-2823) add FLOAT terms to a float accumulator: fl32(s + x).  L and Z
 // (nem_alg.c:2826-2827: `cL = cL + log(fi)`, `cZ = cZ - log(zi)`) add DOUBLE terms: the sum is formed in double and stored
 // to the float accumulator, fl32(fl64(s + x)) -- at 50 000 rows the drift of that float accumulator is 1.2e-5 of M
@@ -1911,7 +1951,6 @@ struct TermsD2 {
 };
 
 constexpr int kCcChunk = 512;
-constexpr int kCcMinTerms = 8192;    // below this many terms the plain chain wins
 struct CcState { float s[2]; int cur[2]; int rounds; int seq_chunks[2]; };   // per chain (0: D, 1: G): exact running sum, next chunk
 
 __device__ __forceinline__ bool cc_binade(float s, int& E) {   // normal, non-zero, finite
@@ -1949,202 +1988,211 @@ __device__ __forceinline__ long long cc_round_units(double x, int Eu, bool doubl
   return (bits >> 63) ? -r : r;
 }
 
-// One CTA (16 warps) per pair of chains: the rounds are separated by block barriers, so a batch of instances (blockIdx.x =
-// job) runs all its chains side by side, and a round costs the window's records (32 chunks per pass of the CTA) plus the walk.
+// The scheme as it runs (four small launches, every one over all chains of a batch of instances -- blockIdx.y = job):
+//   k_cc_sums     per chunk of 512 terms its fp64 sum                                              (all SMs)
+//   k_cc_predict  prefix sums of those -> for every chunk the binade the float accumulator will be in when it gets there
+//                 (the fp64 prefix differs from the float state by ~1e-6 relative: wrong only next to a binade crossing)
+//   k_cc_records  per chunk, for the predicted u: integer total, extreme partial sums, flags         (all SMs, once per chunk)
+//   k_cc_walk     one warp per chain walks the chunks with the EXACT state: 32 chunks per step by integer prefix sums
+//                 while the records were made for the state's binade and the partial sums stay inside it; any other
+//                 chunk (a crossing, a tie, a misprediction, a zero / subnormal state) is added term by term
+// In the worst case it degrades to plain sequential adds, never to another result (tests compare it bit for bit with
+// k_crit_chain and a numpy loop on adversarial inputs).
 struct CcJob {
   const void* terms;            // float2* (D, G: compacted terms) or double2* (L, Z: one pair per row)
   const int* total_ptr;         // number of terms
   long long* recR; long long* recMn; long long* recMx;   // [nchunks][2]
+  double* csum;                 // [nchunks][2] fp64 chunk sums
   int* recFlag;                 // [nchunks][2]; bit 0: needs the sequential path, bit 1: all terms zero
+  int* epred;                   // [nchunks][2] binade the records were made for (INT_MIN: none)
   CcState* state;
   double* out2;                 // the two sums
   const unsigned* run_state;    // batched runs: kSt* words of the instance (a failed run is skipped); may be null
   int double_terms;             // 0: float2 terms (D, G), 1: double2 terms (L, Z)
 };
 
+__device__ __forceinline__ bool cc_job(const CcJob* __restrict__ jobs, const CcJob& job0, CcJob& job) {
+  job = jobs != nullptr ? jobs[blockIdx.y] : job0;
+  return !(job.run_state != nullptr && job.run_state[kStStatus] != 0u);
+}
+
 template <class Terms>
-__device__ __forceinline__ void cc_chain_cta(const CcJob& job) {
+__device__ __forceinline__ void cc_sums_body(const CcJob& job) {
   Terms dense{reinterpret_cast<decltype(Terms::p)>(job.terms)};
-  long long* __restrict__ recR = job.recR; long long* __restrict__ recMn = job.recMn; long long* __restrict__ recMx = job.recMx;
-  int* __restrict__ recFlag = job.recFlag;
-  double* out4 = job.out2;
   const int total = *job.total_ptr;
   const int nchunks = (total + kCcChunk - 1) / kCcChunk;
   const int lane = threadIdx.x & 31;
-  const int warp_global = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
-  volatile CcState* vs = job.state;
-  if (total < kCcMinTerms) {   // short sums: the plain chain is quicker than a dozen rounds (uniform branch: no barrier is skipped)
-    if ((threadIdx.x >> 5) < 2) {
-      const int which = threadIdx.x >> 5;
-      auto fetch = [&](int t) -> double {
-        if (t < total) { double a, b; dense.get(t, a, b); return which == 0 ? a : b; }
-        return 0.0;
-      };
-      float acc = 0.0f;
-      double x = fetch(lane), x1 = fetch(32 + lane);
-      for (int t0 = 0; t0 < total; t0 += 32) {
-        const double x2 = fetch(t0 + 64 + lane);
-        const int m = min(32, total - t0);               // terms past the end are not added (a double 0.0 is not the identity of -0.0f)
-        for (int q = 0; q < m; q++) acc = Terms::add(acc, __shfl_sync(0xffffffffu, x, q));
-        x = x1; x1 = x2;
-      }
-      if (lane == 0) out4[which] = (double)acc;
-    }
-    return;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int c = warp; c < nchunks; c += nwarps) {
+    double sa = 0.0, sb = 0.0;
+    const int t_end = min(total, (c + 1) * kCcChunk);
+#pragma unroll 4
+    for (int t = c * kCcChunk + lane; t < t_end; t += 32) { double a, b; dense.get(t, a, b); sa += a; sb += b; }
+    for (int off = 16; off > 0; off >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, off); sb += __shfl_xor_sync(0xffffffffu, sb, off); }
+    if (lane == 0) { job.csum[(size_t)c * 2] = sa; job.csum[(size_t)c * 2 + 1] = sb; }
   }
-  if (threadIdx.x == 0) {
-    vs->s[0] = 0.0f; vs->s[1] = 0.0f; vs->cur[0] = 0; vs->cur[1] = 0; vs->rounds = 0; vs->seq_chunks[0] = 0; vs->seq_chunks[1] = 0;
-  }
-  __syncthreads();
-  for (int round = 0; round < 2 * nchunks + 4; round++) {
-    const int cur0 = vs->cur[0], cur1 = vs->cur[1];
-    if (cur0 >= nchunks && cur1 >= nchunks) break;
-    const float s0 = vs->s[0], s1 = vs->s[1];
-    // ---- A: records of the next chunks for the current binade of each chain.  Only a window is prepared: a sum of
-    // like-signed terms cannot leave its binade before it has doubled, so about as many chunks as are behind it.
-    int E0 = 0, E1 = 0;
-    const bool ok0 = cc_binade(s0, E0), ok1 = cc_binade(s1, E1);
-    const int first = min(cur0, cur1);
-    const int last = min(nchunks, max(cur0 < nchunks ? 2 * cur0 + 32 : 0, cur1 < nchunks ? 2 * cur1 + 32 : 0));
-    for (int c = first + warp_global; c < last; c += nwarps) {
-      // lane l owns the 16 consecutive terms [16 l, 16 l + 16) of the chunk: a lane-local running sum with its extremes,
-      // then one scan over the 32 lane totals
-      constexpr int kPer = kCcChunk / 32;
-      const int t_end = min(total, (c + 1) * kCcChunk);
-      const int t_lane = c * kCcChunk + lane * kPer;
-      double vx[kPer], vy[kPer];
-#pragma unroll
-      for (int j = 0; j < kPer; j++) { vx[j] = 0.0; vy[j] = 0.0; if (t_lane + j < t_end) dense.get(t_lane + j, vx[j], vy[j]); }
-      long long run[2] = {0, 0}, mn[2] = {LLONG_MAX, LLONG_MAX}, mx[2] = {LLONG_MIN, LLONG_MIN};
-      int flag[2] = {2, 2};
-#pragma unroll
-      for (int ch = 0; ch < 2; ch++) {
-        if (c < (ch ? cur1 : cur0)) continue;                              // warp-uniform
-        bool nz = false, needseq = false;
-        long long pre = 0, lmn = LLONG_MAX, lmx = LLONG_MIN;
-        const bool okc = ch ? ok1 : ok0;
-        const int sh = 23 - (ch ? E1 : E0);
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-          const double x = ch ? vy[j] : vx[j];
-          nz = nz || (x != 0.0);
-          if (okc) {
-            pre += cc_round_units(x, -sh, Terms::kDouble, needseq);        // u = 2^(E - 23)
-            if (t_lane + j < t_end) { lmn = min(lmn, pre); lmx = max(lmx, pre); }
-          }
-        }
-        if (__any_sync(0xffffffffu, nz)) flag[ch] &= ~2;
-        if (!okc || __any_sync(0xffffffffu, needseq)) flag[ch] |= 1;
-        long long incl = pre;                                              // inclusive scan of the lane totals
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const long long o = __shfl_up_sync(0xffffffffu, incl, off);
-          if (lane >= off) incl += o;
-        }
-        const long long base = incl - pre;
-        long long lo = (lmn == LLONG_MAX) ? LLONG_MAX : base + lmn, hi = (lmx == LLONG_MIN) ? LLONG_MIN : base + lmx;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-          hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
-        }
-        mn[ch] = lo; mx[ch] = hi;
-        run[ch] = __shfl_sync(0xffffffffu, incl, 31);
-      }
-      if (lane < 2) {
-        const int ch = lane;
-        if (c >= (ch ? cur1 : cur0)) {
-          const size_t i = (size_t)c * 2 + ch;
-          recR[i] = run[ch]; recMn[i] = mn[ch]; recMx[i] = mx[ch]; recFlag[i] = flag[ch];
-        }
-      }
-    }
-    __syncthreads();
-    // ---- B: CTA 0, warp ch walks chain ch over the prepared chunks; a chunk that cannot be taken by integer arithmetic
-    // is added the plain way, and the walk goes on as long as the records still fit the state
-    if ((threadIdx.x >> 5) < 2) {
-      const int ch = threadIdx.x >> 5;
-      int cur = ch ? cur1 : cur0;
-      if (cur < nchunks) {
-        float sacc = ch ? s1 : s0;
-        const bool have = ch ? ok1 : ok0;       // the records were made for exponent Ec
-        const int Ec = ch ? E1 : E0;
-        int nseq = 0;
-        while (cur < last) {
-          const int c = cur + lane;
-          int nvalid;
-          if (have) {
-            const long long S0 = (long long)scalbn((double)sacc, 23 - Ec);   // exact integer, 2^23 <= |S0| < 2^24
-            long long R = 0, mnv = 0, mxv = 0;
-            int fl = 1;
-            if (c < last) {
-              const size_t i = (size_t)c * 2 + ch;
-              R = __ldcg(recR + i); mnv = __ldcg(recMn + i); mxv = __ldcg(recMx + i); fl = __ldcg(recFlag + i);
-            }
-            long long incl = R;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-              const long long o = __shfl_up_sync(0xffffffffu, incl, off);
-              if (lane >= off) incl += o;
-            }
-            const long long Sstart = S0 + incl - R;
-            const long long lo = Sstart + mnv, hi = Sstart + mxv;
-            bool okc = !(fl & 1) && c < last;
-            if (S0 > 0) okc = okc && lo >= (1LL << 23) && hi <= (1LL << 24) - 1;
-            else        okc = okc && hi <= -(1LL << 23) && lo >= -((1LL << 24) - 1);
-            const unsigned m = __ballot_sync(0xffffffffu, !okc);
-            nvalid = m ? __ffs(m) - 1 : 32;
-            if (nvalid > 0) {
-              const long long Send = S0 + __shfl_sync(0xffffffffu, incl, nvalid - 1);
-              sacc = (float)scalbn((double)Send, Ec - 23);                   // exact: |Send| < 2^24, same binade
-            }
-          } else {                                                           // zero / subnormal state: only all-zero chunks are free
-            const bool z = c < last && (__ldcg(recFlag + (size_t)c * 2 + ch) & 2);
-            const unsigned m = __ballot_sync(0xffffffffu, !z);
-            nvalid = m ? __ffs(m) - 1 : 32;
-          }
-          cur += nvalid;
-          if (nvalid == 32) continue;
-          if (cur >= last) break;
-          {   // chunk `cur` the plain way
-            const int t_begin = cur * kCcChunk, t_end = min(total, t_begin + kCcChunk);
-            double xs[kCcChunk / 32];                                         // 16 independent loads, then the chain
-#pragma unroll
-            for (int b = 0; b < kCcChunk / 32; b++) {
-              const int t = t_begin + b * 32 + lane;
-              xs[b] = 0.0;
-              if (t < t_end) { double a, bb; dense.get(t, a, bb); xs[b] = ch ? bb : a; }
-            }
-            float acc = sacc;
-#pragma unroll
-            for (int b = 0; b < kCcChunk / 32; b++) {
-              const int m = min(32, t_end - (t_begin + b * 32));              // warp-uniform; <= 0 past the end
-              for (int q = 0; q < m; q++) acc = Terms::add(acc, __shfl_sync(0xffffffffu, xs[b], q));
-            }
-            sacc = acc;
-            cur++; nseq++;
-          }
-          int En = 0;
-          const bool now = cc_binade(sacc, En);
-          if (have ? !(now && En == Ec) : now) break;                        // the next records must be made for another u
-        }
-        if (lane == 0) { vs->s[ch] = sacc; vs->cur[ch] = cur; vs->seq_chunks[ch] += nseq; }
-      }
-    }
-    if (threadIdx.x == 64) vs->rounds = round + 1;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { out4[0] = (double)vs->s[0]; out4[1] = (double)vs->s[1]; }
+}
+__global__ void __launch_bounds__(256) k_cc_sums(const CcJob* __restrict__ jobs, CcJob job0) {
+  CcJob job;
+  if (!cc_job(jobs, job0, job)) return;
+  if (job.double_terms) cc_sums_body<TermsD2>(job); else cc_sums_body<TermsF2>(job);
 }
 
-constexpr int kCcTpb = 512;      // 16 warps: the records of a chunk hold 32 doubles per lane, 1024 threads would spill
-__global__ void __launch_bounds__(kCcTpb)
-k_crit_chain_par(const CcJob* __restrict__ jobs, CcJob job0) {
-  const CcJob job = jobs != nullptr ? jobs[blockIdx.x] : job0;
-  if (job.run_state != nullptr && job.run_state[kStStatus] != 0u) return;
-  if (job.double_terms) cc_chain_cta<TermsD2>(job);
-  else cc_chain_cta<TermsF2>(job);
+// one warp per chain: exclusive fp64 prefix of the chunk sums -> predicted binade at the start of every chunk
+__global__ void __launch_bounds__(64) k_cc_predict(const CcJob* __restrict__ jobs, CcJob job0) {
+  CcJob job;
+  if (!cc_job(jobs, job0, job)) return;
+  const int total = *job.total_ptr;
+  const int nchunks = (total + kCcChunk - 1) / kCcChunk;
+  const int lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
+  double carry = 0.0;
+  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+    const int c = c0 + lane;
+    const double v = c < nchunks ? job.csum[(size_t)c * 2 + ch] : 0.0;
+    double incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const double o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+    const double start = carry + incl - v;
+    if (c < nchunks) {
+      const float sf = (float)start;
+      int E = INT_MIN;
+      if (fabsf(sf) >= 1.17549435e-38f && isfinite(sf)) E = ilogbf(sf);
+      job.epred[(size_t)c * 2 + ch] = E;
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+template <class Terms>
+__device__ __forceinline__ void cc_records_body(const CcJob& job) {
+  Terms dense{reinterpret_cast<decltype(Terms::p)>(job.terms)};
+  const int total = *job.total_ptr;
+  const int nchunks = (total + kCcChunk - 1) / kCcChunk;
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int c = warp; c < nchunks; c += nwarps) {
+    // lane l owns the 16 consecutive terms [16 l, 16 l + 16) of the chunk: a lane-local running sum with its extremes,
+    // then one scan over the 32 lane totals
+    constexpr int kPer = kCcChunk / 32;
+    const int t_end = min(total, (c + 1) * kCcChunk);
+    const int t_lane = c * kCcChunk + lane * kPer;
+    double vx[kPer], vy[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; j++) { vx[j] = 0.0; vy[j] = 0.0; if (t_lane + j < t_end) dense.get(t_lane + j, vx[j], vy[j]); }
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+      const int E = job.epred[(size_t)c * 2 + ch];
+      const bool okc = E != INT_MIN;
+      bool nz = false, needseq = false;
+      long long pre = 0, lmn = LLONG_MAX, lmx = LLONG_MIN;
+#pragma unroll
+      for (int j = 0; j < kPer; j++) {
+        const double x = ch ? vy[j] : vx[j];
+        nz = nz || (x != 0.0);
+        if (okc) {
+          pre += cc_round_units(x, E - 23, Terms::kDouble, needseq);     // u = 2^(E - 23)
+          if (t_lane + j < t_end) { lmn = min(lmn, pre); lmx = max(lmx, pre); }
+        }
+      }
+      int flag = 2;
+      if (__any_sync(0xffffffffu, nz)) flag &= ~2;
+      if (!okc || __any_sync(0xffffffffu, needseq)) flag |= 1;
+      long long incl = pre;                                              // inclusive scan of the lane totals
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+      const long long base = incl - pre;
+      long long lo = (lmn == LLONG_MAX) ? LLONG_MAX : base + lmn, hi = (lmx == LLONG_MIN) ? LLONG_MIN : base + lmx;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+      }
+      const long long run = __shfl_sync(0xffffffffu, incl, 31);
+      if (lane == 0) {
+        const size_t i = (size_t)c * 2 + ch;
+        job.recR[i] = run; job.recMn[i] = lo; job.recMx[i] = hi; job.recFlag[i] = flag;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_cc_records(const CcJob* __restrict__ jobs, CcJob job0) {
+  CcJob job;
+  if (!cc_job(jobs, job0, job)) return;
+  if (job.double_terms) cc_records_body<TermsD2>(job); else cc_records_body<TermsF2>(job);
+}
+
+template <class Terms>
+__device__ __forceinline__ void cc_walk_body(const CcJob& job) {
+  Terms dense{reinterpret_cast<decltype(Terms::p)>(job.terms)};
+  const int total = *job.total_ptr;
+  const int nchunks = (total + kCcChunk - 1) / kCcChunk;
+  const int lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
+  float sacc = 0.0f;
+  int cur = 0, nseq = 0;
+  while (cur < nchunks) {
+    int Ec = 0;
+    const bool have = cc_binade(sacc, Ec);
+    const int c = cur + lane;
+    int nvalid;
+    if (have) {
+      const long long S0 = (long long)scalbn((double)sacc, 23 - Ec);   // exact integer, 2^23 <= |S0| < 2^24
+      long long R = 0, mnv = 0, mxv = 0;
+      int fl = 1, Ep = INT_MIN;
+      if (c < nchunks) {
+        const size_t i = (size_t)c * 2 + ch;
+        R = job.recR[i]; mnv = job.recMn[i]; mxv = job.recMx[i]; fl = job.recFlag[i]; Ep = job.epred[i];
+      }
+      if (Ep != Ec) { R = 0; fl |= 1; }                                  // records made for another u: not usable
+      long long incl = R;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+      const long long Sstart = S0 + incl - R;
+      const long long lo = Sstart + mnv, hi = Sstart + mxv;
+      bool okc = !(fl & 1) && c < nchunks;
+      if (fl & 2) okc = c < nchunks;                                     // an all-zero chunk leaves any state alone
+      else if (S0 > 0) okc = okc && lo >= (1LL << 23) && hi <= (1LL << 24) - 1;
+      else             okc = okc && hi <= -(1LL << 23) && lo >= -((1LL << 24) - 1);
+      const unsigned m = __ballot_sync(0xffffffffu, !okc);
+      nvalid = m ? __ffs(m) - 1 : 32;
+      if (nvalid > 0) {
+        const long long Send = S0 + __shfl_sync(0xffffffffu, incl, nvalid - 1);
+        sacc = (float)scalbn((double)Send, Ec - 23);                     // exact: |Send| < 2^24, same binade
+      }
+    } else {                                                             // zero / subnormal / non-finite state: only all-zero chunks are free
+      const bool z = c < nchunks && (job.recFlag[(size_t)c * 2 + ch] & 2);
+      const unsigned m = __ballot_sync(0xffffffffu, !z);
+      nvalid = m ? __ffs(m) - 1 : 32;
+    }
+    cur += nvalid;
+    if (nvalid == 32 || cur >= nchunks) continue;
+    {   // chunk `cur` term by term
+      const int t_begin = cur * kCcChunk, t_end = min(total, t_begin + kCcChunk);
+      double xs[kCcChunk / 32];                                           // 16 independent loads, then the chain
+#pragma unroll
+      for (int b = 0; b < kCcChunk / 32; b++) {
+        const int t = t_begin + b * 32 + lane;
+        xs[b] = 0.0;
+        if (t < t_end) { double a, bb; dense.get(t, a, bb); xs[b] = ch ? bb : a; }
+      }
+      float acc = sacc;
+#pragma unroll
+      for (int b = 0; b < kCcChunk / 32; b++) {
+        const int mcount = min(32, t_end - (t_begin + b * 32));           // warp-uniform; <= 0 past the end
+        for (int q = 0; q < mcount; q++) acc = Terms::add(acc, __shfl_sync(0xffffffffu, xs[b], q));
+      }
+      sacc = acc;
+      cur++; nseq++;
+    }
+  }
+  if (lane == 0) {
+    job.out2[ch] = (double)sacc;
+    if (job.state != nullptr) { job.state->s[ch] = sacc; job.state->cur[ch] = cur; job.state->seq_chunks[ch] = nseq; job.state->rounds = 1; }
+  }
+}
+__global__ void __launch_bounds__(64) k_cc_walk(const CcJob* __restrict__ jobs, CcJob job0) {
+  CcJob job;
+  if (!cc_job(jobs, job0, job)) return;
+  if (job.double_terms) cc_walk_body<TermsD2>(job); else cc_walk_body<TermsF2>(job);
 }
 
 // D (warp 0) and G (warp 1) re-accumulated in float32 in the reference's order.  The warp loads 32 terms at a time
@@ -2372,7 +2420,7 @@ __global__ void __launch_bounds__(TPB, 1) k_b_density_ring(const BatchInst* __re
   density_sk_ring_cta<KB, KX, RB, P, TPB>(reinterpret_cast<const uint4*>(I.bits), I.N, W4, kc, G,
                                           reinterpret_cast<const uint4*>(I.P.m1) + (size_t)k0 * W4,
                                           reinterpret_cast<const uint4*>(I.P.valid) + (size_t)k0 * W4, I.P.L + k0, I.P.B + k0,
-                                          I.P.has_half, I.logf + k0, I.K);
+                                          I.P.has_half, I.logf + k0, I.K, I.D);
 }
 
 __global__ void __launch_bounds__(kOhTpb, 1) k_b_onehot_ring(const BatchInst* __restrict__ B, int tile_w) {
