@@ -162,6 +162,16 @@ int nemb200_peer_logf(nemb200_plan* plan, double** logf_full);
 int nemb200_density_peers(nemb200_plan* plan, const uint32_t* bits, int64_t row_offset, void* stream);
 int nemb200_peer_wait_densities(nemb200_plan* plan, void* stream);
 
+/* A whole row-sharded run with the device-resident loop (no host synchronisation between iterations): this rank's part.
+ * `plan` = created with NEMB200_PEER_EXCHANGE for this rank's rows [row_offset, row_offset + N_local) and attached; every
+ * rank calls it with the same graph (all rows), beta and iteration cap.  The convergence test runs on the replicated
+ * posteriors, so all ranks stop at the same iteration.  T_out: N_total x K (device, may be NULL); the parameters stay in
+ * the plan (nemb200_get_params). */
+int nemb200_nem_sharded(nemb200_plan* plan, const uint32_t* bits_local, int64_t row_offset, const int32_t* rowptr,
+                        const int32_t* col, const float* w, const int32_t* sched_level_ptr, const int32_t* sched_rows,
+                        int32_t n_levels, float beta, int32_t itermax, float cv_th, float* T_out, nemb200_result* result,
+                        void* stream);
+
 /* E-step, part 2 (nem_alg.c:2412-2489, :2630-2701): posterior sweep over rows [0, N) of logf/T (full-length arrays),
  * reading T_old and writing T_new; maxdiff_bits receives max |T_new - T_old| as float bits (atomicMax).
  * beta_now lets the caller run the "blind" beta = 0 pass of nem_alg.c:2043-2050.  maxdiff_bits == NULL uses (and first

@@ -161,7 +161,7 @@ struct nemb200_plan {
   uint32_t* flags2 = nullptr;     // [0] max |T_new - T_old| as float bits, [1] status (P.status points here)
   // row-sharded exchange over NVLink peer memory (nemb200_peer_*)
   double* logf_full = nullptr;    // [N_total][K] log-densities of ALL rows: every rank's density kernel stores into it
-  int* sig = nullptr;             // [2][kMaxPeers] epochs completed by each rank: phase 0 = M-step statistics, 1 = densities
+  int* sig = nullptr;             // [4][kMaxPeers] epochs completed by each rank: phase 0 = M-step statistics, 1 = densities, 2 = run start
   int* peer_err = nullptr;        // [1] set when a peer wait timed out
   int** sig_ptrs = nullptr;       // [kMaxPeers] device array: the ranks' sig arrays
   int world = 1, rank = 0;
@@ -170,7 +170,7 @@ struct nemb200_plan {
   double* peer_logf[kMaxPeers] = {nullptr};
   const int* peer_iblock[kMaxPeers] = {nullptr};
   const double* peer_dblock[kMaxPeers] = {nullptr};
-  int epoch_stats = 0, epoch_dens = 0;
+  int epoch_stats = 0, epoch_dens = 0, epoch_run = 0;
   int* bcast_ticket = nullptr;    // [1] CTAs of k_peer_broadcast that have finished
   int sweep_cta_cap = 0;          // > 0: CTAs of the cooperative sweep (instances of a batch run side by side)
   bool sweep_waits = false;       // the next sweep waits for every rank's densities (nemb200_peer_wait_densities)
@@ -225,8 +225,13 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   pl->Ltab = ar.take<double>(pl->free_disp ? K * Ws * 128 : (size_t)1); pl->Lword = ar.take<double>(K * Ws); pl->eps_init = ar.take<float>(K);
   pl->fin_partial = ar.take<double>((size_t)K * pl->fin_chunks * 2); pl->fin_tickets = ar.take<int>(K);
   pl->crit_partial = ar.take<double>((size_t)pl->crit_blocks * 4); pl->crit4 = ar.take<double>(8);
-  pl->sig = ar.take<int>(2 * kMaxPeers); pl->peer_err = ar.take<int>(1); pl->bcast_ticket = ar.take<int>(1); pl->sig_ptrs = ar.take<int*>(kMaxPeers);
-  if (pl->flags & NEMB200_PEER_EXCHANGE) pl->logf_full = ar.take<double>((size_t)pl->N_total * K);
+  pl->sig = ar.take<int>(4 * kMaxPeers); pl->peer_err = ar.take<int>(1); pl->bcast_ticket = ar.take<int>(1); pl->sig_ptrs = ar.take<int*>(kMaxPeers);
+  if (pl->flags & NEMB200_PEER_EXCHANGE) {
+    pl->logf_full = ar.take<double>((size_t)pl->N_total * K);
+    // the device-resident loop of a sharded run (nemb200_nem_sharded): replicated posteriors and graph copy of ALL rows
+    pl->run_Ta = ar.take<float>((size_t)pl->N_total * K); pl->run_Tb = ar.take<float>((size_t)pl->N_total * K);
+    pl->ell_in_block = ar.take<char>((size_t)pl->N_total * (sizeof(int4) + kEllW * sizeof(int2)));
+  }
   // the sweep and the criteria run over all rows, also on a shard's plan; one region of ceil(N/warps) rows per warp
   pl->crit_terms = ar.take<float>(((size_t)pl->N_total + (size_t)pl->crit_blocks * 8) * K * 2);
   pl->crit_counts = ar.take<int>((size_t)pl->crit_blocks * 8);
@@ -287,7 +292,7 @@ static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int6
   Arena real;
   real.base = (char*)pl->block; real.counting = false;
   plan_layout(pl, real);
-  if (cudaMemset(pl->sig, 0, 2 * kMaxPeers * sizeof(int)) != cudaSuccess || cudaMemset(pl->peer_err, 0, sizeof(int)) != cudaSuccess || cudaMemset(pl->bcast_ticket, 0, sizeof(int)) != cudaSuccess ||
+  if (cudaMemset(pl->sig, 0, 4 * kMaxPeers * sizeof(int)) != cudaSuccess || cudaMemset(pl->peer_err, 0, sizeof(int)) != cudaSuccess || cudaMemset(pl->bcast_ticket, 0, sizeof(int)) != cudaSuccess ||
       cudaMemset(pl->fin_tickets, 0, K * sizeof(int)) != cudaSuccess) {
     nemb200_plan_destroy(pl);
     return fail(NEMB200_ERR_CUDA, "plan_create: memset");
@@ -1290,6 +1295,25 @@ extern "C" int nemb200_nem_device(const uint32_t* bits, int64_t N, int64_t D, in
   pl->stepwise_used = false;   // everything this run enqueued has completed
   nemb200_plan_destroy(pl);
   return rc;
+}
+
+/* One rank's part of a row-sharded run with the device-resident loop: `pl` was created with NEMB200_PEER_EXCHANGE for this
+ * rank's rows and attached to its peers; every rank calls this with the same graph, K, beta and iteration cap. */
+extern "C" int nemb200_nem_sharded(nemb200_plan* pl, const uint32_t* bits_local, int64_t row_offset, const int32_t* rowptr,
+                                   const int32_t* col, const float* w, const int32_t* sched_level_ptr, const int32_t* sched_rows,
+                                   int32_t n_levels, float beta, int32_t itermax, float cv_th, float* T_out, nemb200_result* result,
+                                   void* stream_) {
+  if (!pl || !pl->attached || !pl->logf_full) return fail(NEMB200_ERR_ARG, "nem_sharded: plan is not attached to its peers");
+  if (pl->N_local > 0 && !bits_local) return fail(NEMB200_ERR_ARG, "nem_sharded: null matrix");
+  if (beta != 0.0f && (!rowptr || !col || !w)) return fail(NEMB200_ERR_ARG, "nem_sharded: beta != 0 needs the neighbour graph");
+  if (row_offset < 0 || row_offset + pl->N_local > pl->N_total) return fail(NEMB200_ERR_ARG, "nem_sharded: row block outside the instance");
+  nemb200_result tmp;
+  const std::vector<int> one{0};
+  const int64_t N = pl->N_local, D = pl->D, Ws = pl->Ws;
+  const int32_t K = pl->K, fd = pl->free_disp;
+  float *nomu = nullptr;
+  return batch_run(one, &bits_local, &N, &D, &Ws, &rowptr, &col, &w, &sched_level_ptr, &sched_rows, &n_levels, &K, &beta, &fd, &itermax,
+                   cv_th, pl->flags, &T_out, &nomu, &nomu, &nomu, result ? result : &tmp, (cudaStream_t)stream_, true, pl, row_offset);
 }
 
 extern "C" int nemb200_nem_device_batch(int32_t n_inst, const uint32_t* const* bits, const int64_t* N, const int64_t* D,

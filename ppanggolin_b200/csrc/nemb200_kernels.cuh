@@ -2286,8 +2286,15 @@ __global__ void k_sum_partials(const double* __restrict__ p, int n, double* __re
 // ------------------------------------------------------------------------------------------------------------------
 
 struct BatchInst {
-  const uint32_t* bits;
-  long long N;
+  const uint32_t* bits;        // this rank's rows of the matrix
+  long long N;                 // rows of the instance: the sweep and the criteria run over all of them (replicated)
+  long long N_loc, row_off;    // this rank's row block [row_off, row_off + N_loc) (N_loc == N, row_off == 0 without sharding)
+  // row-sharded runs (one process per GPU): the two exchange steps of an iteration over NVLink peer memory
+  int world, rank, epoch0;     // epochs of run-local iteration s: epoch0 + s (the same on every rank)
+  int* const* sig_ptrs; const int* sig; int* peer_err; int* bcast_ticket;
+  PeerStats ps;                // the ranks' statistic blocks (ps.n == 1 without sharding)
+  PeerOut push;                // the ranks' log-density buffers
+  double* logf_loc;            // = logf + row_off * K
   int D, Ws, Dpad, K, free_disp;
   const int* rowptr; const int* col; const float* w;
   const int* level_ptr; const int* level_rows; int n_levels;
@@ -2329,7 +2336,7 @@ __global__ void __launch_bounds__(256) k_b_start(const BatchInst* __restrict__ B
     init_params_body(P, I.base_prop, I.eps_init);
   }
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-  for (long long t = tid; t < I.N; t += nth) I.prev[t] = kNone;
+  for (long long t = tid; t < I.N_loc; t += nth) I.prev[t] = kNone;
   const long long nkd = (long long)I.K * I.Dpad;
   for (long long t = tid; t < nkd; t += nth) I.cnt[t] = 0;
   const long long ntk = I.N * I.K;
@@ -2365,14 +2372,14 @@ __global__ void __launch_bounds__(256) k_b_ell_build(const BatchInst* __restrict
 template <int KB>
 __global__ void __launch_bounds__(256) k_b_classify(const BatchInst* __restrict__ B, int s) {
   const BatchInst& I = B[blockIdx.z];
-  if (!b_active(I) || (long long)blockIdx.x * 256 >= I.N) return;
-  classify_body<KB>(I.T[(I.c0 + s - 1) & 1], I.N, I.K, I.prev, I.ent, I.hist, I.nk_cnt, I.nk_fz, I.full_recount);
+  if (!b_active(I) || (long long)blockIdx.x * 256 >= I.N_loc) return;
+  classify_body<KB>(I.T[(I.c0 + s - 1) & 1] + I.row_off * I.K, I.N_loc, I.K, I.prev, I.ent, I.hist, I.nk_cnt, I.nk_fz, I.full_recount);
 }
 
 __global__ void __launch_bounds__(256) k_b_scatter(const BatchInst* __restrict__ B) {
   const BatchInst& I = B[blockIdx.z];
-  if (!b_active(I) || (long long)blockIdx.x * 256 >= I.N) return;
-  scatter_body(I.ent, I.N, I.hist, 2 * I.K + 1, I.offsets, I.cursor, I.perm);
+  if (!b_active(I) || (long long)blockIdx.x * 256 >= I.N_loc) return;
+  scatter_body(I.ent, I.N_loc, I.hist, 2 * I.K + 1, I.offsets, I.cursor, I.perm);
 }
 
 __global__ void __launch_bounds__(kMsTpb) k_b_onehot(const BatchInst* __restrict__ B, int tile_w) {
@@ -2385,30 +2392,28 @@ template <int KB>
 __global__ void __launch_bounds__(256) k_b_fuzzy(const BatchInst* __restrict__ B, int s) {
   const BatchInst& I = B[blockIdx.z];
   if (!b_active(I)) return;
-  mstep_fuzzy_body<KB>(I.bits, I.Ws, I.K, I.D, I.offsets, I.perm, I.T[(I.c0 + s - 1) & 1], I.fsum, I.Dpad);
+  mstep_fuzzy_body<KB>(I.bits, I.Ws, I.K, I.D, I.offsets, I.perm, I.T[(I.c0 + s - 1) & 1] + I.row_off * I.K, I.fsum, I.Dpad);
 }
 
 template <int KT>
 __global__ void __launch_bounds__(256) k_b_fuzzy_mma(const BatchInst* __restrict__ B, int s) {
   const BatchInst& I = B[blockIdx.z];
   if (!b_active(I)) return;
-  mstep_fuzzy_mma_body<KT>(I.bits, I.Ws, I.K, I.D, I.offsets, I.perm, I.T[(I.c0 + s - 1) & 1], I.fsum, I.Dpad);
+  mstep_fuzzy_mma_body<KT>(I.bits, I.Ws, I.K, I.D, I.offsets, I.perm, I.T[(I.c0 + s - 1) & 1] + I.row_off * I.K, I.fsum, I.Dpad);
 }
 
 __global__ void __launch_bounds__(256) k_b_finalize(const BatchInst* __restrict__ B) {
   const BatchInst& I = B[blockIdx.z];
   if (!b_active(I) || blockIdx.y >= (unsigned)I.K) return;
-  PeerStats ps;
-  ps.n = 1; ps.iblock[0] = I.cnt; ps.dblock[0] = I.fsum;
-  mstep_finalize_body(I.P, ps, I.N, I.fin_partial, I.fin_tickets);
+  mstep_finalize_body(I.P, I.ps, I.N, I.fin_partial, I.fin_tickets);
 }
 
 template <int KB, int KX, int RB>
 __global__ void __launch_bounds__(kDensTpb) k_b_density_sk(const BatchInst* __restrict__ B, int G, int gate, int planes_in_smem) {
   const BatchInst& I = B[blockIdx.z];
   if (gate && !b_active(I)) return;
-  density_sk_cta<KB, KX, RB>(reinterpret_cast<const uint4*>(I.bits), I.N, I.Ws / 4, I.K, G, reinterpret_cast<const uint4*>(I.P.m1),
-                             reinterpret_cast<const uint4*>(I.P.valid), I.P.L, I.P.B, I.P.has_half, I.logf, planes_in_smem);
+  density_sk_cta<KB, KX, RB>(reinterpret_cast<const uint4*>(I.bits), I.N_loc, I.Ws / 4, I.K, G, reinterpret_cast<const uint4*>(I.P.m1),
+                             reinterpret_cast<const uint4*>(I.P.valid), I.P.L, I.P.B, I.P.has_half, I.logf_loc, planes_in_smem);
 }
 
 // large matrices: the streaming (shared-memory ring) kernels, classes [k0, k0 + kc) per launch
@@ -2417,10 +2422,10 @@ __global__ void __launch_bounds__(TPB, 1) k_b_density_ring(const BatchInst* __re
   const BatchInst& I = B[blockIdx.z];
   if (gate && !b_active(I)) return;
   const int W4 = I.Ws / 4;
-  density_sk_ring_cta<KB, KX, RB, P, TPB>(reinterpret_cast<const uint4*>(I.bits), I.N, W4, kc, G,
+  density_sk_ring_cta<KB, KX, RB, P, TPB>(reinterpret_cast<const uint4*>(I.bits), I.N_loc, W4, kc, G,
                                           reinterpret_cast<const uint4*>(I.P.m1) + (size_t)k0 * W4,
                                           reinterpret_cast<const uint4*>(I.P.valid) + (size_t)k0 * W4, I.P.L + k0, I.P.B + k0,
-                                          I.P.has_half, I.logf + k0, I.K, I.D);
+                                          I.P.has_half, I.logf_loc + k0, I.K, I.D);
 }
 
 __global__ void __launch_bounds__(kOhTpb, 1) k_b_onehot_ring(const BatchInst* __restrict__ B, int tile_w) {
@@ -2433,7 +2438,66 @@ template <int KB>
 __global__ void __launch_bounds__(256) k_b_density_skd(const BatchInst* __restrict__ B, int G, int gate) {
   const BatchInst& I = B[blockIdx.z];
   if (gate && !b_active(I)) return;
-  density_skd_body<KB>(I.bits, I.N, I.Ws, I.K, G, I.P.m1, I.P.valid, I.Ltab, I.Lword, I.P.B, I.logf);
+  density_skd_body<KB>(I.bits, I.N_loc, I.Ws, I.K, G, I.P.m1, I.P.valid, I.Ltab, I.Lword, I.P.B, I.logf_loc);
+}
+
+// row-sharded runs, M-step: "my statistics of iteration s are complete", then wait for every rank's (one block per instance)
+__global__ void __launch_bounds__(32) k_b_stats_barrier(const BatchInst* __restrict__ B, int s) {
+  const BatchInst& I = B[blockIdx.z];
+  if (I.world <= 1 || !b_active(I)) return;
+  const int epoch = I.epoch0 + s;
+  if (threadIdx.x < I.world) {
+    __threadfence_system();
+    volatile int* dst = I.sig_ptrs[threadIdx.x] + 0 * kMaxPeers + I.rank;
+    *dst = epoch;
+    __threadfence_system();
+  }
+  peer_wait_lane(I.sig, I.world, 0, epoch, I.peer_err);
+}
+// row-sharded runs, start of a run: no rank may overwrite the others' log-densities (push) while they still read them for
+// the criteria of the previous run -- every rank reports "my previous run is complete" and waits for all (phase 2)
+__global__ void __launch_bounds__(32) k_b_run_barrier(const BatchInst* __restrict__ B) {
+  const BatchInst& I = B[blockIdx.z];
+  if (I.world <= 1) return;
+  if (threadIdx.x < I.world) {
+    __threadfence_system();
+    volatile int* dst = I.sig_ptrs[threadIdx.x] + 2 * kMaxPeers + I.rank;
+    *dst = I.epoch0;
+    __threadfence_system();
+  }
+  peer_wait_lane(I.sig, I.world, 2, I.epoch0, I.peer_err);
+}
+// row-sharded runs, E-step: push this rank's fresh log-densities into every peer's buffer; the last CTA publishes the epoch
+__global__ void __launch_bounds__(256) k_b_push_densities(const BatchInst* __restrict__ B, int s, int gate) {
+  const BatchInst& I = B[blockIdx.z];
+  if (I.world <= 1 || (gate && !b_active(I))) return;
+  const int peer = blockIdx.y + 1;
+  const long long first = I.row_off * I.K, count = I.N_loc * (long long)I.K;   // the shard, in doubles
+  if (peer < I.push.n && count > 0) {
+    const double* src = I.logf + first;
+    double* dst = I.push.ptr[peer] + first;
+    const long long head = (first & 1) ? 1 : 0;                                   // 16-byte stores need an even start
+    if (head && blockIdx.x == 0 && threadIdx.x == 0) dst[0] = src[0];
+    const double2* s2 = reinterpret_cast<const double2*>(src + head);
+    double2* d2 = reinterpret_cast<double2*>(dst + head);
+    const long long n2 = (count - head) / 2;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (long long)gridDim.x * blockDim.x) d2[t] = s2[t];
+    if (((count - head) & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[count - 1] = src[count - 1];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int total = gridDim.x * gridDim.y;
+    if (atomicAdd(I.bcast_ticket, 1) == total - 1) {
+      *I.bcast_ticket = 0;
+      __threadfence_system();
+      for (int r = 0; r < I.world; r++) {
+        volatile int* dst = I.sig_ptrs[r] + 1 * kMaxPeers + I.rank;
+        *dst = I.epoch0 + s;
+      }
+      __threadfence_system();
+    }
+  }
 }
 
 // s >= 1: the sweep of EM iteration s (reads the posteriors of iteration s - 1); s == 0 / -1: the two start sweeps of
@@ -2453,6 +2517,9 @@ __global__ void __launch_bounds__(COOP ? 1024 : 256) k_b_sweep(const BatchInst* 
   a.maxdiff_bits = I.state + (s >= 1 ? kStMaxdiff : kStWords - 1);   // the start sweeps are not convergence-tested
   a.ell_hdr = I.ell_hdr; a.ell_nb = I.ell_nb; a.stamps = nullptr;
   a.wait_sig = nullptr; a.wait_n = 0; a.wait_epoch = 0; a.wait_err = nullptr;
+  if (I.world > 1 && s >= 0) {        // the densities of this sweep's epoch, pushed by every rank (the start sweep with beta
+    a.wait_sig = I.sig; a.wait_n = I.world; a.wait_epoch = I.epoch0 + s; a.wait_err = I.peer_err;   // reuses those of s = 0)
+  }
   const bool levels = COOP && beta != 0.0f && I.rowptr != nullptr && !I.jacobi && I.n_levels > 1;
   a.level_ptr = levels ? I.level_ptr : nullptr; a.level_rows = levels ? I.level_rows : nullptr; a.n_levels = levels ? I.n_levels : 1;
   InstBar bar{I.barrier, gridDim.x};

@@ -69,6 +69,8 @@ SIGNATURES = {
     "nemb200_peer_logf": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
     "nemb200_density_peers": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     "nemb200_peer_wait_densities": (ctypes.c_int, [_vp, _vp]),
+    "nemb200_nem_sharded": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _i32, _f32, _vp,
+                                           ctypes.POINTER(_Result), _vp]),
     "nemb200_sweep": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp]),
     "nemb200_plan_graph_changed": (ctypes.c_int, [_vp]),
     "nemb200_selftest_float_chain": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
@@ -465,6 +467,16 @@ class Plan:
         a = _A()
         a.__cuda_array_interface__ = {"shape": (self.N_total, self.K), "typestr": "<f8", "data": (p.value, False), "version": 3}
         return torch.as_tensor(a, device=f"cuda:{torch.cuda.current_device()}")
+
+    def nem_sharded(self, bits_local, row_offset: int, inp: Optional[DeviceInput], beta: float, itermax: int, cv_th: float, T_out):
+        """This rank's part of a whole row-sharded run with the device-resident loop (``nemb200_nem_sharded``)."""
+        g = inp is not None and inp.rowptr is not None
+        res = _Result()
+        _check(lib().nemb200_nem_sharded(self._h, _ptr(bits_local), row_offset, _ptr(inp.rowptr) if g else 0, _ptr(inp.col) if g else 0,
+                                         _ptr(inp.w) if g else 0, _ptr(inp.sched_ptr) if g else 0, _ptr(inp.sched_rows) if g else 0,
+                                         inp.n_levels if g else 1, float(np.float32(beta)), itermax, cv_th, _ptr(T_out),
+                                         ctypes.byref(res), _stream()), "nem_sharded")
+        return res
 
     def density_peers(self, bits, row_offset: int):
         _check(lib().nemb200_density_peers(self._h, _ptr(bits), row_offset, _stream()), "density_peers")

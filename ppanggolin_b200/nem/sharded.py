@@ -98,6 +98,13 @@ class CudaBackend:
     def criteria(self, T, beta):
         return self.plan.criteria(self.N, self.logf_full, T, self.graph, beta)
 
+    def run_device_loop(self, beta: float, itermax: int, cv_th: float):
+        """The whole run with the device-resident loop (peer mode only): no host synchronisation between iterations, the
+        convergence test runs on the replicated posteriors of every rank.  Returns (T, crit, n_iter, converged, status)."""
+        res = self.plan.nem_sharded(self.bits, self.row_offset, self.graph, beta, itermax, cv_th, self.T[0])
+        self.launches += 5 + 10 * (res.n_iter + 1) + 9
+        return self.T[0], list(res.crit), int(res.n_iter), bool(res.converged), int(res.status)
+
 
 @dataclass
 class EmOutcome:
@@ -177,6 +184,9 @@ class ShardedEM:
         return self.b.read_flags()
 
     def run(self, beta: float, itermax: int = 100, cv_th: float = 0.01) -> EmOutcome:
+        if getattr(self.b, "peer", False) and hasattr(self.b, "run_device_loop") and self.world > 1:
+            T, crit, it, converged, status = self.b.run_device_loop(beta, itermax, cv_th)
+            return EmOutcome(T, crit, it, converged, status)
         self.start(beta)
         it, converged, status = 0, False, 0
         while it < itermax and not converged and status == 0:
