@@ -196,6 +196,8 @@ struct nemb200_plan {
   bool with_run_buffers = false;
   bool batch_ell = false;         // batched runs: the schedule-ordered graph copy lives in the plan's block
   void* ell_in_block = nullptr;
+  int* spec_chg = nullptr;        // speculative sweep: change marks [2][rows], words [8]
+  int* spec_words = nullptr;
   double* run_logf = nullptr;
   float *run_Ta = nullptr, *run_Tb = nullptr;
   void* block = nullptr;          // the one device allocation everything above is carved from
@@ -231,6 +233,7 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
     // the device-resident loop of a sharded run (nemb200_nem_sharded): replicated posteriors and graph copy of ALL rows
     pl->run_Ta = ar.take<float>((size_t)pl->N_total * K); pl->run_Tb = ar.take<float>((size_t)pl->N_total * K);
     pl->ell_in_block = ar.take<char>((size_t)pl->N_total * (sizeof(int4) + kEllW * sizeof(int2)));
+    pl->spec_chg = ar.take<int>(2 * (size_t)pl->N_total); pl->spec_words = ar.take<int>(8);
   }
   // the sweep and the criteria run over all rows, also on a shard's plan; one region of ceil(N/warps) rows per warp
   pl->crit_terms = ar.take<float>(((size_t)pl->N_total + (size_t)pl->crit_blocks * 8) * K * 2);
@@ -247,7 +250,10 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
   }
   if (pl->with_run_buffers) {
     pl->run_logf = ar.take<double>(N * K); pl->run_Ta = ar.take<float>(N * K); pl->run_Tb = ar.take<float>(N * K);
-    if (pl->batch_ell) pl->ell_in_block = ar.take<char>(N * (sizeof(int4) + kEllW * sizeof(int2)));
+    if (pl->batch_ell) {
+      pl->ell_in_block = ar.take<char>(N * (sizeof(int4) + kEllW * sizeof(int2)));
+      pl->spec_chg = ar.take<int>(2 * N); pl->spec_words = ar.take<int>(8);
+    }
   }
 }
 
@@ -794,6 +800,7 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
   a.jacobi = (pl->flags & NEMB200_JACOBI) ? 1 : 0;
   a.maxdiff_bits = maxdiff_bits;
   a.ell_hdr = nullptr; a.ell_nb = nullptr; a.stamps = nullptr;
+  a.chg = nullptr; a.spec_words = nullptr; a.spec_limit = 0; a.spec_parity = 0;   // the host-polled driver sweeps by levels only
   a.wait_sig = nullptr; a.wait_n = 0; a.wait_epoch = 0; a.wait_err = nullptr;
   if (pl->sweep_waits) {
     a.wait_sig = pl->sig; a.wait_n = pl->world; a.wait_epoch = pl->epoch_dens; a.wait_err = pl->peer_err;

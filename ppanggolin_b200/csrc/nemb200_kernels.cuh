@@ -589,6 +589,11 @@ struct SweepArgs {
   int wait_n, wait_epoch;
   int* wait_err;
   unsigned long long* stamps;   // profiling builds (-DNEMB200_SWEEP_STAMPS): per CTA, %globaltimer at level start / end
+  // speculative sweep (see sweep_spec): per-row "changed in the previous / this round" marks and the sweep's bookkeeping
+  int* chg;                     // [2][N], may be null: level-scheduled sweep only
+  int* spec_words;              // [8]: 0..2 rotating "any row changed this round" flags, 3..4 rows changed by the last two sweeps
+  int spec_limit;               // speculative when the previous sweep changed at most this many rows
+  int spec_parity;              // this sweep adds its count to spec_words[3 + parity] and reads the other one
 };
 
 // One group of GS lanes (GS = power of two >= K) updates one row; lane `sub` of the group owns class `sub`.
@@ -670,13 +675,18 @@ __device__ __forceinline__ SweepPre<GS> sweep_preload_csr(const SweepArgs& a, lo
   return p;
 }
 
-template <int GS>
-__device__ __forceinline__ void sweep_finish(const SweepArgs& a, const SweepPre<GS>& p, int sub, float& wmax) {
+// MODE 0: the row's update as part of the in-order sweep (neighbours j < i from T_new); the posterior change against T_old
+//         goes into wmax.  Returns whether the row's posterior differs from T_old (any class).
+// MODE 1: speculative first round: every neighbour from T_old.  Returns whether the row's posterior differs from T_old.
+// MODE 2: speculative repair round: neighbours j < i from T_new.  Returns whether it differs from the row's previous T_new.
+template <int GS, int MODE = 0>
+__device__ __forceinline__ bool sweep_finish(const SweepArgs& a, const SweepPre<GS>& p, int sub, float& wmax) {
   const int K = a.K;
   const int k = sub < K ? sub : K - 1;
   const long long i = p.i;
   const double lf = a.logf[(size_t)i * K + k];
-  const float told = a.T_old[(size_t)i * K + k];
+  const float told = MODE == 2 ? __ldcg(a.T_new + (size_t)i * K + k) : a.T_old[(size_t)i * K + k];
+  const bool all_old = a.jacobi || MODE == 1;
   float ctx = 0.0f;
   // deg is the same in all lanes of the group; groups of one warp may differ, the shuffles below are group-local and
   // executed by every lane (invalid rows have deg = 0 but still take part)
@@ -690,7 +700,7 @@ __device__ __forceinline__ void sweep_finish(const SweepArgs& a, const SweepPre<
         const int jj = __shfl_sync(0xffffffffu, p.j[u / GS], u % GS, GS);
         wt[u] = __shfl_sync(0xffffffffu, p.w[u / GS], u % GS, GS);
         if (u < p.deg) {
-          const float* src = (!a.jacobi && jj < i) ? a.T_new : a.T_old;
+          const float* src = (!all_old && jj < i) ? a.T_new : a.T_old;
           c[u] = __ldcg(src + (size_t)jj * K + k);      // L2 read: T_new rows are written by other SMs in this launch
         }
       }
@@ -700,7 +710,7 @@ __device__ __forceinline__ void sweep_finish(const SweepArgs& a, const SweepPre<
       if (u < p.deg) ctx = __fadd_rn(ctx, __fmul_rn(wt[u], c[u]));
     for (int n = p.n0 + kEllW; n < p.n0 + p.deg; n++) {  // rows with more than kEllW neighbours
       const int j = a.col[n];
-      const float* src = (!a.jacobi && j < i) ? a.T_new : a.T_old;
+      const float* src = (!all_old && j < i) ? a.T_new : a.T_old;
       ctx = __fadd_rn(ctx, __fmul_rn(a.w[n], __ldcg(src + (size_t)j * K + k)));
     }
   }
@@ -731,11 +741,106 @@ __device__ __forceinline__ void sweep_finish(const SweepArgs& a, const SweepPre<
     for (int kk = 0; kk < K; kk++) sum = sum + __shfl_sync(0xffffffffu, e, kk, GS);
     cnew = (m == -INFINITY) ? (float)(1.0 / K) : (float)(e / sum);
   }
+  bool differs = false;
   if (p.valid && sub < K) {
     __stcg(a.T_new + (size_t)i * K + sub, cnew);
-    float dif = cnew - told;
-    if (dif < 0) dif = -dif;
-    wmax = fmaxf(wmax, dif);
+    differs = __float_as_uint(cnew) != __float_as_uint(told);
+    if (MODE == 0) {
+      float dif = cnew - told;
+      if (dif < 0) dif = -dif;
+      wmax = fmaxf(wmax, dif);
+    }
+  }
+  // any class of the row (the GS lanes of the group)
+  const unsigned m = __ballot_sync(0xffffffffu, differs);
+  const int lane = threadIdx.x & 31;
+  return ((m >> (lane & ~(GS - 1))) & (GS == 32 ? 0xffffffffu : ((1u << GS) - 1u))) != 0u;
+}
+
+// ---- speculative sweep -------------------------------------------------------------------------------------------------
+// In a converging run almost every posterior is saturated (exactly one-hot in float32) and does not change from one
+// iteration to the next, although every row formally depends on its lower-indexed neighbours.  The level-scheduled sweep
+// still pays a grid barrier and two dependent L2 round trips for each of the graph's levels (65-73 us for 200 000 rows in
+// 12 levels).  Speculation: round 0 updates ALL rows at once from the old posteriors (one level's worth of latency);
+// a row whose lower-indexed neighbour came out different from what the row used is repaired in the next round with the
+// neighbours' current values, and so on until a round changes nothing.  Dependencies only point to lower indices, so the
+// fixed point is unique and is the in-order sweep's result, bit for bit (a row's last repair evaluates the same
+// expression on the same inputs); rounds are bounded by the schedule depth, and in a converging run two or three rounds
+// that touch a handful of rows replace the twelve levels.  A racing read of a posterior that is being rewritten in the
+// same round is harmless: the writer's change mark sends the reader into the next round.
+template <int GS, class Bar>
+__device__ __forceinline__ void sweep_spec(const SweepArgs& a, const Bar& bar, float& wmax, int& n_changed) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (GS - 1), grp = lane / GS;
+  constexpr int RPW = 32 / GS;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long gtotal = nwarps * RPW;
+  int* chg_prev = a.chg;
+  int* chg_cur = a.chg + a.N;
+  volatile int* words = a.spec_words;
+  // round 0: every row from the old posteriors
+  {
+    bool any = false;
+    long long idx0 = warp_global * RPW;
+    if (idx0 < a.N) {
+      SweepPre<GS> cur = sweep_preload_slot<GS>(a, idx0 + grp, idx0 + grp < a.N, sub);
+      for (; idx0 < a.N; idx0 += gtotal) {
+        const long long nx = idx0 + gtotal;
+        SweepPre<GS> nxt = cur;
+        if (nx < a.N) nxt = sweep_preload_slot<GS>(a, nx + grp, nx + grp < a.N, sub);
+        const bool d = sweep_finish<GS, 1>(a, cur, sub, wmax);
+        if (cur.valid && sub == 0) __stcg(chg_prev + cur.i, d ? 1 : 0);
+        any = any || (cur.valid && d);
+        cur = nxt;
+      }
+    }
+    if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr((int*)&words[0], 1);
+  }
+  bar.sync();
+  // repair rounds
+  for (int r = 1;; r++) {
+    const int prev_flag = __ldcg((const int*)&words[(r - 1) % 3]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) words[(r + 1) % 3] = 0;     // used again two rounds from now
+    if (!prev_flag) break;
+    bool any = false;
+    for (long long idx0 = warp_global * RPW; idx0 < a.N; idx0 += gtotal) {
+      const long long idx = idx0 + grp;
+      SweepPre<GS> p = sweep_preload_slot<GS>(a, idx, idx < a.N, sub);
+      // dirty: a lower-indexed neighbour changed in the previous round (the lanes of the group hold the inline neighbours)
+      bool mine = false;
+#pragma unroll
+      for (int q = 0; q < SweepCfg<GS>::NS; q++) {
+        const int u = q * GS + sub;
+        if (p.valid && u < p.deg && u < kEllW && p.j[q] < p.i) mine = mine || (__ldcg(chg_prev + p.j[q]) != 0);
+      }
+      if (p.valid && sub == 0)
+        for (int n = p.n0 + kEllW; n < p.n0 + p.deg; n++) { const int j = a.col[n]; if (j < p.i) mine = mine || (__ldcg(chg_prev + j) != 0); }
+      const unsigned bal = __ballot_sync(0xffffffffu, mine);
+      const bool dirty = ((bal >> (lane & ~(GS - 1))) & (GS == 32 ? 0xffffffffu : ((1u << GS) - 1u))) != 0u;
+      bool d = false;
+      if (bal != 0u) {                                                    // warp-uniform: someone in the warp repairs a row
+        SweepPre<GS> q = p;
+        q.valid = p.valid && dirty;
+        if (!q.valid) q.deg = 0;
+        d = sweep_finish<GS, 2>(a, q, sub, wmax) && q.valid;
+      }
+      if (p.valid && sub == 0) __stcg(chg_cur + p.i, d ? 1 : 0);
+      any = any || d;
+    }
+    if (__any_sync(0xffffffffu, any) && lane == 0) atomicOr((int*)&words[r % 3], 1);
+    int* t = chg_prev; chg_prev = chg_cur; chg_cur = t;
+    bar.sync();
+  }
+  // the sweep's change against the previous posteriors (nem_alg.c:2160-2173) and how many rows it changed
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < a.N; t += (long long)gridDim.x * blockDim.x) {
+    bool differs = false;
+    for (int k = 0; k < a.K; k++) {
+      const float n = __ldcg(a.T_new + (size_t)t * a.K + k), o = a.T_old[(size_t)t * a.K + k];
+      wmax = fmaxf(wmax, fabsf(n - o));
+      differs = differs || (__float_as_uint(n) != __float_as_uint(o));
+    }
+    n_changed += differs ? 1 : 0;
   }
 }
 
@@ -771,15 +876,22 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   float wmax = 0.0f;
+  int n_changed = 0;            // rows whose posterior differs from T_old (counted by the lane with sub == 0)
+  auto fin = [&](const SweepPre<GS>& p) { if (sweep_finish<GS>(a, p, sub, wmax) && p.valid && sub == 0) n_changed++; };
   if (a.wait_sig != nullptr) {     // every CTA checks the flags itself (phase 1 = densities): no wait kernel in front
     peer_wait_lane(a.wait_sig, a.wait_n, 1, a.wait_epoch, a.wait_err);
     __syncthreads();
   }
-  if (a.level_ptr == nullptr) {
+  bool spec = false;
+  if (COOP && a.level_ptr != nullptr && a.chg != nullptr && a.n_levels > 3)
+    spec = __ldcg(a.spec_words + 3 + (a.spec_parity ^ 1)) <= a.spec_limit;     // the previous sweep changed few rows (grid-uniform)
+  if (spec) {
+    sweep_spec<GS>(a, bar, wmax, n_changed);
+  } else if (a.level_ptr == nullptr) {
     for (long long i0 = warp_global * RPW; i0 < a.N; i0 += nwarps * RPW) {
       const long long i = i0 + grp;
       const SweepPre<GS> p = sweep_preload_csr<GS>(a, i, i < a.N, sub);
-      sweep_finish<GS>(a, p, sub, wmax);
+      fin(p);
     }
   } else {
     // Levels are separated by grid-wide barriers; a run of consecutive small levels (deep, thin tails of the schedule)
@@ -811,7 +923,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
             for (long long idx0 = b + (long long)block_warp * RPW; idx0 < e; idx0 += (long long)block_warps * RPW) {
               const long long idx = idx0 + grp;
               const SweepPre<GS> p = sweep_preload_slot<GS>(a, idx, idx < e, sub);
-              sweep_finish<GS>(a, p, sub, wmax);
+              fin(p);
             }
             __syncthreads();
           }
@@ -823,8 +935,8 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
       } else {
         long long idx = b + gidx;
         if (COOP && have_pre) {
-          sweep_finish<GS>(a, p0, sub, wmax);
-          if (b + gtotal < e) sweep_finish<GS>(a, p1, sub, wmax);   // grid-uniform condition
+          fin(p0);
+          if (b + gtotal < e) fin(p1);   // grid-uniform condition
           idx += 2 * gtotal;
         }
         // the rest of the level, software-pipelined: the graph side of the group's next row (one L2 round trip that does
@@ -836,7 +948,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
             const long long nx = idx0 + gtotal;
             SweepPre<GS> nxt = cur;
             if (nx < e) nxt = sweep_preload_slot<GS>(a, nx + grp, nx + grp < e, sub);
-            sweep_finish<GS>(a, cur, sub, wmax);
+            fin(cur);
             cur = nxt;
           }
         }
@@ -858,6 +970,10 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
   }
   for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
   if (lane == 0 && wmax > 0.0f) atomicMax(a.maxdiff_bits, __float_as_uint(wmax));  // non-negative floats order as uints
+  if (a.chg != nullptr) {           // rows this sweep changed: the next sweep's choice between levels and speculation
+    for (int off = 16; off > 0; off >>= 1) n_changed += __shfl_xor_sync(0xffffffffu, n_changed, off);
+    if (lane == 0 && n_changed > 0) atomicAdd(a.spec_words + 3 + a.spec_parity, n_changed);
+  }
 }
 
 template <bool COOP, int GS>
@@ -2309,6 +2425,7 @@ struct BatchInst {
   float* T[2];
   unsigned* state;             // kSt* words; P.status aliases state + kStStatus
   unsigned* barrier;           // InstBar counter of the sweep
+  int* chg; int* spec_words;   // speculative sweep: per-row change marks [2][N], bookkeeping words [8] (null: level sweeps only)
   char* zero_from; long long zero_bytes;   // statistics cleared before every M-step
   float base_prop;
   float eps_init[NEMB200_MAX_K];
@@ -2346,6 +2463,10 @@ __global__ void __launch_bounds__(256) k_b_start(const BatchInst* __restrict__ B
   if (tid == 0) {
     I.state[kStMaxdiff] = 0u; I.state[kStActive] = I.itermax >= 1 ? 1u : 0u; I.state[kStIter] = 0u; I.state[kStConverged] = 0u;
     *I.barrier = 0u;
+    if (I.spec_words != nullptr) {
+      for (int q = 0; q < 8; q++) I.spec_words[q] = 0;
+      I.spec_words[3] = 0x3fffffff;      // "the previous sweep changed everything": the first iteration sweeps by levels
+    }
   }
   if (tid < I.K) I.fin_tickets[tid] = 0;
 }
@@ -2516,6 +2637,7 @@ __global__ void __launch_bounds__(COOP ? 1024 : 256) k_b_sweep(const BatchInst* 
   a.rowptr = I.rowptr; a.col = I.col; a.w = I.w; a.beta = beta; a.logspace = I.logspace; a.jacobi = I.jacobi;
   a.maxdiff_bits = I.state + (s >= 1 ? kStMaxdiff : kStWords - 1);   // the start sweeps are not convergence-tested
   a.ell_hdr = I.ell_hdr; a.ell_nb = I.ell_nb; a.stamps = nullptr;
+  a.chg = s >= 1 ? I.chg : nullptr; a.spec_words = I.spec_words; a.spec_limit = (int)(I.N / 32); a.spec_parity = s & 1;
   a.wait_sig = nullptr; a.wait_n = 0; a.wait_epoch = 0; a.wait_err = nullptr;
   if (I.world > 1 && s >= 0) {        // the densities of this sweep's epoch, pushed by every rank (the start sweep with beta
     a.wait_sig = I.sig; a.wait_n = I.world; a.wait_epoch = I.epoch0 + s; a.wait_err = I.peer_err;   // reuses those of s = 0)
@@ -2553,6 +2675,7 @@ __global__ void __launch_bounds__(256) k_b_poll(const BatchInst* __restrict__ B,
     }
     I.state[kStMaxdiff] = 0u;
     *I.barrier = 0u;
+    if (I.spec_words != nullptr) I.spec_words[3 + ((s + 1) & 1)] = 0;
     if (!still) I.state[kStActive] = 0u;
   }
   // last instance to report publishes the group's flag (the ticket counter is the scratch word's high half)
