@@ -259,6 +259,10 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
 
 static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int64_t D, int64_t row_stride_words,
                       int32_t K, int32_t free_disp, uint32_t flags, bool with_run_buffers, bool batch_ell = false);
+static bool batch_enabled_for_plans() {
+  const char* e = getenv("NEMB200_NO_BATCH");
+  return !(e && atoi(e) != 0);
+}
 
 extern "C" int nemb200_abi_version(void) { return NEMB200_ABI_VERSION; }
 extern "C" const char* nemb200_last_error(void) { return g_err.c_str(); }
@@ -298,10 +302,14 @@ static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int6
   Arena real;
   real.base = (char*)pl->block; real.counting = false;
   plan_layout(pl, real);
-  if (cudaMemset(pl->sig, 0, 4 * kMaxPeers * sizeof(int)) != cudaSuccess || cudaMemset(pl->peer_err, 0, sizeof(int)) != cudaSuccess || cudaMemset(pl->bcast_ticket, 0, sizeof(int)) != cudaSuccess ||
-      cudaMemset(pl->fin_tickets, 0, K * sizeof(int)) != cudaSuccess) {
-    nemb200_plan_destroy(pl);
-    return fail(NEMB200_ERR_CUDA, "plan_create: memset");
+  // whole-run plans of the device-resident loop clear their words in k_b_start; the stepwise / sharded interfaces need the
+  // exchange words and the finalize tickets cleared here (blocking memsets: 10-20 us each, kept off the per-run path)
+  if (!with_run_buffers || (flags & NEMB200_PEER_EXCHANGE) || !batch_enabled_for_plans()) {
+    if (cudaMemset(pl->sig, 0, 4 * kMaxPeers * sizeof(int)) != cudaSuccess || cudaMemset(pl->peer_err, 0, sizeof(int)) != cudaSuccess || cudaMemset(pl->bcast_ticket, 0, sizeof(int)) != cudaSuccess ||
+        cudaMemset(pl->fin_tickets, 0, K * sizeof(int)) != cudaSuccess) {
+      nemb200_plan_destroy(pl);
+      return fail(NEMB200_ERR_CUDA, "plan_create: memset");
+    }
   }
   *out = pl;
   return NEMB200_OK;

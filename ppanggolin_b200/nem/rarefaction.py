@@ -7,18 +7,23 @@ Same names, arguments and results for the partitioning part: genome samples of g
 soft core and accessory counts and the NEM partition counts, written to ``rarefaction.csv`` with the reference's
 columns (rarefaction.py:214-252).  Differences, all below the API:
 
-* no fork pool (rarefaction.py:707): a CUDA context does not survive ``fork``; samples run one after the other, each
-  instance derived from the cached array form of the pangenome (``export_arrays``) and run through the C ABI;
-* the per-sample core / soft-core statistics use the presence tensor (column gather + row sums) instead of gmpy2
-  bitarrays (rarefaction.py:657-684) -- same integer counts;
-* the Heaps'-law fit and the plotly figures (``draw_curve``, rarefaction.py:254-535) are not part of the hot path: the
-  CSV is written, the fit and the HTML are produced only when scipy / plotly are importable (``draw_curve``).
+* no fork pool (rarefaction.py:707): a CUDA context does not survive ``fork``; with a fixed K the samples of one size are
+  exported and run as batches (one CUDA exporter call + one batched EM call per 16 samples, ``raref_batch``), the others
+  one after the other, every instance derived on the device from the array form of the pangenome (``export_device``);
+* the per-sample core / soft-core statistics come from a popcount kernel over the bit-packed presence matrix
+  (``nemb200_subset_counts``) instead of gmpy2 bitarrays (rarefaction.py:657-684) -- same integer counts;
+* ``draw_curve`` (rarefaction.py:205-535) writes ``rarefaction.csv`` and the Heaps'-law fit ``rarefaction_parameters.csv``
+  (scipy); the plotly figure is produced only when plotly is importable -- neither is part of the hot path;
+* ``launch`` / ``subparser`` / ``parser_rarefaction`` (rarefaction.py:727-912): same flags, defaults and types.
 """
 from __future__ import annotations
 
+import argparse
 import logging
+import os
 import random
 import tempfile
+import time
 from collections import Counter
 from pathlib import Path
 from typing import Dict, List, Tuple, Union
@@ -260,3 +265,121 @@ def make_rarefaction_curve(pangenome, output: Path, tmpdir: Path = None, beta: f
     ppp._ARRAYS["pan"], ppp._ARRAYS["arrays"] = None, None
     logger.info("Done making the rarefaction curves")
     return samp_nb_per_part
+
+
+def draw_curve(output: Path, data: list, max_sampling: int = 10):
+    """rarefaction.py:205-535: ``rarefaction.csv``, the Heaps'-law fit kappa * n^gamma of every partition on the samples of
+    more than 15 genomes (``rarefaction_parameters.csv``: partition, kappa, gamma, their standard errors, IQR area) and,
+    when plotly is available, ``rarefaction_curve.html``."""
+    import numpy
+    from scipy import optimize as optimization
+    output = Path(output)
+    write_rarefaction_csv(output, data)
+    cols = {c: numpy.array([float("nan") if part.get(k, "NA") == "NA" else float(part[k]) for part in data])
+            for c, k in (("genomes_count", "nborgs"), ("persistent", "persistent"), ("shell", "shell"), ("cloud", "cloud"),
+                         ("undefined", "undefined"), ("exact_core", "exact_core"), ("exact_accessory", "exact_accessory"),
+                         ("soft_core", "soft_core"), ("soft_accessory", "soft_accessory"))}
+    cols["pangenome"] = cols["exact_core"] + cols["exact_accessory"]
+
+    def heap_law(n, p_kappa, p_gamma):
+        return p_kappa * n ** p_gamma
+
+    def poly_area(p_x, p_y):
+        return 0.5 * numpy.abs(numpy.dot(p_x, numpy.roll(p_y, 1)) - numpy.dot(p_y, numpy.roll(p_x, 1)))
+
+    nb_org_min_fitting = 15
+    fits = {}
+    with open(output / "rarefaction_parameters.csv", "w") as params_file:
+        params_file.write("partition,kappa,gamma,kappa_std_error,gamma_std_error,IQR_area\n")
+        for partition in ["persistent", "shell", "cloud", "undefined", "exact_core", "exact_accessory", "soft_core", "soft_accessory",
+                          "pangenome"]:
+            sizes = [i for i in range(1, max_sampling + 1) if numpy.any(cols["genomes_count"] == i)]
+            q25 = [numpy.nanpercentile(cols[partition][cols["genomes_count"] == i], 25) for i in sizes]
+            q75 = [numpy.nanpercentile(cols[partition][cols["genomes_count"] == i], 75) for i in sizes]
+            area_iqr = poly_area(sizes + list(reversed(sizes)), q25 + q75) if sizes else 0.0
+            sel = (cols["genomes_count"] > nb_org_min_fitting) & ~numpy.isnan(cols[partition])
+            try:
+                res = optimization.curve_fit(heap_law, cols["genomes_count"][sel], cols[partition][sel], numpy.array([0.0, 0.0]))
+                kappa, gamma = res[0]
+                error_k, error_g = numpy.sqrt(numpy.diag(res[1]))
+                if numpy.isinf(error_k) and numpy.isinf(error_g):
+                    params_file.write(",".join([partition, "NA", "NA", "NA", "NA", str(area_iqr)]) + "\n")
+                else:
+                    params_file.write(",".join([partition, str(kappa), str(gamma), str(error_k), str(error_g), str(area_iqr)]) + "\n")
+                    fits[partition] = (kappa, gamma)
+            except (TypeError, RuntimeError, ValueError):  # too few points, no convergence
+                params_file.write(",".join([partition, "NA", "NA", "NA", "NA", str(area_iqr)]) + "\n")
+    try:
+        import plotly.graph_objs as go
+        import plotly.offline as out_plotly
+    except ImportError:
+        logging.getLogger("PPanGGOLiN").warning("plotly is not installed: rarefaction_curve.html is not drawn")
+        return fits
+    traces = []
+    for partition, (kappa, gamma) in fits.items():
+        xs = list(range(nb_org_min_fitting + 1, max_sampling + 1))
+        traces.append(go.Scatter(x=xs, y=[heap_law(x, kappa, gamma) for x in xs], name=partition + ": Heaps' law", mode="lines"))
+        traces.append(go.Scatter(x=cols["genomes_count"].tolist(), y=cols[partition].tolist(), name=partition, mode="markers"))
+    layout = go.Layout(title="Rarefaction curve", xaxis=dict(title="size of genome subsets"), yaxis=dict(title="# of gene families"),
+                       plot_bgcolor="#ffffff")
+    out_plotly.plot(go.Figure(data=traces, layout=layout), filename=(output / "rarefaction_curve.html").as_posix(), auto_open=False)
+    return fits
+
+
+def launch(args: argparse.Namespace):
+    """rarefaction.py:727-755"""
+    ppp.mk_outdir(args.output, args.force)
+    pangenome = ppp.Pangenome()
+    pangenome.add_file(args.pangenome)
+    make_rarefaction_curve(pangenome=pangenome, output=args.output, tmpdir=args.tmpdir, beta=args.beta, depth=args.depth,
+                           min_sampling=args.min, max_sampling=args.max, sm_degree=args.max_degree_smoothing,
+                           free_dispersion=args.free_dispersion, chunk_size=args.chunk_size, kval=args.nb_of_partitions,
+                           krange=args.krange, cpu=args.cpu, seed=args.seed, kestimate=args.reestimate_K, soft_core=args.soft_core,
+                           disable_bar=args.disable_prog_bar)
+
+
+def subparser(sub_parser: argparse._SubParsersAction) -> argparse.ArgumentParser:
+    """rarefaction.py:758-772"""
+    parser = sub_parser.add_parser("rarefaction", description="Compute the rarefaction curve of the pangenome",
+                                   formatter_class=argparse.RawTextHelpFormatter)
+    parser_rarefaction(parser)
+    return parser
+
+
+def parser_rarefaction(parser: argparse.ArgumentParser):
+    """rarefaction.py:775-912: same flags, defaults and types."""
+    required = parser.add_argument_group(title="Required arguments", description="One of the following arguments is required :")
+    required.add_argument("-p", "--pangenome", required=False, type=Path, help="The pangenome .h5 file")
+    optional = parser.add_argument_group(title="Optional arguments")
+    optional.add_argument("-b", "--beta", required=False, default=2.5, type=float,
+                          help="beta is the strength of the smoothing using the graph topology during  partitioning. "
+                               "0 will deactivate spatial smoothing.")
+    optional.add_argument("--depth", required=False, default=30, type=int, help="Number of samplings at each sampling point")
+    optional.add_argument("--min", required=False, default=1, type=int, help="Minimum number of genomes in a sample")
+    optional.add_argument("--max", required=False, type=float, default=100,
+                          help="Maximum number of genomes in a sample (if above the number of provided genomes, "
+                               "the provided genomes will be the maximum)")
+    optional.add_argument("-ms", "--max_degree_smoothing", required=False, default=10, type=float,
+                          help="max. degree of the nodes to be included in the smoothing process.")
+    optional.add_argument("-o", "--output", required=False, type=Path,
+                          default=Path(f"ppanggolin_output{time.strftime('DATE%Y-%m-%d_HOUR%H.%M.%S', time.localtime())}"
+                                       f"_PID{str(os.getpid())}"), help="Output directory")
+    optional.add_argument("-fd", "--free_dispersion", required=False, default=False, action="store_true",
+                          help="use if the dispersion around the centroid vector of each partition during must be free."
+                               " It will be the same for all genomes by default.")
+    optional.add_argument("-ck", "--chunk_size", required=False, default=500, type=int,
+                          help="Size of the chunks when performing partitioning using chunks of genomes. "
+                               "Chunk partitioning will be used automatically if the number of genomes is above this number.")
+    optional.add_argument("-K", "--nb_of_partitions", required=False, default=-1, type=int,
+                          help="Number of partitions to use. Must be at least 2. By default reuse K if it exists else compute it.")
+    optional.add_argument("--reestimate_K", required=False, action="store_true",
+                          help=" Will recompute the number of partitions for each sample "
+                               "(between the values provided by --krange) (VERY intensive. Can take a long time.)")
+    optional.add_argument("-Kmm", "--krange", nargs=2, required=False, type=int, default=[3, -1],
+                          help="Range of K values to test when detecting K automatically. "
+                               "Default between 3 and the K previously computed if there is one, or 20 if there are none.")
+    optional.add_argument("--soft_core", required=False, type=float, default=0.95, help="Soft core threshold")
+    optional.add_argument("-se", "--seed", type=int, default=42, help="seed used to generate random numbers")
+    optional.add_argument("-c", "--cpu", required=False, default=1, type=int, help="Number of available cpus")
+    optional.add_argument("--tmpdir", required=False, type=str, default=Path(tempfile.gettempdir()),
+                          help="directory for storing temporary files")

@@ -113,3 +113,22 @@ def test_run_partitioning_requires_export_and_rejects_random_init(tmp_path):
         part.run_partitioning(tmp_path / "nothing", 10)
     with pytest.raises(NotImplementedError):
         part.run_partitioning(tmp_path, 10, init="random")
+
+
+def test_rarefaction_parser_flags_match_reference_defaults():
+    """parser_rarefaction (rarefaction.py:775-912): same flags, defaults and types as the reference."""
+    import argparse
+    from pathlib import Path
+    from ppanggolin_b200.nem import rarefaction as raref
+    ap = argparse.ArgumentParser()
+    raref.parser_rarefaction(ap)
+    a = ap.parse_args([])
+    assert (a.beta, a.depth, a.min, a.max, a.max_degree_smoothing) == (2.5, 30, 1, 100, 10)
+    assert isinstance(a.max, (int, float)) and isinstance(ap.parse_args(["--max", "7"]).max, float)
+    assert (a.free_dispersion, a.chunk_size, a.nb_of_partitions, a.reestimate_K, a.krange) == (False, 500, -1, False, [3, -1])
+    assert (a.soft_core, a.seed, a.cpu) == (0.95, 42, 1) and a.pangenome is None
+    b = ap.parse_args(["-p", "x.h5", "-b", "3", "--depth", "5", "-ms", "4", "-fd", "-ck", "50", "-K", "4", "--reestimate_K",
+                       "-Kmm", "3", "9", "--soft_core", "0.9", "-se", "7", "-c", "3"])
+    assert b.pangenome == Path("x.h5") and b.krange == [3, 9] and b.free_dispersion and b.reestimate_K and b.max_degree_smoothing == 4.0
+    sub = argparse.ArgumentParser().add_subparsers()
+    assert raref.subparser(sub).prog.endswith("rarefaction")
