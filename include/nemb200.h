@@ -147,7 +147,7 @@ int nemb200_density(nemb200_plan* plan, const uint32_t* bits, double* logf, void
 
 /* ---- row-sharded runs: the two exchange steps of an iteration over NVLink peer memory, fused into the kernels ------
  * One process per GPU; every rank creates its plan with NEMB200_PEER_EXCHANGE, exports (CUDA IPC handle of the plan's
- * block + 4 offsets), the driver all-gathers those 96 bytes per rank out of band (torch.distributed), and every rank
+ * block + 16 offsets), the driver all-gathers those 192 bytes per rank out of band (torch.distributed), and every rank
  * attaches.  From then on
  *   - nemb200_density_peers stores the shard's log-densities into the log-density buffer of EVERY rank (peer stores)
  *     and publishes an epoch; nemb200_peer_wait_densities blocks the stream until all ranks have published it: together
@@ -155,9 +155,10 @@ int nemb200_density(nemb200_plan* plan, const uint32_t* bits, double* logf, void
  *   - nemb200_mstep_finalize publishes / waits for the statistics epoch and reads every rank's statistic blocks (peer
  *     loads), adding them in rank order: the all-reduce of the M-step, identical parameters on every rank.
  * world <= 8 (one NVSwitch box).  The reference has no counterpart (one process per NEM instance, partition.py:505). */
-int nemb200_peer_export(nemb200_plan* plan, unsigned char handle_out[64], int64_t offsets_out[4]);
+#define NEMB200_PEER_OFFSETS 16
+int nemb200_peer_export(nemb200_plan* plan, unsigned char handle_out[64], int64_t offsets_out[NEMB200_PEER_OFFSETS]);
 int nemb200_peer_attach(nemb200_plan* plan, int32_t world, int32_t rank, const unsigned char* handles /*world*64*/,
-                        const int64_t* offsets /*world*4*/);
+                        const int64_t* offsets /*world*NEMB200_PEER_OFFSETS*/);
 int nemb200_peer_logf(nemb200_plan* plan, double** logf_full);
 int nemb200_density_peers(nemb200_plan* plan, const uint32_t* bits, int64_t row_offset, void* stream);
 int nemb200_peer_wait_densities(nemb200_plan* plan, void* stream);

@@ -168,6 +168,7 @@ struct nemb200_plan {
   bool attached = false;
   void* peer_base[kMaxPeers] = {nullptr};
   double* peer_logf[kMaxPeers] = {nullptr};
+  PeerParams peer_params{};      // the ranks' parameter arrays (column-sliced finalize of the device-resident sharded loop)
   const int* peer_iblock[kMaxPeers] = {nullptr};
   const double* peer_dblock[kMaxPeers] = {nullptr};
   int epoch_stats = 0, epoch_dens = 0, epoch_run = 0;
@@ -692,7 +693,7 @@ extern "C" int nemb200_density(nemb200_plan* pl, const uint32_t* bits, double* l
 }
 
 // ---- row-sharded exchange over peer memory -------------------------------------------------------------------------
-extern "C" int nemb200_peer_export(nemb200_plan* pl, unsigned char handle_out[64], int64_t offsets_out[4]) {
+extern "C" int nemb200_peer_export(nemb200_plan* pl, unsigned char handle_out[64], int64_t offsets_out[NEMB200_PEER_OFFSETS]) {
   if (!pl || !handle_out || !offsets_out) return fail(NEMB200_ERR_ARG, "peer_export: null argument");
   if (!pl->logf_full) return fail(NEMB200_ERR_ARG, "peer_export: plan was not created with NEMB200_PEER_EXCHANGE");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -704,6 +705,11 @@ extern "C" int nemb200_peer_export(nemb200_plan* pl, unsigned char handle_out[64
   offsets_out[1] = (const char*)pl->fsum - base;
   offsets_out[2] = (const char*)pl->logf_full - base;
   offsets_out[3] = (const char*)pl->sig - base;
+  offsets_out[4] = (const char*)pl->P.mu - base; offsets_out[5] = (const char*)pl->P.eps - base;
+  offsets_out[6] = (const char*)pl->P.L - base; offsets_out[7] = (const char*)pl->P.m1 - base;
+  offsets_out[8] = (const char*)pl->P.valid - base; offsets_out[9] = (const char*)pl->fin_partial - base;
+  offsets_out[10] = (const char*)pl->P.has_half - base;
+  for (int q = 11; q < NEMB200_PEER_OFFSETS; q++) offsets_out[q] = 0;
   return NEMB200_OK;
 }
 
@@ -724,11 +730,17 @@ extern "C" int nemb200_peer_attach(nemb200_plan* pl, int32_t world, int32_t rank
       pl->peer_base[r] = p;
       base = (char*)p;
     }
-    pl->peer_iblock[r] = (const int*)(base + offsets[r * 4 + 0]);
-    pl->peer_dblock[r] = (const double*)(base + offsets[r * 4 + 1]);
-    pl->peer_logf[r] = (double*)(base + offsets[r * 4 + 2]);
-    sig_host[r] = (int*)(base + offsets[r * 4 + 3]);
+    const int64_t* o = offsets + (size_t)r * NEMB200_PEER_OFFSETS;
+    pl->peer_iblock[r] = (const int*)(base + o[0]);
+    pl->peer_dblock[r] = (const double*)(base + o[1]);
+    pl->peer_logf[r] = (double*)(base + o[2]);
+    sig_host[r] = (int*)(base + o[3]);
+    pl->peer_params.mu[r] = (float*)(base + o[4]); pl->peer_params.eps[r] = (float*)(base + o[5]);
+    pl->peer_params.L[r] = (double*)(base + o[6]); pl->peer_params.m1[r] = (uint32_t*)(base + o[7]);
+    pl->peer_params.valid[r] = (uint32_t*)(base + o[8]); pl->peer_params.fin_partial[r] = (double*)(base + o[9]);
+    pl->peer_params.has_half[r] = (int*)(base + o[10]);
   }
+  pl->peer_params.n = world; pl->peer_params.rank = rank;
   CK(cudaMemcpy(pl->sig_ptrs, sig_host, sizeof sig_host, cudaMemcpyHostToDevice));
   pl->world = world; pl->rank = rank; pl->attached = true;
   return NEMB200_OK;

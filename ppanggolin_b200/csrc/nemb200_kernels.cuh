@@ -76,6 +76,12 @@ struct PeerOut {            // k_peer_broadcast: ptr[1..n-1] = the peers' buffer
   int n;
   long long row_off;
 };
+struct PeerParams {         // column-sliced finalize of a row-sharded run: where a rank writes its column chunks' results
+  float* mu[kMaxPeers]; float* eps[kMaxPeers]; double* L[kMaxPeers];
+  uint32_t* m1[kMaxPeers]; uint32_t* valid[kMaxPeers];
+  double* fin_partial[kMaxPeers]; int* has_half[kMaxPeers];
+  int n, rank;
+};
 struct PeerStats {          // where k_mstep_finalize reads: the statistic blocks of the n ranks
   const int* iblock[kMaxPeers];     // cnt[K][Dpad] followed by nk_cnt[K]
   const double* dblock[kMaxPeers];  // fsum[K][Dpad] followed by nk_fz[K]
@@ -1657,12 +1663,19 @@ k_mstep_fuzzy_mma(const uint32_t* __restrict__ bits, int Ws, int K, int D, const
 // dispersion of "sk_" (nem_mod.c:1053-1068, MISSING_IGNORE) and the E-step constants L_k, B_k.
 constexpr int kFinCols = 1024;
 
+__device__ __forceinline__ void finalize_class_scalars(const Params& P, int k, double nk, int nchunk, const double* __restrict__ partial,
+                                                       long long N_total, int lane);
+
+// With `pp` (row-sharded run, device-resident loop) the column chunks are dealt out to the ranks: a rank reduces only its
+// chunks (1 / n of the peer loads) and writes their centres, planes, dispersions and partial sums into EVERY rank's
+// parameter block (peer stores); the class scalars follow in finalize_scalars_body after a flag barrier.
 __device__ __forceinline__ void
 mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, double* __restrict__ partial /*[K][nchunk][2]*/,
-                    int* __restrict__ tickets /*[K]*/) {
+                    int* __restrict__ tickets /*[K]*/, const PeerParams* pp = nullptr) {
   __shared__ double s_red[8][2];
   __shared__ int s_last;
   const int k = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const int nw = pp != nullptr ? pp->n : 1;                 // ranks that receive this CTA's results
   const int D = P.D, Dpad = P.Dpad, Ws = P.Ws;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t KD = (size_t)P.K * Dpad;
@@ -1674,6 +1687,7 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
     if (threadIdx.x == 0 && chunk == 0) atomicMax(P.status, 1);
     return;
   }
+  if (pp != nullptr && chunk % pp->n != pp->rank) return;   // another rank's chunk
   double iner_sum = 0.0, b_sum = 0.0;
   int any_half = 0;
 #pragma unroll
@@ -1703,27 +1717,32 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
       if (w0 > half) { m = 0.0f; iner = s1; }
       else if (w0 < half) { m = 1.0f; iner = s0; }
       else { m = 0.5f; iner = 0.5 * nk; any_half = 1; }   // tie: midway between a 0 and a 1 (nem_mod.c:1463-1471)
-      P.mu[(size_t)k * D + d] = m;
+      if (pp == nullptr) P.mu[(size_t)k * D + d] = m;
+      else for (int q = 0; q < nw; q++) pp->mu[q][(size_t)k * D + d] = m;
       if (P.free_disp) {
         const float e = (float)(iner / nk);                // nem_mod.c:1162-1163
-        P.eps[(size_t)k * D + d] = e;
         double Lv;
         if (e > kEps) { Lv = log((double)((1.0f - e) / e)); b_sum += log((double)(1.0f - e)); }  // nem_mod.c:660
         else Lv = INFINITY;
-        P.L[(size_t)k * Dpad + d] = Lv;
+        if (pp == nullptr) { P.eps[(size_t)k * D + d] = e; P.L[(size_t)k * Dpad + d] = Lv; }
+        else for (int q = 0; q < nw; q++) { pp->eps[q][(size_t)k * D + d] = e; pp->L[q][(size_t)k * Dpad + d] = Lv; }
       }
     } else if (P.free_disp && d < Dpad) {
-      P.L[(size_t)k * Dpad + d] = 0.0;
+      if (pp == nullptr) P.L[(size_t)k * Dpad + d] = 0.0;
+      else for (int q = 0; q < nw; q++) pp->L[q][(size_t)k * Dpad + d] = 0.0;
     }
     iner_sum += iner;
     const unsigned b1 = __ballot_sync(0xffffffffu, m == 1.0f);
     const unsigned bv = __ballot_sync(0xffffffffu, m != 0.5f);
     if (lane == 0 && (d >> 5) < Ws) {
-      P.m1[(size_t)k * Ws + (d >> 5)] = b1;
-      P.valid[(size_t)k * Ws + (d >> 5)] = bv;
+      if (pp == nullptr) { P.m1[(size_t)k * Ws + (d >> 5)] = b1; P.valid[(size_t)k * Ws + (d >> 5)] = bv; }
+      else for (int q = 0; q < nw; q++) { pp->m1[q][(size_t)k * Ws + (d >> 5)] = b1; pp->valid[q][(size_t)k * Ws + (d >> 5)] = bv; }
     }
   }
-  if (__any_sync(0xffffffffu, any_half) && lane == 0) atomicOr(P.has_half, 1);
+  if (__any_sync(0xffffffffu, any_half) && lane == 0) {
+    if (pp == nullptr) atomicOr(P.has_half, 1);
+    else for (int q = 0; q < nw; q++) atomicOr(pp->has_half[q], 1);
+  }
   for (int off = 16; off > 0; off >>= 1) {
     iner_sum += __shfl_xor_sync(0xffffffffu, iner_sum, off);
     b_sum += __shfl_xor_sync(0xffffffffu, b_sum, off);
@@ -1733,14 +1752,33 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
   if (threadIdx.x == 0) {
     double t0 = 0.0, t1 = 0.0;
     for (int q = 0; q < 8; q++) { t0 += s_red[q][0]; t1 += s_red[q][1]; }
-    partial[((size_t)k * nchunk + chunk) * 2 + 0] = t0;
-    partial[((size_t)k * nchunk + chunk) * 2 + 1] = t1;
-    __threadfence();
-    s_last = (atomicAdd(&tickets[k], 1) == nchunk - 1);
+    if (pp != nullptr) {                                   // every rank receives the partials; the scalars follow after the barrier
+      for (int q = 0; q < nw; q++) {
+        pp->fin_partial[q][((size_t)k * nchunk + chunk) * 2 + 0] = t0;
+        pp->fin_partial[q][((size_t)k * nchunk + chunk) * 2 + 1] = t1;
+      }
+      __threadfence_system();
+      s_last = 0;
+    } else {
+      partial[((size_t)k * nchunk + chunk) * 2 + 0] = t0;
+      partial[((size_t)k * nchunk + chunk) * 2 + 1] = t1;
+      __threadfence();
+      s_last = (atomicAdd(&tickets[k], 1) == nchunk - 1);
+    }
   }
   __syncthreads();
+  if (pp != nullptr) { __threadfence_system(); return; }
   if (!s_last || wid != 0) return;
   __threadfence();
+  finalize_class_scalars(P, k, nk, nchunk, partial, N_total, lane);
+  if (lane == 0) tickets[k] = 0;  // ready for the next M-step
+}
+
+// class scalars from the chunk partials (added in chunk order: deterministic): proportion (nem_mod.c:455-459), the shared
+// dispersion of "sk_" (nem_mod.c:1053-1068, MISSING_IGNORE) and the E-step constants L_k, B_k.  One warp.
+__device__ __forceinline__ void finalize_class_scalars(const Params& P, int k, double nk, int nchunk, const double* __restrict__ partial,
+                                                       long long N_total, int lane) {
+  const int D = P.D;
   // chunk partials added in chunk order (deterministic); the loads of 32 chunks are in flight together
   double tot_iner = 0.0, tot_b = 0.0;
   for (int c0 = 0; c0 < nchunk; c0 += 32) {
@@ -1757,7 +1795,6 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
     }
   }
   if (lane != 0) return;
-  tickets[k] = 0;  // ready for the next M-step
   const float pkf = (float)(nk / (double)N_total);       // nem_mod.c:455-459
   P.pk[k] = pkf;
   const double lp = ((double)pkf > kEps) ? log((double)pkf) : -INFINITY;  // nem_alg.c:2350-2356
@@ -2410,6 +2447,7 @@ struct BatchInst {
   int* const* sig_ptrs; const int* sig; int* peer_err; int* bcast_ticket;
   PeerStats ps;                // the ranks' statistic blocks (ps.n == 1 without sharding)
   PeerOut push;                // the ranks' log-density buffers
+  PeerParams pp;               // the ranks' parameter blocks (column-sliced finalize)
   double* logf_loc;            // = logf + row_off * K
   int D, Ws, Dpad, K, free_disp;
   const int* rowptr; const int* col; const float* w;
@@ -2526,7 +2564,34 @@ __global__ void __launch_bounds__(256) k_b_fuzzy_mma(const BatchInst* __restrict
 __global__ void __launch_bounds__(256) k_b_finalize(const BatchInst* __restrict__ B) {
   const BatchInst& I = B[blockIdx.z];
   if (!b_active(I) || blockIdx.y >= (unsigned)I.K) return;
-  mstep_finalize_body(I.P, I.ps, I.N, I.fin_partial, I.fin_tickets);
+  mstep_finalize_body(I.P, I.ps, I.N, I.fin_partial, I.fin_tickets, I.world > 1 ? &I.pp : nullptr);
+}
+
+// row-sharded runs: "my column chunks of iteration s are written everywhere", wait for every rank's (phase 3), ...
+__global__ void __launch_bounds__(32) k_b_fin_barrier(const BatchInst* __restrict__ B, int s) {
+  const BatchInst& I = B[blockIdx.z];
+  if (I.world <= 1 || !b_active(I)) return;
+  const int epoch = I.epoch0 + s;
+  if (threadIdx.x < I.world) {
+    __threadfence_system();
+    volatile int* dst = I.sig_ptrs[threadIdx.x] + 3 * kMaxPeers + I.rank;
+    *dst = epoch;
+    __threadfence_system();
+  }
+  peer_wait_lane(I.sig, I.world, 3, epoch, I.peer_err);
+}
+// ... then the class scalars from the partial sums of all chunks (identical on every rank: same values, same order)
+__global__ void __launch_bounds__(32) k_b_finalize_scalars(const BatchInst* __restrict__ B, int nchunk) {
+  const BatchInst& I = B[blockIdx.z];
+  const int k = blockIdx.y;
+  if (I.world <= 1 || !b_active(I) || k >= I.K) return;
+  const size_t KD = (size_t)I.K * I.Dpad;
+  long long nk_i = 0;
+  double nk_f = 0.0;
+  for (int q = 0; q < I.ps.n; q++) { nk_i += I.ps.iblock[q][KD + k]; nk_f += I.ps.dblock[q][KD + k]; }
+  const double nk = (double)nk_i + nk_f;
+  if (!(nk > kEps)) return;                                  // empty class: status was set, parameters kept
+  finalize_class_scalars(I.P, k, nk, nchunk, I.fin_partial, I.N, threadIdx.x & 31);
 }
 
 template <int KB, int KX, int RB>

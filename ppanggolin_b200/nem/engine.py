@@ -25,6 +25,7 @@ FULL_RECOUNT = 4
 PEER_EXCHANGE = 8
 MAX_K = 32
 MAX_PEERS = 8          # kMaxPeers of the peer-memory exchange (one NVSwitch box)
+PEER_OFFSETS = 16      # NEMB200_PEER_OFFSETS
 
 STS_OK, STS_EMPTYCLASS, STS_INFINITE = 0, 1, 2
 
@@ -447,13 +448,13 @@ class Plan:
     def peer_export(self):
         """(64-byte CUDA IPC handle of the plan's block, 4 offsets) to be all-gathered by the driver."""
         h = (ctypes.c_ubyte * 64)()
-        offs = (ctypes.c_int64 * 4)()
+        offs = (ctypes.c_int64 * PEER_OFFSETS)()
         _check(lib().nemb200_peer_export(self._h, ctypes.cast(h, _vp), ctypes.cast(offs, _vp)), "peer_export")
         return bytes(h), list(offs)
 
     def peer_attach(self, world: int, rank: int, handles, offsets):
         hb = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
-        ob = (ctypes.c_int64 * (4 * world))(*[v for o in offsets for v in o])
+        ob = (ctypes.c_int64 * (PEER_OFFSETS * world))(*[v for o in offsets for v in o])
         _check(lib().nemb200_peer_attach(self._h, world, rank, ctypes.cast(hb, _vp), ctypes.cast(ob, _vp)), "peer_attach")
 
     def peer_logf(self):
