@@ -889,7 +889,9 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
     __syncthreads();
   }
   bool spec = false;
-  if (COOP && a.level_ptr != nullptr && a.chg != nullptr && a.n_levels > 3)
+  // speculation pays where the level-scheduled sweep is latency (few passes of the grid per level); a batch whose instances
+  // each own a small share of the SMs is throughput-bound, and the repair rounds' scans of all rows would only add to it
+  if (COOP && a.level_ptr != nullptr && a.chg != nullptr && a.n_levels > 3 && a.N <= 8 * nwarps * RPW)
     spec = __ldcg(a.spec_words + 3 + (a.spec_parity ^ 1)) <= a.spec_limit;     // the previous sweep changed few rows (grid-uniform)
   if (spec) {
     sweep_spec<GS>(a, bar, wmax, n_changed);
