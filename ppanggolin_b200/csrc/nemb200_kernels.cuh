@@ -1011,45 +1011,45 @@ classify_body(const float* __restrict__ T, long long N, int K, int* __restrict__
   for (int t = threadIdx.x; t < 2 * KB + 1; t += blockDim.x) s_hist[t] = 0;
   for (int t = threadIdx.x; t < KB; t += blockDim.x) { s_fz[t] = 0.0; s_nk[t] = 0; }
   __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  float t[KB];
+  // one row per thread and pass; a grid smaller than the rows takes several passes (the tail of the sweep kernel)
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < N; base += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + threadIdx.x;
+    bool fuzzy = false;
+    if (i < N) {
+      int ones = 0, zeros = 0, arg = 0;
 #pragma unroll
-  for (int k = 0; k < KB; k++) t[k] = 0.0f;
-  bool fuzzy = false;
-  if (i < N) {
-    int ones = 0, zeros = 0, arg = 0;
-#pragma unroll
-    for (int k = 0; k < KB; k++) {
-      if (k < K) {
-        t[k] = T[(size_t)i * K + k];
-        if (t[k] == 1.0f) { ones++; arg = k; }
-        else if (t[k] == 0.0f) zeros++;
+      for (int k = 0; k < KB; k++) {
+        if (k < K) {
+          const float t = T[(size_t)i * K + k];
+          if (t == 1.0f) { ones++; arg = k; }
+          else if (t == 0.0f) zeros++;
+        }
       }
+      int key;
+      if (ones == 1 && zeros == K - 1) { key = arg; atomicAdd(&s_nk[key], 1); }
+      else { key = K; fuzzy = true; }
+      const int old = ignore_prev ? kNone : prev[i];
+      int e0 = -1, e1 = -1;
+      if (key == K) e1 = 2 * K;                   // fuzzy: always recomputed
+      if (old != key) {
+        if (old >= 0 && old < K) e0 = K + old;    // leaves class `old`
+        if (key < K) e1 = key;                     // enters class `key`
+        if (!ignore_prev) prev[i] = key;
+      }
+      ent[i] = make_int2(e0, e1);
+      if (e0 >= 0) atomicAdd(&s_hist[e0], 1);
+      if (e1 >= 0) atomicAdd(&s_hist[e1], 1);
     }
-    int key;
-    if (ones == 1 && zeros == K - 1) { key = arg; atomicAdd(&s_nk[key], 1); }
-    else { key = K; fuzzy = true; }
-    const int old = ignore_prev ? kNone : prev[i];
-    int e0 = -1, e1 = -1;
-    if (key == K) e1 = 2 * K;                   // fuzzy: always recomputed
-    if (old != key) {
-      if (old >= 0 && old < K) e0 = K + old;    // leaves class `old`
-      if (key < K) e1 = key;                     // enters class `key`
-      if (!ignore_prev) prev[i] = key;
-    }
-    ent[i] = make_int2(e0, e1);
-    if (e0 >= 0) atomicAdd(&s_hist[e0], 1);
-    if (e1 >= 0) atomicAdd(&s_hist[e1], 1);
-  }
-  // class sizes of the fuzzy rows: warp reduction first (in the K sweep nearly every row is fuzzy and per-thread
-  // shared-memory fp64 atomics serialise), one shared atomic per warp and class
-  if (__any_sync(0xffffffffu, fuzzy)) {
+    // class sizes of the fuzzy rows: warp reduction first (in the K sweep nearly every row is fuzzy and per-thread
+    // shared-memory fp64 atomics serialise), one shared atomic per warp and class
+    if (__any_sync(0xffffffffu, fuzzy)) {
 #pragma unroll
-    for (int k = 0; k < KB; k++) {
-      if (k < K) {
-        double v = fuzzy ? (double)t[k] : 0.0;
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&s_fz[k], v);
+      for (int k = 0; k < KB; k++) {
+        if (k < K) {
+          double v = fuzzy ? (double)T[(size_t)i * K + k] : 0.0;
+          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+          if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&s_fz[k], v);
+        }
       }
     }
   }
@@ -1102,12 +1102,14 @@ scatter_body(const int2* __restrict__ ent, long long N, const int* __restrict__ 
   }
   __syncthreads();
   if (blockIdx.x == 0) for (int b = threadIdx.x; b <= nb; b += blockDim.x) offsets[b] = s_off[b];
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  int2 e = make_int2(-1, -1);
-  if (i < N) e = ent[i];
-  if (__any_sync(0xffffffffu, e.x >= 0)) scatter_one(e.x, i, lane, s_off, fill, perm);   // "leaves a class": rare, never on a full recount
-  if (__any_sync(0xffffffffu, e.y >= 0)) scatter_one(e.y, i, lane, s_off, fill, perm);
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < N; base += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + threadIdx.x;
+    int2 e = make_int2(-1, -1);
+    if (i < N) e = ent[i];
+    if (__any_sync(0xffffffffu, e.x >= 0)) scatter_one(e.x, i, lane, s_off, fill, perm);   // "leaves a class": rare, never on a full recount
+    if (__any_sync(0xffffffffu, e.y >= 0)) scatter_one(e.y, i, lane, s_off, fill, perm);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1329,7 +1331,7 @@ __host__ __device__ inline size_t onehot_ring_smem() {
 
 __device__ __forceinline__ void
 mstep_onehot_ring_body(const uint4* __restrict__ bits4, int W4, int tile_w /*<= kOhTpb*/, int K, const int* __restrict__ offsets,
-                       const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad) {
+                       const int* __restrict__ perm, int* __restrict__ cnt /*[K][Dpad]*/, int Dpad, int slice_rows = 256) {
   extern __shared__ uint4 smem4[];
   uint4* ring = smem4;                                            // [kOhGroups][kOhRows][kOhTpb]
   int* s_rows = reinterpret_cast<int*>(ring + kOhGroups * kOhRows * kOhTpb);
@@ -1340,7 +1342,7 @@ mstep_onehot_ring_body(const uint4* __restrict__ bits4, int W4, int tile_w /*<= 
   // few listed rows (steady state of the incremental update): fewer, fuller slices.  A CTA's counter flush (one RED per
   // non-zero column of its tile and bucket, ~53 000 of them) costs as much as streaming ~200 rows, and with 64-row slices
   // it was the whole M-step of a converging run (measured: ~70 us per iteration at 2 000 changed rows)
-  const long long S = min((long long)gridDim.y, max(1LL, ((long long)total + 255) / 256));
+  const long long S = min((long long)gridDim.y, max(1LL, ((long long)total + slice_rows - 1) / slice_rows));
   if (blockIdx.y >= S) return;
   const int lo = (int)((long long)total * blockIdx.y / S), hi = (int)((long long)total * (blockIdx.y + 1) / S);
   if (lo >= hi) return;
@@ -2616,10 +2618,10 @@ __global__ void __launch_bounds__(TPB, 1) k_b_density_ring(const BatchInst* __re
                                           I.P.has_half, I.logf_loc + k0, I.K, I.D);
 }
 
-__global__ void __launch_bounds__(kOhTpb, 1) k_b_onehot_ring(const BatchInst* __restrict__ B, int tile_w) {
+__global__ void __launch_bounds__(kOhTpb, 1) k_b_onehot_ring(const BatchInst* __restrict__ B, int tile_w, int slice_rows) {
   const BatchInst& I = B[blockIdx.z];
   if (!b_active(I)) return;
-  mstep_onehot_ring_body(reinterpret_cast<const uint4*>(I.bits), I.Ws / 4, tile_w, I.K, I.offsets, I.perm, I.cnt, I.Dpad);
+  mstep_onehot_ring_body(reinterpret_cast<const uint4*>(I.bits), I.Ws / 4, tile_w, I.K, I.offsets, I.perm, I.cnt, I.Dpad, slice_rows);
 }
 
 template <int KB>
@@ -2688,17 +2690,82 @@ __global__ void __launch_bounds__(256) k_b_push_densities(const BatchInst* __res
   }
 }
 
-// s >= 1: the sweep of EM iteration s (reads the posteriors of iteration s - 1); s == 0 / -1: the two start sweeps of
-// nem_alg.c:2043-2054 (blind beta = 0 from the zero posteriors in T[0] into T[1]; then with beta from T[1] into T[0])
-template <bool COOP, int GS>
-__global__ void __launch_bounds__(COOP ? 1024 : 256) k_b_sweep(const BatchInst* __restrict__ B, int s) {
+// nem_alg.c:1868-1892 after the sweep of iteration s, for one instance: convergence / failure / iteration cap (one thread)
+__device__ __forceinline__ int b_poll_decide(const BatchInst& I, int s, bool reset_barrier) {
+  const float maxdif = __uint_as_float(I.state[kStMaxdiff]);
+  const int status = (int)I.state[kStStatus];
+  I.state[kStIter] = (unsigned)s;
+  int still = 1;
+  if (status != 0) still = 0;                                       // empty class: the reference stops (nem_alg.c:1873-1892)
+  else {
+    const int conv = maxdif < I.cv_th;                              // nem_alg.c:2160-2173
+    I.state[kStConverged] = (unsigned)conv;
+    if (conv || s >= I.itermax) still = 0;
+  }
+  I.state[kStMaxdiff] = 0u;
+  if (reset_barrier) *I.barrier = 0u;
+  if (I.spec_words != nullptr) I.spec_words[3 + ((s + 1) & 1)] = 0;
+  if (!still) I.state[kStActive] = 0u;
+  return still;
+}
+// the last instance of a group to report publishes "instances still active" into the host's mapped word (the ticket counter
+// is the scratch word's high half)
+__device__ __forceinline__ void b_poll_publish(int still, int n, volatile int* any_active, int* group_active) {
+  __threadfence();
+  const int prevv = atomicAdd(group_active, (still ? 1 : 0) + (1 << 16));
+  if ((prevv >> 16) == n - 1) {
+    const int total = (prevv & 0xffff) + (still ? 1 : 0);
+    *group_active = 0;
+    __threadfence_system();
+    *any_active = total;
+    __threadfence_system();
+  }
+}
+
+// Tail of a cooperative sweep launch; replaces three launches of the next iteration: the statistics of the next M-step are
+// cleared, [s >= 1: the convergence decision, k_b_poll's,] and the rows of the fresh posteriors are classified and scattered
+// into the bucket lists (k_b_classify / k_b_scatter) -- separated by the instance's barrier instead of kernel boundaries.
+// Not inlined: its registers must not weigh on the sweep's loops (the kernel runs 1024 threads per CTA, 64 registers each).
+template <int GS>
+__device__ __noinline__ void b_sweep_tail(const BatchInst* __restrict__ B, int s, volatile int* any_active, int* __restrict__ group_active) {
   const BatchInst& I = B[blockIdx.z];
-  if (s >= 1 && !b_active(I)) return;
+  InstBar bar{I.barrier, gridDim.x};
+  // the M-step statistics are not read by anything between the last finalize and the next count kernels
+  {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    for (long long t = tid; t < I.zero_bytes / 4; t += nth) reinterpret_cast<int*>(I.zero_from)[t] = 0;
+    if (tid == 0) *I.P.has_half = 0;
+  }
+  bar.sync();        // every row's posterior, the sweep's max |dT| and the cleared statistics are visible
+  if (s >= 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int still = b_poll_decide(I, s, false);     // (the barrier counter is monotonic across the launches of a run)
+    b_poll_publish(still, (int)gridDim.z, any_active, group_active);
+  }
+  // classification of the fresh posteriors for the next M-step (an instance that just stopped does it for nothing);
+  // buffer read by the M-step of iteration s + 1: (c0 + s) & 1, after the start sweeps: c0
+  const int cur = s >= 1 ? ((I.c0 + s) & 1) : I.c0;
+  classify_body<GS>(I.T[cur] + I.row_off * I.K, I.N_loc, I.K, I.prev, I.ent, I.hist, I.nk_cnt, I.nk_fz, I.full_recount);
+  bar.sync();
+  scatter_body(I.ent, I.N_loc, I.hist, 2 * I.K + 1, I.offsets, I.cursor, I.perm);
+}
+
+// s >= 1: the sweep of EM iteration s (reads the posteriors of iteration s - 1); s == 0 / -1: the two start sweeps of
+// nem_alg.c:2043-2054 (blind beta = 0 from the zero posteriors in T[0] into T[1]; then with beta from T[1] into T[0]).
+template <bool COOP, int GS>
+__global__ void __launch_bounds__(COOP ? 1024 : 256) k_b_sweep(const BatchInst* __restrict__ B, int s, int tail,
+                                                                 volatile int* any_active, int* __restrict__ group_active) {
+  const BatchInst& I = B[blockIdx.z];
+  if (s >= 1 && !b_active(I)) {      // a finished instance still reports to the group's "any active" word
+    if (COOP && tail && blockIdx.x == 0 && threadIdx.x == 0) b_poll_publish(0, (int)gridDim.z, any_active, group_active);
+    return;
+  }
+  const bool skip = s == -1 && I.beta == 0.0f;   // an instance without a graph (in a group with one): no second start sweep
+  if (skip && !(COOP && tail)) return;
   int from, to;
   float beta = I.beta;
   if (s >= 1) { from = (I.c0 + s - 1) & 1; to = from ^ 1; }
   else if (s == 0) { from = 0; to = 1; beta = 0.0f; }
-  else { if (I.beta == 0.0f) return; from = 1; to = 0; }
+  else { from = 1; to = 0; }
   SweepArgs a;
   a.N = I.N; a.K = I.K; a.logf = I.logf; a.pk = I.P.pk; a.logpk64 = I.P.logpk64; a.T_old = I.T[from]; a.T_new = I.T[to];
   a.rowptr = I.rowptr; a.col = I.col; a.w = I.w; a.beta = beta; a.logspace = I.logspace; a.jacobi = I.jacobi;
@@ -2712,7 +2779,8 @@ __global__ void __launch_bounds__(COOP ? 1024 : 256) k_b_sweep(const BatchInst* 
   const bool levels = COOP && beta != 0.0f && I.rowptr != nullptr && !I.jacobi && I.n_levels > 1;
   a.level_ptr = levels ? I.level_ptr : nullptr; a.level_rows = levels ? I.level_rows : nullptr; a.n_levels = levels ? I.n_levels : 1;
   InstBar bar{I.barrier, gridDim.x};
-  sweep_body<COOP, GS>(a, bar);
+  if (!skip) sweep_body<COOP, GS>(a, bar);
+  if (COOP && tail) b_sweep_tail<GS>(B, s, any_active, group_active);
 }
 
 // nem_alg.c:1868-1892 on the device, after the sweep of iteration s: convergence / failure / iteration cap per instance,
@@ -2728,34 +2796,8 @@ __global__ void __launch_bounds__(256) k_b_poll(const BatchInst* __restrict__ B,
   }
   __syncthreads();
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  int still = 0;
-  if (was) {
-    const float maxdif = __uint_as_float(I.state[kStMaxdiff]);
-    const int status = (int)I.state[kStStatus];
-    I.state[kStIter] = (unsigned)s;
-    still = 1;
-    if (status != 0) still = 0;                                       // empty class: the reference stops (nem_alg.c:1873-1892)
-    else {
-      const int conv = maxdif < I.cv_th;                              // nem_alg.c:2160-2173
-      I.state[kStConverged] = (unsigned)conv;
-      if (conv || s >= I.itermax) still = 0;
-    }
-    I.state[kStMaxdiff] = 0u;
-    *I.barrier = 0u;
-    if (I.spec_words != nullptr) I.spec_words[3 + ((s + 1) & 1)] = 0;
-    if (!still) I.state[kStActive] = 0u;
-  }
-  // last instance to report publishes the group's flag (the ticket counter is the scratch word's high half)
-  __threadfence();
-  const int n = (int)gridDim.z;
-  const int prevv = atomicAdd(group_active, (still ? 1 : 0) + (1 << 16));
-  if ((prevv >> 16) == n - 1) {
-    const int total = (prevv & 0xffff) + (still ? 1 : 0);
-    *group_active = 0;
-    __threadfence_system();
-    *any_active = total;
-    __threadfence_system();
-  }
+  const int still = was ? b_poll_decide(I, s, true) : 0;
+  b_poll_publish(still, (int)gridDim.z, any_active, group_active);
 }
 
 // criteria of all instances of a group (nem_alg.c:1906): per-row terms, then the float32 sums in the reference's order
