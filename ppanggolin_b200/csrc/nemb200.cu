@@ -196,6 +196,7 @@ struct nemb200_plan {
   bool stepwise_used = false;     // work was enqueued through the stepwise entry points on a stream this library does not own
   bool with_run_buffers = false;
   bool batch_ell = false;         // batched runs: the schedule-ordered graph copy lives in the plan's block
+  const void* run_ell_key[4] = {nullptr, nullptr, nullptr, nullptr};   // row-sharded device loop: graph the copy in the block was built from
   void* ell_in_block = nullptr;
   int* spec_chg = nullptr;        // speculative sweep: change marks [2][rows], words [8]
   int* spec_words = nullptr;
@@ -799,6 +800,7 @@ extern "C" int nemb200_peer_wait_densities(nemb200_plan* pl, void* stream_) {
 extern "C" int nemb200_plan_graph_changed(nemb200_plan* pl) {
   if (!pl) return fail(NEMB200_ERR_ARG, "plan_graph_changed: null plan");
   pl->ell_N = 0;
+  pl->run_ell_key[0] = nullptr;
   return NEMB200_OK;
 }
 

@@ -87,6 +87,10 @@ struct PeerStats {          // where k_mstep_finalize reads: the statistic block
   const double* dblock[kMaxPeers];  // fsum[K][Dpad] followed by nk_fz[K]
   int n;
 };
+struct FinSync {            // the flag barriers of a row-sharded M-step, folded into the finalize kernel (device-resident loop)
+  int* const* sig_ptrs; const int* sig; int* err; int* ticket;
+  int world, rank, epoch;
+};
 
 // push this rank's freshly computed shard of log-densities (contiguous rows of its own buffer) into the same rows of
 // every peer's buffer: 16-byte coalesced peer stores, one peer per blockIdx.y.  With `ticket` != null the last CTA to
@@ -1665,7 +1669,7 @@ k_mstep_fuzzy_mma(const uint32_t* __restrict__ bits, int Ws, int K, int D, const
 // for "skd", the per-column dispersion and log-odds.  The last CTA of a class to finish (ticket counter) adds the chunk
 // partials in chunk order (deterministic) and derives the class scalars: proportion (nem_mod.c:455-459), the shared
 // dispersion of "sk_" (nem_mod.c:1053-1068, MISSING_IGNORE) and the E-step constants L_k, B_k.
-constexpr int kFinCols = 1024;
+constexpr int kFinCols = 256;     // one column per thread: the kernel is a chain of dependent memory round trips, many small CTAs hide them
 
 __device__ __forceinline__ void finalize_class_scalars(const Params& P, int k, double nk, int nchunk, const double* __restrict__ partial,
                                                        long long N_total, int lane);
@@ -1673,9 +1677,25 @@ __device__ __forceinline__ void finalize_class_scalars(const Params& P, int k, d
 // With `pp` (row-sharded run, device-resident loop) the column chunks are dealt out to the ranks: a rank reduces only its
 // chunks (1 / n of the peer loads) and writes their centres, planes, dispersions and partial sums into EVERY rank's
 // parameter block (peer stores); the class scalars follow in finalize_scalars_body after a flag barrier.
+// size of class k over all ranks (rank order: the same value on every rank); every peer load in flight at once
+__device__ __forceinline__ double class_size_all_ranks(const PeerStats& ps, size_t KD, int k) {
+  int ni[kMaxPeers];
+  double nf[kMaxPeers];
+#pragma unroll
+  for (int q = 0; q < kMaxPeers; q++) {
+    ni[q] = 0; nf[q] = 0.0;
+    if (q < ps.n) { ni[q] = ps.iblock[q][KD + k]; nf[q] = ps.dblock[q][KD + k]; }
+  }
+  long long nk_i = 0;
+  double nk_f = 0.0;
+#pragma unroll
+  for (int q = 0; q < kMaxPeers; q++) { nk_i += ni[q]; nk_f += nf[q]; }
+  return (double)nk_i + nk_f;
+}
+
 __device__ __forceinline__ void
 mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, double* __restrict__ partial /*[K][nchunk][2]*/,
-                    int* __restrict__ tickets /*[K]*/, const PeerParams* pp = nullptr) {
+                    int* __restrict__ tickets /*[K]*/, const PeerParams* pp = nullptr, const FinSync* fs = nullptr) {
   __shared__ double s_red[8][2];
   __shared__ int s_last;
   const int k = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
@@ -1683,34 +1703,48 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
   const int D = P.D, Dpad = P.Dpad, Ws = P.Ws;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t KD = (size_t)P.K * Dpad;
-  long long nk_i = 0;
-  double nk_f = 0.0;
-  for (int q = 0; q < ps.n; q++) { nk_i += ps.iblock[q][KD + k]; nk_f += ps.dblock[q][KD + k]; }   // rank order: same on every rank
-  const double nk = (double)nk_i + nk_f;
-  if (!(nk > kEps)) {  // empty class: nem_mod.c:1399-1403 -> STS_W_EMPTYCLASS, parameters kept
-    if (threadIdx.x == 0 && chunk == 0) atomicMax(P.status, 1);
-    return;
+  if (fs != nullptr) {
+    // the all-reduce's flag barrier (phase 0): "my statistics of this iteration are complete" -- they are, the count kernels
+    // precede this launch -- by the first CTA; every CTA waits for all ranks' before it loads their statistics
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < fs->world) {
+      __threadfence_system();
+      volatile int* dst = fs->sig_ptrs[threadIdx.x] + 0 * kMaxPeers + fs->rank;
+      *dst = fs->epoch;
+      __threadfence_system();
+    }
+    peer_wait_lane(fs->sig, fs->world, 0, fs->epoch, fs->err);
+    __syncthreads();
   }
-  if (pp != nullptr && chunk % pp->n != pp->rank) return;   // another rank's chunk
+  const double nk = class_size_all_ranks(ps, KD, k);
+  const bool empty = !(nk > kEps);   // empty class: nem_mod.c:1399-1403 -> STS_W_EMPTYCLASS, parameters kept
+  if (empty && threadIdx.x == 0 && chunk == 0) atomicMax(P.status, 1);
+  const bool mine = !empty && !(pp != nullptr && chunk % pp->n != pp->rank);   // (else: another rank's chunk)
+  if (fs == nullptr && !mine) return;
+  if (mine) {
   double iner_sum = 0.0, b_sum = 0.0;
   int any_half = 0;
+  // every statistic of the CTA's columns is requested before the first result is stored (peer loads: one round trip)
+  int ci[kFinCols / 256][kMaxPeers];
+  double cf[kFinCols / 256][kMaxPeers];
+#pragma unroll
+  for (int j = 0; j < kFinCols / 256; j++) {
+    const int d = chunk * kFinCols + j * 256 + threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; q++) {
+      ci[j][q] = 0; cf[j][q] = 0.0;
+      if (d < D && q < ps.n) { ci[j][q] = ps.iblock[q][(size_t)k * Dpad + d]; cf[j][q] = ps.dblock[q][(size_t)k * Dpad + d]; }
+    }
+  }
 #pragma unroll
   for (int j = 0; j < kFinCols / 256; j++) {
     const int d = chunk * kFinCols + j * 256 + threadIdx.x;
     float m = 0.0f;
     double iner = 0.0;
     if (d < D) {
-      int ci[kMaxPeers];
-      double cf[kMaxPeers];
-#pragma unroll
-      for (int q = 0; q < kMaxPeers; q++) {          // all peer loads in flight together, then added in rank order
-        ci[q] = 0; cf[q] = 0.0;
-        if (q < ps.n) { ci[q] = ps.iblock[q][(size_t)k * Dpad + d]; cf[q] = ps.dblock[q][(size_t)k * Dpad + d]; }
-      }
       long long c_i = 0;
       double c_f = 0.0;
 #pragma unroll
-      for (int q = 0; q < kMaxPeers; q++) { c_i += ci[q]; c_f += cf[q]; }
+      for (int q = 0; q < kMaxPeers; q++) { c_i += ci[j][q]; c_f += cf[j][q]; }   // added in rank order
       const double s1 = (double)c_i + c_f;
       const double s0 = nk - s1;
       // Weighted median of a 0/1 column (nem_mod.c:1417-1474): 0 if the weight of the zero rows exceeds half the class
@@ -1771,11 +1805,40 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
     }
   }
   __syncthreads();
-  if (pp != nullptr) { __threadfence_system(); return; }
-  if (!s_last || wid != 0) return;
-  __threadfence();
-  finalize_class_scalars(P, k, nk, nchunk, partial, N_total, lane);
-  if (lane == 0) tickets[k] = 0;  // ready for the next M-step
+  if (pp == nullptr) {
+    if (!s_last || wid != 0) return;
+    __threadfence();
+    finalize_class_scalars(P, k, nk, nchunk, partial, N_total, lane);
+    if (lane == 0) tickets[k] = 0;  // ready for the next M-step
+    return;
+  }
+  __threadfence_system();
+  }  // mine
+  if (fs == nullptr) return;
+  // Row-sharded: the last CTA of the launch to get here (every chunk of this rank is written on every rank) publishes
+  // "my chunks of this iteration are everywhere" (phase 3), waits for every rank's, and derives the class scalars from
+  // the partial sums of all chunks -- identical on every rank: same values, same order.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const int total = (int)gridDim.x * P.K;
+    s_last = (atomicAdd(fs->ticket, 1) == total - 1);
+    if (s_last) *fs->ticket = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if ((int)threadIdx.x < fs->world) {
+    __threadfence_system();
+    volatile int* dst = fs->sig_ptrs[threadIdx.x] + 3 * kMaxPeers + fs->rank;
+    *dst = fs->epoch;
+    __threadfence_system();
+  }
+  peer_wait_lane(fs->sig, fs->world, 3, fs->epoch, fs->err);
+  __syncthreads();
+  for (int kk = wid; kk < P.K; kk += (int)(blockDim.x >> 5)) {
+    const double nkk = class_size_all_ranks(ps, KD, kk);
+    if (nkk > kEps) finalize_class_scalars(P, kk, nkk, nchunk, partial, N_total, lane);
+  }
 }
 
 // class scalars from the chunk partials (added in chunk order: deterministic): proportion (nem_mod.c:455-459), the shared
@@ -2565,37 +2628,18 @@ __global__ void __launch_bounds__(256) k_b_fuzzy_mma(const BatchInst* __restrict
   mstep_fuzzy_mma_body<KT>(I.bits, I.Ws, I.K, I.D, I.offsets, I.perm, I.T[(I.c0 + s - 1) & 1] + I.row_off * I.K, I.fsum, I.Dpad);
 }
 
-__global__ void __launch_bounds__(256) k_b_finalize(const BatchInst* __restrict__ B) {
+// row-sharded runs (world > 1): the two flag barriers of the M-step and the class scalars are part of this launch (FinSync)
+__global__ void __launch_bounds__(256) k_b_finalize(const BatchInst* __restrict__ B, int s) {
   const BatchInst& I = B[blockIdx.z];
   if (!b_active(I) || blockIdx.y >= (unsigned)I.K) return;
-  mstep_finalize_body(I.P, I.ps, I.N, I.fin_partial, I.fin_tickets, I.world > 1 ? &I.pp : nullptr);
-}
-
-// row-sharded runs: "my column chunks of iteration s are written everywhere", wait for every rank's (phase 3), ...
-__global__ void __launch_bounds__(32) k_b_fin_barrier(const BatchInst* __restrict__ B, int s) {
-  const BatchInst& I = B[blockIdx.z];
-  if (I.world <= 1 || !b_active(I)) return;
-  const int epoch = I.epoch0 + s;
-  if (threadIdx.x < I.world) {
-    __threadfence_system();
-    volatile int* dst = I.sig_ptrs[threadIdx.x] + 3 * kMaxPeers + I.rank;
-    *dst = epoch;
-    __threadfence_system();
+  if (I.world > 1) {
+    FinSync fs;
+    fs.sig_ptrs = I.sig_ptrs; fs.sig = I.sig; fs.err = I.peer_err; fs.ticket = I.fin_tickets;   // (the per-class tickets are unused here)
+    fs.world = I.world; fs.rank = I.rank; fs.epoch = I.epoch0 + s;
+    mstep_finalize_body(I.P, I.ps, I.N, I.fin_partial, I.fin_tickets, &I.pp, &fs);
+  } else {
+    mstep_finalize_body(I.P, I.ps, I.N, I.fin_partial, I.fin_tickets);
   }
-  peer_wait_lane(I.sig, I.world, 3, epoch, I.peer_err);
-}
-// ... then the class scalars from the partial sums of all chunks (identical on every rank: same values, same order)
-__global__ void __launch_bounds__(32) k_b_finalize_scalars(const BatchInst* __restrict__ B, int nchunk) {
-  const BatchInst& I = B[blockIdx.z];
-  const int k = blockIdx.y;
-  if (I.world <= 1 || !b_active(I) || k >= I.K) return;
-  const size_t KD = (size_t)I.K * I.Dpad;
-  long long nk_i = 0;
-  double nk_f = 0.0;
-  for (int q = 0; q < I.ps.n; q++) { nk_i += I.ps.iblock[q][KD + k]; nk_f += I.ps.dblock[q][KD + k]; }
-  const double nk = (double)nk_i + nk_f;
-  if (!(nk > kEps)) return;                                  // empty class: status was set, parameters kept
-  finalize_class_scalars(I.P, k, nk, nchunk, I.fin_partial, I.N, threadIdx.x & 31);
 }
 
 template <int KB, int KX, int RB>
@@ -2606,9 +2650,12 @@ __global__ void __launch_bounds__(kDensTpb) k_b_density_sk(const BatchInst* __re
                              reinterpret_cast<const uint4*>(I.P.valid), I.P.L, I.P.B, I.P.has_half, I.logf_loc, planes_in_smem);
 }
 
-// large matrices: the streaming (shared-memory ring) kernels, classes [k0, k0 + kc) per launch
+// large matrices: the streaming (shared-memory ring) kernels, classes [k0, k0 + kc) per launch.  Row-sharded runs
+// (push_s >= 0, the launch of the last class chunk): the all-gather of the log-densities is the kernel's epilogue -- a CTA
+// stores the rows it computed into every peer's buffer (they are still in L2), and the last CTA of the launch to finish
+// publishes the epoch of iteration push_s (phase 1) that the sweep kernels of all ranks wait for.
 template <int KB, int KX, int RB, int P, int TPB>
-__global__ void __launch_bounds__(TPB, 1) k_b_density_ring(const BatchInst* __restrict__ B, int G, int gate, int k0, int kc) {
+__global__ void __launch_bounds__(TPB, 1) k_b_density_ring(const BatchInst* __restrict__ B, int G, int gate, int k0, int kc, int push_s) {
   const BatchInst& I = B[blockIdx.z];
   if (gate && !b_active(I)) return;
   const int W4 = I.Ws / 4;
@@ -2616,6 +2663,34 @@ __global__ void __launch_bounds__(TPB, 1) k_b_density_ring(const BatchInst* __re
                                           reinterpret_cast<const uint4*>(I.P.m1) + (size_t)k0 * W4,
                                           reinterpret_cast<const uint4*>(I.P.valid) + (size_t)k0 * W4, I.P.L + k0, I.P.B + k0,
                                           I.P.has_half, I.logf_loc + k0, I.K, I.D);
+  if (push_s < 0 || I.world <= 1) return;
+  __syncthreads();
+  {
+    const long long rows_cta = (long long)(TPB / 32) * (32 / G) * RB;     // the contiguous row block of one pass of this CTA
+    const long long stride = rows_cta * gridDim.x;
+    for (long long base = (long long)blockIdx.x * rows_cta; base < I.N_loc; base += stride) {
+      const long long first = (I.row_off + base) * I.K;
+      const int cnt = (int)(min(rows_cta, I.N_loc - base) * I.K);
+      const double* src = I.logf + first;
+      for (int q = 1; q < I.push.n; q++) {
+        double* dst = I.push.ptr[q] + first;
+        for (int t = threadIdx.x; t < cnt; t += TPB) dst[t] = src[t];
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(I.bcast_ticket, 1) == (int)gridDim.x - 1) {
+      *I.bcast_ticket = 0;
+      __threadfence_system();
+      for (int r = 0; r < I.world; r++) {
+        volatile int* dst = I.sig_ptrs[r] + 1 * kMaxPeers + I.rank;
+        *dst = I.epoch0 + push_s;
+      }
+      __threadfence_system();
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kOhTpb, 1) k_b_onehot_ring(const BatchInst* __restrict__ B, int tile_w, int slice_rows) {
@@ -2631,19 +2706,6 @@ __global__ void __launch_bounds__(256) k_b_density_skd(const BatchInst* __restri
   density_skd_body<KB>(I.bits, I.N_loc, I.Ws, I.K, G, I.P.m1, I.P.valid, I.Ltab, I.Lword, I.P.B, I.logf_loc);
 }
 
-// row-sharded runs, M-step: "my statistics of iteration s are complete", then wait for every rank's (one block per instance)
-__global__ void __launch_bounds__(32) k_b_stats_barrier(const BatchInst* __restrict__ B, int s) {
-  const BatchInst& I = B[blockIdx.z];
-  if (I.world <= 1 || !b_active(I)) return;
-  const int epoch = I.epoch0 + s;
-  if (threadIdx.x < I.world) {
-    __threadfence_system();
-    volatile int* dst = I.sig_ptrs[threadIdx.x] + 0 * kMaxPeers + I.rank;
-    *dst = epoch;
-    __threadfence_system();
-  }
-  peer_wait_lane(I.sig, I.world, 0, epoch, I.peer_err);
-}
 // row-sharded runs, start of a run: no rank may overwrite the others' log-densities (push) while they still read them for
 // the criteria of the previous run -- every rank reports "my previous run is complete" and waits for all (phase 2)
 __global__ void __launch_bounds__(32) k_b_run_barrier(const BatchInst* __restrict__ B) {
