@@ -198,6 +198,9 @@ struct nemb200_plan {
   bool batch_ell = false;         // batched runs: the schedule-ordered graph copy lives in the plan's block
   const void* run_ell_key[4] = {nullptr, nullptr, nullptr, nullptr};   // row-sharded device loop: graph the copy in the block was built from
   void* ell_in_block = nullptr;
+  char* ll_base = nullptr;        // PEER_EXCHANGE: this rank's LL region (see LLayout); peer_ll[r] = rank r's
+  char* peer_ll[kMaxPeers] = {nullptr};
+  LLayout ll_lay{};
   int* spec_chg = nullptr;        // speculative sweep: change marks [2][rows], words [8]
   int* spec_words = nullptr;
   double* run_logf = nullptr;
@@ -236,6 +239,8 @@ static void plan_layout(nemb200_plan* pl, Arena& ar) {
     pl->run_Ta = ar.take<float>((size_t)pl->N_total * K); pl->run_Tb = ar.take<float>((size_t)pl->N_total * K);
     pl->ell_in_block = ar.take<char>((size_t)pl->N_total * (sizeof(int4) + kEllW * sizeof(int2)));
     pl->spec_chg = ar.take<int>(2 * (size_t)pl->N_total); pl->spec_words = ar.take<int>(8);
+    pl->ll_lay = ll_layout(K, pl->D, pl->Dpad, pl->Ws, pl->fin_chunks, pl->free_disp);
+    pl->ll_base = (char*)ar.take<uint4>((size_t)(pl->ll_lay.bytes / 16 + 1));
   }
   // the sweep and the criteria run over all rows, also on a shard's plan; one region of ceil(N/warps) rows per warp
   pl->crit_terms = ar.take<float>(((size_t)pl->N_total + (size_t)pl->crit_blocks * 8) * K * 2);
@@ -312,6 +317,10 @@ static int plan_build(nemb200_plan** out, int64_t N_local, int64_t N_total, int6
       nemb200_plan_destroy(pl);
       return fail(NEMB200_ERR_CUDA, "plan_create: memset");
     }
+  }
+  if (pl->ll_base != nullptr && cudaMemset(pl->ll_base, 0, pl->ll_lay.bytes) != cudaSuccess) {   // no word carries a valid epoch yet
+    nemb200_plan_destroy(pl);
+    return fail(NEMB200_ERR_CUDA, "plan_create: memset of the exchange words");
   }
   *out = pl;
   return NEMB200_OK;
@@ -710,7 +719,8 @@ extern "C" int nemb200_peer_export(nemb200_plan* pl, unsigned char handle_out[64
   offsets_out[6] = (const char*)pl->P.L - base; offsets_out[7] = (const char*)pl->P.m1 - base;
   offsets_out[8] = (const char*)pl->P.valid - base; offsets_out[9] = (const char*)pl->fin_partial - base;
   offsets_out[10] = (const char*)pl->P.has_half - base;
-  for (int q = 11; q < NEMB200_PEER_OFFSETS; q++) offsets_out[q] = 0;
+  offsets_out[11] = (const char*)pl->ll_base - base;
+  for (int q = 12; q < NEMB200_PEER_OFFSETS; q++) offsets_out[q] = 0;
   return NEMB200_OK;
 }
 
@@ -740,6 +750,7 @@ extern "C" int nemb200_peer_attach(nemb200_plan* pl, int32_t world, int32_t rank
     pl->peer_params.L[r] = (double*)(base + o[6]); pl->peer_params.m1[r] = (uint32_t*)(base + o[7]);
     pl->peer_params.valid[r] = (uint32_t*)(base + o[8]); pl->peer_params.fin_partial[r] = (double*)(base + o[9]);
     pl->peer_params.has_half[r] = (int*)(base + o[10]);
+    pl->peer_ll[r] = base + o[11];
   }
   pl->peer_params.n = world; pl->peer_params.rank = rank;
   CK(cudaMemcpy(pl->sig_ptrs, sig_host, sizeof sig_host, cudaMemcpyHostToDevice));

@@ -90,7 +90,81 @@ struct PeerStats {          // where k_mstep_finalize reads: the statistic block
 struct FinSync {            // the flag barriers of a row-sharded M-step, folded into the finalize kernel (device-resident loop)
   int* const* sig_ptrs; const int* sig; int* err; int* ticket;
   int world, rank, epoch;
+  unsigned long long* dbg;   // NEMB200_TRACE: %globaltimer stamps of the launch's phases (null otherwise)
 };
+__device__ __forceinline__ void dbg_stamp(unsigned long long* dbg, int slot) {
+  if (dbg != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[slot] = t;
+  }
+}
+
+// ---- "LL" exchange words for the row-sharded M-step ------------------------------------------------------------------
+// A flag barrier over NVLink costs a system-scope fence on the writer (measured ~12 us with stores to 7 peers in flight)
+// plus a dependent peer load round trip (~5.5 us) on the reader.  Here every value travels as an 8-byte word
+// {payload, epoch} written with one store: the receiver polls ITS OWN memory until the epoch of the current iteration
+// shows up, so there is no fence, no separate flag and no peer load -- one NVLink one-way trip per exchange step.
+// fp64 payloads travel as two such words (low half, high half).  Bit 31 of the epoch word of a count says "the fp64
+// sum of this column is zero and is not sent" (most columns once the run has few fuzzy rows).
+struct LLayout {            // byte offsets inside every rank's LL region (identical on all ranks)
+  unsigned long long in_c, in_f, nk_c, nk_f, out_m1, out_valid, out_part, out_L, out_eps, bytes;
+};
+__host__ __device__ inline LLayout ll_layout(int K, int D, int Dpad, int Ws, int fin_chunks, int free_disp) {
+  LLayout l;
+  unsigned long long o = 0;
+  auto take = [&](unsigned long long n) { const unsigned long long at = o; o += (n + 255ull) & ~255ull; return at; };
+  const unsigned long long KD = (unsigned long long)K * Dpad;
+  l.in_c = take(8ull * kMaxPeers * KD);
+  l.in_f = take(16ull * kMaxPeers * KD);
+  l.nk_c = take(8ull * kMaxPeers * 32);
+  l.nk_f = take(16ull * kMaxPeers * 32);
+  l.out_m1 = take(8ull * K * Ws);
+  l.out_valid = take(8ull * K * Ws);
+  l.out_part = take(16ull * K * fin_chunks * 2);
+  l.out_L = take(free_disp ? 16ull * KD : 0ull);
+  l.out_eps = take(free_disp ? 8ull * K * D : 0ull);
+  l.bytes = o;
+  return l;
+}
+__device__ __forceinline__ void ll_put(uint2* p, uint32_t v, uint32_t e) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(e) : "memory");
+}
+__device__ __forceinline__ void ll_put_f64(uint4* p, double v, uint32_t e) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)b), "r"(e), "r"((uint32_t)(b >> 32)), "r"(e)
+               : "memory");
+}
+__device__ __forceinline__ uint2 ll_peek(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint4 ll_peek16(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+constexpr long long kLlSpins = 1LL << 24;   // bounded: a stalled peer shows up as an error, never as a hung GPU
+// word of the current epoch (own memory); the epoch word comes back with its flag bit
+__device__ __forceinline__ uint2 ll_get(const uint2* p, uint32_t e, int* err) {
+  uint2 r = ll_peek(p);
+  long long spins = 0;
+  while ((r.y & 0x7fffffffu) != e) {
+    if (++spins > kLlSpins) { atomicExch(err, 3); break; }
+    r = ll_peek(p);
+  }
+  return r;
+}
+__device__ __forceinline__ double ll_get_f64(const uint4* p, uint32_t e, int* err) {
+  uint4 r = ll_peek16(p);
+  long long spins = 0;
+  while (r.y != e || r.w != e) {
+    if (++spins > kLlSpins) { atomicExch(err, 3); break; }
+    r = ll_peek16(p);
+  }
+  return __longlong_as_double((long long)(((unsigned long long)r.z << 32) | r.x));
+}
 
 // push this rank's freshly computed shard of log-densities (contiguous rows of its own buffer) into the same rows of
 // every peer's buffer: 16-byte coalesced peer stores, one peer per blockIdx.y.  With `ticket` != null the last CTA to
@@ -1703,6 +1777,8 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
   const int D = P.D, Dpad = P.Dpad, Ws = P.Ws;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t KD = (size_t)P.K * Dpad;
+  unsigned long long* dbg = (fs != nullptr && (int)blockIdx.x == fs->rank && blockIdx.y == 0 && threadIdx.x == 0) ? fs->dbg : nullptr;
+  dbg_stamp(dbg, 0);
   if (fs != nullptr) {
     // the all-reduce's flag barrier (phase 0): "my statistics of this iteration are complete" -- they are, the count kernels
     // precede this launch -- by the first CTA; every CTA waits for all ranks' before it loads their statistics
@@ -1715,6 +1791,7 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
     peer_wait_lane(fs->sig, fs->world, 0, fs->epoch, fs->err);
     __syncthreads();
   }
+  dbg_stamp(dbg, 1);
   const double nk = class_size_all_ranks(ps, KD, k);
   const bool empty = !(nk > kEps);   // empty class: nem_mod.c:1399-1403 -> STS_W_EMPTYCLASS, parameters kept
   if (empty && threadIdx.x == 0 && chunk == 0) atomicMax(P.status, 1);
@@ -1746,6 +1823,7 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
 #pragma unroll
       for (int q = 0; q < kMaxPeers; q++) { c_i += ci[j][q]; c_f += cf[j][q]; }   // added in rank order
       const double s1 = (double)c_i + c_f;
+      if (s1 >= 0.0) dbg_stamp(dbg, 2);
       const double s0 = nk - s1;
       // Weighted median of a 0/1 column (nem_mod.c:1417-1474): 0 if the weight of the zero rows exceeds half the class
       // size, 1 if it falls short, midway (0.5) on a tie.  The reference compares float32 sums, in which weights below
@@ -1812,7 +1890,9 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
     if (lane == 0) tickets[k] = 0;  // ready for the next M-step
     return;
   }
+  dbg_stamp(dbg, 3);
   __threadfence_system();
+  dbg_stamp(dbg, 4);
   }  // mine
   if (fs == nullptr) return;
   // Row-sharded: the last CTA of the launch to get here (every chunk of this rank is written on every rank) publishes
@@ -1827,18 +1907,25 @@ mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, dou
   }
   __syncthreads();
   if (!s_last) return;
+  unsigned long long* dbg2 = threadIdx.x == 0 ? fs->dbg : nullptr;
+  dbg_stamp(dbg2, 5);
   if ((int)threadIdx.x < fs->world) {
     __threadfence_system();
     volatile int* dst = fs->sig_ptrs[threadIdx.x] + 3 * kMaxPeers + fs->rank;
     *dst = fs->epoch;
     __threadfence_system();
   }
+  dbg_stamp(dbg2, 6);
   peer_wait_lane(fs->sig, fs->world, 3, fs->epoch, fs->err);
   __syncthreads();
+  dbg_stamp(dbg2, 7);
   for (int kk = wid; kk < P.K; kk += (int)(blockDim.x >> 5)) {
     const double nkk = class_size_all_ranks(ps, KD, kk);
+    if (kk == 0 && nkk >= 0.0 && lane == 0) dbg_stamp(fs->dbg, 8);
     if (nkk > kEps) finalize_class_scalars(P, kk, nkk, nchunk, partial, N_total, lane);
   }
+  __syncthreads();
+  dbg_stamp(dbg2, 9);
 }
 
 // class scalars from the chunk partials (added in chunk order: deterministic): proportion (nem_mod.c:455-459), the shared
@@ -2540,6 +2627,9 @@ struct BatchInst {
   int* crit_nrows; double* crit4;
   // outputs of the run (device pointers of the caller, may be null)
   float* T_out; float* mu_out; float* eps_out; float* pk_out;
+  unsigned long long* dbg;     // NEMB200_TRACE: in-kernel phase stamps (null otherwise)
+  char* ll[kMaxPeers];         // row-sharded: every rank's LL region (ll[rank] = this rank's own), laid out by `lay`
+  LLayout lay;
 };
 
 __device__ __forceinline__ int b_final_buffer(const BatchInst& I) {
@@ -2635,11 +2725,197 @@ __global__ void __launch_bounds__(256) k_b_finalize(const BatchInst* __restrict_
   if (I.world > 1) {
     FinSync fs;
     fs.sig_ptrs = I.sig_ptrs; fs.sig = I.sig; fs.err = I.peer_err; fs.ticket = I.fin_tickets;   // (the per-class tickets are unused here)
-    fs.world = I.world; fs.rank = I.rank; fs.epoch = I.epoch0 + s;
+    fs.world = I.world; fs.rank = I.rank; fs.epoch = I.epoch0 + s; fs.dbg = I.dbg;
     mstep_finalize_body(I.P, I.ps, I.N, I.fin_partial, I.fin_tickets, &I.pp, &fs);
   } else {
     mstep_finalize_body(I.P, I.ps, I.N, I.fin_partial, I.fin_tickets);
   }
+}
+
+// Row-sharded M-step in ONE launch without fences: the column-sliced all-reduce of the statistics and the all-gather of
+// the parameters both travel as LL words (see LLayout).  grid.x <= the number of co-resident CTAs (every CTA's sends of
+// phase 1 are issued before anything waits); work items = (class, chunk of kFinCols columns), chunk c is reduced by rank
+// c % world.
+//   phase 1  every rank sends its counts / fuzzy sums of every item to the item's owner, and its class sizes to everyone
+//   phase 2  the owner adds the ranks' statistics in rank order (same arithmetic as mstep_finalize_body), sends the
+//            centre plane words, [skd: dispersions and log-odds] and the chunk's partial sums to every rank
+//   phase 3  every rank takes the words of every item into its plain parameter arrays; the last CTA derives the class
+//            scalars from the chunk partials (identical on every rank: same values, same order)
+__global__ void __launch_bounds__(256, 4) k_b_finalize_ll(const BatchInst* __restrict__ B, int s) {
+  const BatchInst& I = B[blockIdx.z];
+  if (!b_active(I)) return;
+  __shared__ int s_nki[kMaxPeers][NEMB200_MAX_K];
+  __shared__ double s_nkf[kMaxPeers][NEMB200_MAX_K];
+  __shared__ double s_nk[NEMB200_MAX_K];
+  __shared__ double s_red[8][2];
+  __shared__ int s_last;
+  const Params& P = I.P;
+  const int K = I.K, D = I.D, Dpad = I.Dpad, Ws = I.Ws, W = I.world, me = I.rank;
+  const int nchunk = (Dpad + kFinCols - 1) / kFinCols;
+  const int items = K * nchunk;
+  const uint32_t ep = (uint32_t)(I.epoch0 + s);
+  const size_t KD = (size_t)K * Dpad;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const LLayout& L = I.lay;
+  unsigned long long* dbg = (blockIdx.x == 0 && threadIdx.x == 0) ? I.dbg : nullptr;
+  dbg_stamp(dbg, 0);
+  // ---- phase 1
+  if (blockIdx.x == 0 && (int)threadIdx.x < K) {
+    const int k = threadIdx.x;
+    const int ni = I.nk_cnt[k];
+    const double nf = I.nk_fz[k];
+    for (int q = 0; q < W; q++) {
+      ll_put(reinterpret_cast<uint2*>(I.ll[q] + L.nk_c) + me * 32 + k, (uint32_t)ni, ep);
+      ll_put_f64(reinterpret_cast<uint4*>(I.ll[q] + L.nk_f) + me * 32 + k, nf, ep);
+    }
+  }
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int k = it / nchunk, c = it - k * nchunk;
+    const int d = c * kFinCols + threadIdx.x;
+    if (d < D) {
+      char* dst = I.ll[c % W];
+      const size_t at = (size_t)me * KD + (size_t)k * Dpad + d;
+      const int ci = __ldcg(I.cnt + (size_t)k * Dpad + d);
+      const double cf = __ldcg(I.fsum + (size_t)k * Dpad + d);
+      if (cf != 0.0) ll_put_f64(reinterpret_cast<uint4*>(dst + L.in_f) + at, cf, ep);
+      ll_put(reinterpret_cast<uint2*>(dst + L.in_c) + at, (uint32_t)ci, cf != 0.0 ? ep : (ep | 0x80000000u));
+    }
+  }
+  dbg_stamp(dbg, 1);
+  // class sizes over all ranks (rank order: the same value on every rank)
+  if ((int)threadIdx.x < W * K) {
+    const int r = threadIdx.x / K, k = threadIdx.x - r * K;
+    s_nki[r][k] = (int)ll_get(reinterpret_cast<const uint2*>(I.ll[me] + L.nk_c) + r * 32 + k, ep, I.peer_err).x;
+    s_nkf[r][k] = ll_get_f64(reinterpret_cast<const uint4*>(I.ll[me] + L.nk_f) + r * 32 + k, ep, I.peer_err);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < K) {
+    long long ni = 0;
+    double nf = 0.0;
+    for (int r = 0; r < W; r++) { ni += s_nki[r][threadIdx.x]; nf += s_nkf[r][threadIdx.x]; }
+    const double nk = (double)ni + nf;
+    s_nk[threadIdx.x] = nk;
+    if (!(nk > kEps) && blockIdx.x == 0) atomicMax(P.status, 1);   // empty class: nem_mod.c:1399-1403, parameters kept
+  }
+  __syncthreads();
+  dbg_stamp(dbg, 2);
+  // ---- phase 2: the chunks this rank reduces
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int k = it / nchunk, c = it - k * nchunk;
+    if (c % W != me) continue;
+    const double nk = s_nk[k];
+    if (!(nk > kEps)) continue;
+    const int d = c * kFinCols + threadIdx.x;
+    float m = 0.0f;
+    double iner = 0.0, b_add = 0.0;
+    if (d < D) {
+      const uint2* inc = reinterpret_cast<const uint2*>(I.ll[me] + L.in_c) + (size_t)k * Dpad + d;
+      const uint4* inf = reinterpret_cast<const uint4*>(I.ll[me] + L.in_f) + (size_t)k * Dpad + d;
+      uint2 cw[kMaxPeers];
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; r++) cw[r] = r < W ? ll_peek(inc + (size_t)r * KD) : make_uint2(0u, ep | 0x80000000u);
+      long long c_i = 0;
+      double c_f = 0.0;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; r++) {           // added in rank order
+        if (r < W) {
+          if ((cw[r].y & 0x7fffffffu) != ep) cw[r] = ll_get(inc + (size_t)r * KD, ep, I.peer_err);
+          c_i += (int)cw[r].x;
+          if (!(cw[r].y & 0x80000000u)) c_f += ll_get_f64(inf + (size_t)r * KD, ep, I.peer_err);
+        }
+      }
+      const double s1 = (double)c_i + c_f;
+      const double s0 = nk - s1;
+      const float w0 = (float)s0, half = (float)nk * 0.5f;   // see mstep_finalize_body
+      if (w0 > half) { m = 0.0f; iner = s1; }
+      else if (w0 < half) { m = 1.0f; iner = s0; }
+      else { m = 0.5f; iner = 0.5 * nk; }
+      if (P.free_disp) {
+        const float e = (float)(iner / nk);
+        double Lv;
+        if (e > kEps) { Lv = log((double)((1.0f - e) / e)); b_add = log((double)(1.0f - e)); }
+        else Lv = INFINITY;
+        for (int q = 0; q < W; q++) {
+          ll_put(reinterpret_cast<uint2*>(I.ll[q] + L.out_eps) + (size_t)k * D + d, __float_as_uint(e), ep);
+          ll_put_f64(reinterpret_cast<uint4*>(I.ll[q] + L.out_L) + (size_t)k * Dpad + d, Lv, ep);
+        }
+      }
+    }
+    const unsigned b1 = __ballot_sync(0xffffffffu, m == 1.0f);
+    const unsigned bv = __ballot_sync(0xffffffffu, m != 0.5f);
+    if (lane == 0 && (d >> 5) < Ws) {
+      for (int q = 0; q < W; q++) {
+        ll_put(reinterpret_cast<uint2*>(I.ll[q] + L.out_m1) + (size_t)k * Ws + (d >> 5), b1, ep);
+        ll_put(reinterpret_cast<uint2*>(I.ll[q] + L.out_valid) + (size_t)k * Ws + (d >> 5), bv, ep);
+      }
+    }
+    double iner_sum = iner, b_sum = b_add;
+    for (int off = 16; off > 0; off >>= 1) {
+      iner_sum += __shfl_xor_sync(0xffffffffu, iner_sum, off);
+      b_sum += __shfl_xor_sync(0xffffffffu, b_sum, off);
+    }
+    __syncthreads();                                   // (s_red of the previous item is consumed)
+    if (lane == 0) { s_red[wid][0] = iner_sum; s_red[wid][1] = b_sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t0 = 0.0, t1 = 0.0;
+      for (int q = 0; q < 8; q++) { t0 += s_red[q][0]; t1 += s_red[q][1]; }
+      for (int q = 0; q < W; q++) {
+        uint4* o = reinterpret_cast<uint4*>(I.ll[q] + L.out_part) + ((size_t)k * nchunk + c) * 2;
+        ll_put_f64(o, t0, ep);
+        ll_put_f64(o + 1, t1, ep);
+      }
+    }
+  }
+  dbg_stamp(dbg, 3);
+  // ---- phase 3: every item's results into the plain parameter arrays of this rank
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int k = it / nchunk, c = it - k * nchunk;
+    if (!(s_nk[k] > kEps)) continue;
+    const int d = c * kFinCols + threadIdx.x;
+    const int w = d >> 5;
+    unsigned b1 = 0u, bv = 0xffffffffu;
+    if (w < Ws) {
+      if (lane == 0) {
+        b1 = ll_get(reinterpret_cast<const uint2*>(I.ll[me] + L.out_m1) + (size_t)k * Ws + w, ep, I.peer_err).x;
+        bv = ll_get(reinterpret_cast<const uint2*>(I.ll[me] + L.out_valid) + (size_t)k * Ws + w, ep, I.peer_err).x;
+        P.m1[(size_t)k * Ws + w] = b1;
+        P.valid[(size_t)k * Ws + w] = bv;
+      }
+      b1 = __shfl_sync(0xffffffffu, b1, 0);
+      bv = __shfl_sync(0xffffffffu, bv, 0);
+    }
+    if (d < D) {
+      const bool is_half = !((bv >> lane) & 1u);
+      P.mu[(size_t)k * D + d] = is_half ? 0.5f : (((b1 >> lane) & 1u) ? 1.0f : 0.0f);
+      if (is_half) atomicOr(P.has_half, 1);
+      if (P.free_disp) {
+        P.eps[(size_t)k * D + d] = __uint_as_float(ll_get(reinterpret_cast<const uint2*>(I.ll[me] + L.out_eps) + (size_t)k * D + d, ep, I.peer_err).x);
+        P.L[(size_t)k * Dpad + d] = ll_get_f64(reinterpret_cast<const uint4*>(I.ll[me] + L.out_L) + (size_t)k * Dpad + d, ep, I.peer_err);
+      }
+    } else if (P.free_disp && d < Dpad) {
+      P.L[(size_t)k * Dpad + d] = 0.0;
+    }
+    if (threadIdx.x < 2) {
+      const uint4* o = reinterpret_cast<const uint4*>(I.ll[me] + L.out_part) + ((size_t)k * nchunk + c) * 2 + threadIdx.x;
+      I.fin_partial[((size_t)k * nchunk + c) * 2 + threadIdx.x] = ll_get_f64(o, ep, I.peer_err);
+    }
+  }
+  dbg_stamp(dbg, 4);
+  // ---- class scalars by the last CTA to finish
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_last = (atomicAdd(I.fin_tickets, 1) == (int)gridDim.x - 1);
+    if (s_last) *I.fin_tickets = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int kk = wid; kk < K; kk += (int)(blockDim.x >> 5))
+    if (s_nk[kk] > kEps) finalize_class_scalars(P, kk, s_nk[kk], nchunk, I.fin_partial, I.N, lane);
+  __syncthreads();
+  dbg_stamp(threadIdx.x == 0 ? I.dbg : nullptr, 5);
 }
 
 template <int KB, int KX, int RB>
