@@ -2097,17 +2097,31 @@ __device__ __forceinline__ void criteria_body(const CritArgs& a) {
   float2* region = a.terms ? a.terms + (size_t)row_lo * K : nullptr;
   int cnt = 0;
   double accD = 0, accG = 0, accL = 0, accZ = 0;
+  // the neighbour lists are read eight entries at a time (all column / weight loads in flight, then all posterior
+  // gathers, then the adds in list order), and the list bounds of the group's next row are requested a row ahead
+  int nx0 = 0, nx1 = 0;
+  if (a.rowptr != nullptr && row_lo + grp < row_hi) { nx0 = a.rowptr[row_lo + grp]; nx1 = a.rowptr[row_lo + grp + 1]; }
   for (long long i0 = row_lo; i0 < row_hi; i0 += RPW) {
     const long long i = i0 + grp;
     const bool valid = i < row_hi;
     const long long ii = valid ? i : row_lo;
     const float cik = a.T[(size_t)ii * K + k];
-    float pik = 0.0f;
-    if (valid && a.rowptr != nullptr) {
-      const int n0 = a.rowptr[ii], n1 = a.rowptr[ii + 1];
-      for (int n = n0; n < n1; n++) pik = __fadd_rn(pik, __fmul_rn(a.w[n], a.T[(size_t)a.col[n] * K + k]));
-    }
     const double lf = a.logf[(size_t)ii * K + k];
+    float pik = 0.0f;
+    if (a.rowptr != nullptr) {
+      const int n0 = nx0, n1 = valid ? nx1 : nx0;
+      if (i + RPW < row_hi) { nx0 = a.rowptr[i + RPW]; nx1 = a.rowptr[i + RPW + 1]; }
+      for (int nb = n0; nb < n1; nb += 8) {
+        int cc[8];
+        float ww[8], tv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { cc[u] = 0; ww[u] = 0.0f; if (nb + u < n1) { cc[u] = a.col[nb + u]; ww[u] = a.w[nb + u]; } }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { tv[u] = 0.0f; if (nb + u < n1) tv[u] = a.T[(size_t)cc[u] * K + k]; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (nb + u < n1) pik = __fadd_rn(pik, __fmul_rn(ww[u], tv[u]));
+      }
+    }
     double dik = 0.0, gik = 0.0, term_l, zterm;
     if (!a.logspace) {
       const float lf32 = (lf == -INFINITY) ? -FLT_MAX : (float)lf;
@@ -2193,18 +2207,22 @@ __device__ __forceinline__ void crit_offsets_body(const int* __restrict__ counts
                                                   int* __restrict__ n_rows_out, int n_rows) {
   const int lane = threadIdx.x;
   if (lane == 0) *n_rows_out = n_rows;
-  int carry = 0;
-  for (int base = 0; base < n; base += 32) {
-    const int v = base + lane < n ? counts[base + lane] : 0;
-    int incl = v;
-    for (int off = 1; off < 32; off <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += t;
-    }
-    if (base + lane < n) offsets[base + lane] = carry + incl - v;
-    carry += __shfl_sync(0xffffffffu, incl, 31);
+  // lane l owns the contiguous regions [l seg, (l + 1) seg): its total (independent loads), a scan over the 32 totals,
+  // then the lane's own running sums -- two passes over the counts instead of a chain of n / 32 dependent steps
+  const int seg = (n + 31) / 32;
+  const int b = min(n, lane * seg), e = min(n, b + seg);
+  int tot = 0;
+#pragma unroll 8
+  for (int r = b; r < e; r++) tot += counts[r];
+  int incl = tot;
+  for (int off = 1; off < 32; off <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
   }
-  if (lane == 0) offsets[n] = carry;
+  int run = incl - tot;
+#pragma unroll 8
+  for (int r = b; r < e; r++) { const int v = counts[r]; offsets[r] = run; run += v; }
+  if (lane == 31) offsets[n] = incl;
 }
 
 __global__ void __launch_bounds__(32) k_crit_offsets(const int* __restrict__ counts, int n, int* __restrict__ offsets,
@@ -2257,7 +2275,7 @@ struct TermsD2 {
   static __device__ __forceinline__ float add(float acc, double x) { return (float)__dadd_rn((double)acc, x); }
 };
 
-constexpr int kCcChunk = 512;
+constexpr int kCcChunk = 256;     // terms per chunk: a chunk that cannot be skipped (crossing, tie) is added term by term
 struct CcState { float s[2]; int cur[2]; int rounds; int seq_chunks[2]; };   // per chain (0: D, 1: G): exact running sum, next chunk
 
 __device__ __forceinline__ bool cc_binade(float s, int& E) {   // normal, non-zero, finite
@@ -2430,31 +2448,43 @@ __global__ void __launch_bounds__(256) k_cc_records(const CcJob* __restrict__ jo
 
 template <class Terms>
 __device__ __forceinline__ void cc_walk_body(const CcJob& job) {
+  __shared__ double s_x[2][kCcChunk];
   Terms dense{reinterpret_cast<decltype(Terms::p)>(job.terms)};
   const int total = *job.total_ptr;
   const int nchunks = (total + kCcChunk - 1) / kCcChunk;
   const int lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
   float sacc = 0.0f;
   int cur = 0, nseq = 0;
+  // the records of the 32 chunks after the current step are requested while the current step is evaluated
+  struct Rec { long long R, mn, mx; int fl, Ep; };
+  auto load = [&](int c) {
+    Rec r{0, 0, 0, 1, INT_MIN};
+    if (c < nchunks) {
+      const size_t i = (size_t)c * 2 + ch;
+      r.R = job.recR[i]; r.mn = job.recMn[i]; r.mx = job.recMx[i]; r.fl = job.recFlag[i]; r.Ep = job.epred[i];
+    }
+    return r;
+  };
+  Rec nxt = load(lane);
+  int nxt_at = 0;
   while (cur < nchunks) {
     int Ec = 0;
     const bool have = cc_binade(sacc, Ec);
     const int c = cur + lane;
+    const Rec rec = (nxt_at == cur) ? nxt : load(c);
+    nxt = load(c + 32);
+    nxt_at = cur + 32;
     int nvalid;
     if (have) {
       const long long S0 = (long long)scalbn((double)sacc, 23 - Ec);   // exact integer, 2^23 <= |S0| < 2^24
-      long long R = 0, mnv = 0, mxv = 0;
-      int fl = 1, Ep = INT_MIN;
-      if (c < nchunks) {
-        const size_t i = (size_t)c * 2 + ch;
-        R = job.recR[i]; mnv = job.recMn[i]; mxv = job.recMx[i]; fl = job.recFlag[i]; Ep = job.epred[i];
-      }
-      if (Ep != Ec) { R = 0; fl |= 1; }                                  // records made for another u: not usable
+      long long R = rec.R;
+      int fl = rec.fl;
+      if (rec.Ep != Ec) { R = 0; fl |= 1; }                              // records made for another u: not usable
       long long incl = R;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
       const long long Sstart = S0 + incl - R;
-      const long long lo = Sstart + mnv, hi = Sstart + mxv;
+      const long long lo = Sstart + rec.mn, hi = Sstart + rec.mx;
       bool okc = !(fl & 1) && c < nchunks;
       if (fl & 2) okc = c < nchunks;                                     // an all-zero chunk leaves any state alone
       else if (S0 > 0) okc = okc && lo >= (1LL << 23) && hi <= (1LL << 24) - 1;
@@ -2466,28 +2496,37 @@ __device__ __forceinline__ void cc_walk_body(const CcJob& job) {
         sacc = (float)scalbn((double)Send, Ec - 23);                     // exact: |Send| < 2^24, same binade
       }
     } else {                                                             // zero / subnormal / non-finite state: only all-zero chunks are free
-      const bool z = c < nchunks && (job.recFlag[(size_t)c * 2 + ch] & 2);
+      const bool z = c < nchunks && (rec.fl & 2);
       const unsigned m = __ballot_sync(0xffffffffu, !z);
       nvalid = m ? __ffs(m) - 1 : 32;
     }
     cur += nvalid;
     if (nvalid == 32 || cur >= nchunks) continue;
-    {   // chunk `cur` term by term
+    {   // chunk `cur` term by term: the warp stages it in shared memory, one lane runs the dependent chain of adds
       const int t_begin = cur * kCcChunk, t_end = min(total, t_begin + kCcChunk);
-      double xs[kCcChunk / 32];                                           // 16 independent loads, then the chain
+      const int count = t_end - t_begin;
 #pragma unroll
       for (int b = 0; b < kCcChunk / 32; b++) {
         const int t = t_begin + b * 32 + lane;
-        xs[b] = 0.0;
-        if (t < t_end) { double a, bb; dense.get(t, a, bb); xs[b] = ch ? bb : a; }
+        double v = 0.0;
+        if (t < t_end) { double a, bb; dense.get(t, a, bb); v = ch ? bb : a; }
+        s_x[ch][b * 32 + lane] = v;
       }
+      __syncwarp();
       float acc = sacc;
+      if (lane == 0) {
+        int q = 0;
+        for (; q + 8 <= count; q += 8) {
+          double x[8];
 #pragma unroll
-      for (int b = 0; b < kCcChunk / 32; b++) {
-        const int mcount = min(32, t_end - (t_begin + b * 32));           // warp-uniform; <= 0 past the end
-        for (int q = 0; q < mcount; q++) acc = Terms::add(acc, __shfl_sync(0xffffffffu, xs[b], q));
+          for (int u = 0; u < 8; u++) x[u] = s_x[ch][q + u];
+#pragma unroll
+          for (int u = 0; u < 8; u++) acc = Terms::add(acc, x[u]);
+        }
+        for (; q < count; q++) acc = Terms::add(acc, s_x[ch][q]);
       }
-      sacc = acc;
+      sacc = __shfl_sync(0xffffffffu, acc, 0);
+      __syncwarp();
       cur++; nseq++;
     }
   }
