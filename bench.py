@@ -315,6 +315,7 @@ def run_ours(a):
 
     pg = group if (world > 1 and not a.nccl) else None
     last = {}
+    dens = {"ms": 0.0, "n": 0}     # density launches of the timed runs: device time (library events around each launch) and count
     if world == 1:
         inp = engine.DeviceInput(sp.bits, D, graph.rowptr, graph.col, graph.w, graph.sched_ptr, graph.sched_rows, graph.n_levels)
 
@@ -322,14 +323,16 @@ def run_ours(a):
             def run_once(itermax):
                 r = engine.nem_run_device(inp, K, beta, False, itermax, 0.01, flags, want_params=False)
                 last["run"] = r
-                # kernels of one run of the device-resident loop: start (start kernel, graph copy, densities, 2 sweeps), per
-                # iteration classify / scatter / one-hot counts / fuzzy sums / finalize / densities / sweep / poll, then
-                # one gated iteration in flight when convergence is seen, collect and the criteria kernels
-                return r.n_iter, r.em_ms, r.elapsed_ms, 5 + 8 * (r.n_iter + 1) + 1 + 6
+                dens["ms"] += r.density_ms; dens["n"] += r.density_launches
+                # kernels of one run of the device-resident loop (csrc/nemb200_batch.inc): start (start kernel, graph copy,
+                # densities, 2 sweeps), per iteration one-hot counts / fuzzy sums / finalize / densities / sweep (its tail
+                # carries the convergence decision and the next classification), one gated iteration in flight when
+                # convergence is seen, then criteria, their reduction and collect
+                return r.n_iter, r.em_ms, r.elapsed_ms, 5 + 5 * (r.n_iter + 1) + 3
             return run_once
         be = None
     else:
-        be = CudaBackend(sp.bits, D, N, K, False, engine.EPI_LOGSPACE, graph, peer_group=pg, row_offset=lo)
+        be = CudaBackend(sp.bits, D, N, K, False, engine.EPI_LOGSPACE | engine.TIME_DENSITY, graph, peer_group=pg, row_offset=lo)
         be_full = CudaBackend(sp.bits, D, N, K, False, engine.EPI_LOGSPACE | engine.FULL_RECOUNT, graph, peer_group=pg, row_offset=lo)
 
         def make_run(flags):
@@ -337,12 +340,14 @@ def run_ours(a):
 
             def run_once(itermax):
                 b.launches = 0
+                b.density_ms, b.density_launches = 0.0, 0
                 out = ShardedEM(b, N, K, rank, world, group).run(beta, itermax, 0.01)
                 last["out"] = out
+                dens["ms"] += b.density_ms; dens["n"] += b.density_launches
                 return out.n_iter, 0.0, 0.0, b.launches
             return run_once
 
-    run_default = make_run(engine.EPI_LOGSPACE)
+    run_default = make_run(engine.EPI_LOGSPACE | engine.TIME_DENSITY)
     run_full = make_run(engine.EPI_LOGSPACE | engine.FULL_RECOUNT)
     # warm-up: whole runs until at least a.warmup iterations were executed (allocator cache, module load, clocks)
     w_done = 0
@@ -352,8 +357,10 @@ def run_ours(a):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    dens["ms"], dens["n"] = 0.0, 0
     ms_total, per_run, em_ms, run_ms, launches = timed_runs(run_default, a.steps, barrier, torch, st)
     clocks = sampler.stop() if sampler else None
+    dens_ms, dens_n = dens["ms"], dens["n"]
     ms_full, per_run_full, em_ms_full, _, _ = timed_runs(run_full, a.steps, barrier, torch, st)
     if world > 1:
         t = torch.tensor([ms_total, ms_full], dtype=torch.float64, device=dev)
@@ -407,15 +414,20 @@ def run_ours(a):
             if tp.is_file():
                 traffic = json.loads(tp.read_text()); traffic_src = f"profiles/{tname} (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch; not measured in this run)"
                 break
+        dens_bytes = x_bytes + n_loc * K * 8 + 2 * K * ((D + 7) // 8)
         kernels = {
-            "k_density_sk_ring": {"ms": float(st_mean[2]), "bytes": x_bytes + n_loc * K * 8 + 2 * K * ((D + 7) // 8),
-                                  "what": "matrix bits + log-densities out + centre planes"},
+            "k_b_density_ring": {"ms": dens_ms / max(dens_n, 1), "launches_timed": dens_n, "bytes": dens_bytes,
+                                 "what": "matrix bits + log-densities out + centre planes; mean over the density launches of the "
+                                         "timed region's EM iterations, library-side CUDA events around each launch on its stream "
+                                         "(NEMB200_TIME_DENSITY)" + ("" if world == 1 else "; includes the push of the shard to the peers (kernel epilogue)")},
+            "k_density_sk_ring (stepwise entry, same device body, timed alone after the region)": {
+                "ms": float(st_mean[2]), "bytes": dens_bytes, "what": "matrix bits + log-densities out + centre planes"},
             "k_mstep_onehot_ring": {"ms": onehot_ms / max(onehot_n, 1), "bytes": x_bytes + n_loc * 4 + K * D * 4,
                                     "what": "matrix bits + row lists + column counts out (full recount)"}}
         for kk, v in kernels.items():
             v["achieved_GBs"] = v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] > 0 else None
             v["frac"] = v["achieved_GBs"] / peak if v["ms"] > 0 else None
-        dom = "k_density_sk_ring"      # runs once in every iteration of every mode; the count kernel only streams changed rows
+        dom = "k_b_density_ring"       # runs once in every iteration of every mode; the count kernel only streams changed rows
         biter = b_iter_bytes(N, D, K, nnz)
         tr = traffic.get(dom, {}).get("dram_bytes_per_launch") if world == 1 else None
         t_iter = ms_total / a.steps / 1000.0
@@ -432,7 +444,7 @@ def run_ours(a):
                 "value_full_recount": {"value": a.steps / (ms_full / 1000.0), "unit": "EM iterations/s", "ms_per_step": ms_full / a.steps,
                                        "iterations_per_run": per_run_full,
                                        "what": "the same runs with every one-hot row recounted at every iteration"},
-                "exchange": ("none (1 GPU)" if world == 1 else ("NCCL all-reduce + all-gather" if a.nccl else "NVLink peer memory: peer loads in k_mstep_finalize, k_peer_broadcast after the density kernel")),
+                "exchange": ("none (1 GPU)" if world == 1 else ("NCCL all-reduce + all-gather" if a.nccl else "NVLink peer memory inside the kernels: statistics / parameters as {payload, epoch} words in k_b_finalize_ll (no fence, no flag), log-densities pushed by the epilogue of k_b_density_ring")),
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBs"], "peak": peak,
                              "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": tr,
                              "traffic_source": traffic_src if tr else None, "peak_source": peak_src,

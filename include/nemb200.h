@@ -50,9 +50,11 @@ enum {
                                     sweep (nem_alg.c:2459-2464); off by default                                  */
   NEMB200_PEER_EXCHANGE = 1 << 3, /* plan owns a full-length log-density buffer and signal words that other ranks of a
                                     row-sharded run map through CUDA IPC (nemb200_peer_*)                        */
-  NEMB200_FULL_RECOUNT = 1 << 2  /* M-step: recount every one-hot row at every iteration instead of updating the integer
-                                    column counts with the rows that changed class (same result bit for bit; this is
-                                    the mode the benchmark times as its headline)                                */
+  NEMB200_FULL_RECOUNT = 1 << 2, /* M-step: recount every one-hot row at every iteration instead of updating the integer
+                                    column counts with the rows that changed class (same result bit for bit)    */
+  NEMB200_TIME_DENSITY = 1 << 4  /* whole-run entries: bracket every density launch of an un-batched (large) instance
+                                    with CUDA events and report their sum in result->density_ms (the benchmark's
+                                    roofline figure of the dominant kernel, measured inside the timed runs)       */
 };
 
 typedef struct nemb200_result {
@@ -64,6 +66,8 @@ typedef struct nemb200_result {
   float   elapsed_ms; /* device time of the run (CUDA events): start phase, EM iterations and criteria, excluding copies;
                          for an instance of a batch: of its whole group */
   float   em_ms;      /* of which: from the start phase to the end of the last EM iteration (no criteria) */
+  float   density_ms; /* NEMB200_TIME_DENSITY: device time of the density launches of the run's EM iterations (CUDA */
+  int32_t density_launches; /* events around each launch, on the launching stream) and their number; else 0 */
 } nemb200_result;
 
 int         nemb200_abi_version(void);

@@ -1271,7 +1271,7 @@ struct EmRun {
     if (res) {
       for (int q = 0; q < 5; q++) res->crit[q] = crit[q];
       res->n_iter = iter; res->converged = converged; res->status = status; res->n_levels = n_levels; res->elapsed_ms = ms;
-      res->em_ms = ms;
+      res->em_ms = ms; res->density_ms = 0.0f; res->density_launches = 0;
     }
     return NEMB200_OK;
   }

@@ -952,6 +952,8 @@ struct InstBar {
   }
 };
 
+constexpr int kSpecVeryDeep = 64;
+
 template <bool COOP, int GS, class Bar>
 __device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
   const int lane = threadIdx.x & 31;
@@ -969,7 +971,9 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
   bool spec = false;
   // speculation pays where the level-scheduled sweep is latency (few passes of the grid per level); a batch whose instances
   // each own a small share of the SMs is throughput-bound, and the repair rounds' scans of all rows would only add to it
-  if (COOP && a.level_ptr != nullptr && a.chg != nullptr && a.n_levels > 3 && a.N <= 8 * nwarps * RPW)
+  // (a schedule of kSpecVeryDeep levels or more is the exception: a barrier and an underfilled pass per level cost more
+  //  than a few rounds over all rows -- a family order that follows the genomes has hundreds of thin levels)
+  if (COOP && a.level_ptr != nullptr && a.chg != nullptr && a.n_levels > 3 && (a.N <= 8 * nwarps * RPW || a.n_levels >= kSpecVeryDeep))
     spec = __ldcg(a.spec_words + 3 + (a.spec_parity ^ 1)) <= a.spec_limit;     // the previous sweep changed few rows (grid-uniform)
   if (spec) {
     sweep_spec<GS>(a, bar, wmax, n_changed);
@@ -2657,6 +2661,7 @@ struct BatchInst {
   unsigned* state;             // kSt* words; P.status aliases state + kStStatus
   unsigned* barrier;           // InstBar counter of the sweep
   int* chg; int* spec_words;   // speculative sweep: per-row change marks [2][N], bookkeeping words [8] (null: level sweeps only)
+  int spec_deep;               // schedules of at least this many levels are always swept speculatively (0: never forced)
   char* zero_from; long long zero_bytes;   // statistics cleared before every M-step
   float base_prop;
   float eps_init[NEMB200_MAX_K];
@@ -3118,6 +3123,7 @@ __device__ __noinline__ void b_sweep_tail(const BatchInst* __restrict__ B, int s
     const int still = b_poll_decide(I, s, false);     // (the barrier counter is monotonic across the launches of a run)
     b_poll_publish(still, (int)gridDim.z, any_active, group_active);
   }
+  if (s == -1 && blockIdx.x == 0 && threadIdx.x == 0 && I.spec_words != nullptr) I.spec_words[4] = 0;   // (a speculative start sweep counted there)
   // classification of the fresh posteriors for the next M-step (an instance that just stopped does it for nothing);
   // buffer read by the M-step of iteration s + 1: (c0 + s) & 1, after the start sweeps: c0
   const int cur = s >= 1 ? ((I.c0 + s) & 1) : I.c0;
@@ -3148,7 +3154,11 @@ __global__ void __launch_bounds__(COOP ? 1024 : 256) k_b_sweep(const BatchInst* 
   a.rowptr = I.rowptr; a.col = I.col; a.w = I.w; a.beta = beta; a.logspace = I.logspace; a.jacobi = I.jacobi;
   a.maxdiff_bits = I.state + (s >= 1 ? kStMaxdiff : kStWords - 1);   // the start sweeps are not convergence-tested
   a.ell_hdr = I.ell_hdr; a.ell_nb = I.ell_nb; a.stamps = nullptr;
-  a.chg = s >= 1 ? I.chg : nullptr; a.spec_words = I.spec_words; a.spec_limit = (int)(I.N / 32); a.spec_parity = s & 1;
+  // a deep schedule (a family order that follows the genomes: hundreds of thin levels, up to one row per level) is swept
+  // speculatively whatever the previous sweep changed, the second start sweep included
+  const bool deep = I.spec_deep > 0 && I.n_levels >= I.spec_deep;
+  a.chg = (s >= 1 || (deep && s == -1)) ? I.chg : nullptr; a.spec_words = I.spec_words;
+  a.spec_limit = deep ? 0x7fffffff : (int)(I.N / 32); a.spec_parity = s & 1;
   a.wait_sig = nullptr; a.wait_n = 0; a.wait_epoch = 0; a.wait_err = nullptr;
   if (I.world > 1 && s >= 0) {        // the densities of this sweep's epoch, pushed by every rank (the start sweep with beta
     a.wait_sig = I.sig; a.wait_n = I.world; a.wait_epoch = I.epoch0 + s; a.wait_err = I.peer_err;   // reuses those of s = 0)

@@ -23,6 +23,7 @@ EPI_LOGSPACE = 1
 JACOBI = 2
 FULL_RECOUNT = 4
 PEER_EXCHANGE = 8
+TIME_DENSITY = 16
 MAX_K = 32
 MAX_PEERS = 8          # kMaxPeers of the peer-memory exchange (one NVSwitch box)
 PEER_OFFSETS = 16      # NEMB200_PEER_OFFSETS
@@ -37,7 +38,7 @@ class NemB200Error(RuntimeError):
 class _Result(ctypes.Structure):
     _fields_ = [("crit", ctypes.c_double * 5), ("n_iter", ctypes.c_int32), ("converged", ctypes.c_int32),
                 ("status", ctypes.c_int32), ("n_levels", ctypes.c_int32), ("elapsed_ms", ctypes.c_float),
-                ("em_ms", ctypes.c_float)]
+                ("em_ms", ctypes.c_float), ("density_ms", ctypes.c_float), ("density_launches", ctypes.c_int32)]
 
 
 _lib = None
@@ -143,6 +144,8 @@ class NemRun:
     n_levels: int
     elapsed_ms: float
     em_ms: float = 0.0
+    density_ms: float = 0.0        # TIME_DENSITY: device time of the density launches of the EM iterations, and their number
+    density_launches: int = 0
 
     @property
     def ok(self) -> bool:
@@ -182,7 +185,7 @@ def nem_run_host(bits: np.ndarray, D: int, rowptr, col, w, K: int, beta: float, 
                                 ctypes.byref(res))
     _check(rc, "nemb200_nem_host")
     return NemRun(T, mu, eps, pk, list(res.crit), res.n_iter, bool(res.converged), res.status, res.n_levels, res.elapsed_ms,
-                  res.em_ms)
+                  res.em_ms, res.density_ms, res.density_launches)
 
 
 @dataclass
@@ -250,7 +253,8 @@ def _nem_run_device_impl(bits, rowptr, col, w, sched_ptr, sched_rows, D: int, n_
                                       _ptr(mu) if want_params else 0, _ptr(eps) if want_params else 0,
                                       _ptr(pk) if want_params else 0, ctypes.byref(res), _stream())
     _check(rc, "nemb200_nem_device")
-    stats = torch.tensor(list(res.crit) + [res.n_iter, res.converged, res.status, res.n_levels, res.elapsed_ms, res.em_ms],
+    stats = torch.tensor(list(res.crit) + [res.n_iter, res.converged, res.status, res.n_levels, res.elapsed_ms, res.em_ms,
+                                           res.density_ms, res.density_launches],
                          dtype=torch.float64)
     return T, mu, eps, pk, stats
 
@@ -300,7 +304,7 @@ def nem_run_device(inp: DeviceInput, K: int, beta: float, free_dispersion: bool 
         mu, eps, pk = mu.cpu().numpy(), eps.cpu().numpy(), pk.cpu().numpy()
     else:
         mu = eps = pk = None
-    return NemRun(T, mu, eps, pk, s[:5], int(s[5]), bool(s[6]), int(s[7]), int(s[8]), float(s[9]), float(s[10]))
+    return NemRun(T, mu, eps, pk, s[:5], int(s[5]), bool(s[6]), int(s[7]), int(s[8]), float(s[9]), float(s[10]), float(s[11]), int(s[12]))
 
 
 def nem_run_batch(instances, cv_th: float = 0.01, flags: int = EPI_REF, want_params: bool = True):

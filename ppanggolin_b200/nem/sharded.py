@@ -65,6 +65,7 @@ class CudaBackend:
             self.logf_full = torch.empty((N_total, K), dtype=torch.float64, device=dev)
         self.T = [torch.zeros((N_total, K), dtype=torch.float32, device=dev) for _ in range(2)]
         self.launches = 0
+        self.density_ms, self.density_launches = 0.0, 0
 
     def init_params(self):
         self.plan.init_params(); self.launches += 1
@@ -102,7 +103,8 @@ class CudaBackend:
         """The whole run with the device-resident loop (peer mode only): no host synchronisation between iterations, the
         convergence test runs on the replicated posteriors of every rank.  Returns (T, crit, n_iter, converged, status)."""
         res = self.plan.nem_sharded(self.bits, self.row_offset, self.graph, beta, itermax, cv_th, self.T[0])
-        self.launches += 5 + 10 * (res.n_iter + 1) + 9
+        self.density_ms, self.density_launches = self.density_ms + res.density_ms, self.density_launches + res.density_launches
+        self.launches += 5 + 5 * (res.n_iter + 1) + 3     # see csrc/nemb200_batch.inc: start, per iteration, criteria + collect
         return self.T[0], list(res.crit), int(res.n_iter), bool(res.converged), int(res.status)
 
 

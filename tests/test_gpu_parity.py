@@ -760,7 +760,8 @@ def test_high_degree_rows_match_strict_oracle(eng, K, fd):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", ["graph_K3", "graph_skd", "sweep_K7", "sweep_K20", "large_ring", "large_K12"])
+@pytest.mark.parametrize("shape", ["graph_K3", "graph_skd", "sweep_K7", "sweep_K20", "large_ring", "large_K12", "deep_K3", "chain_K3",
+                                   "chain_skd"])
 def test_device_resident_loop_equals_host_polled_driver(eng, shape, monkeypatch):
     """The device-resident EM loop (nemb200_batch.inc: one launch per phase, convergence decided on the device, the host
     one iteration behind) against the host-polled driver (NEMB200_NO_BATCH=1: one flag read per iteration): same kernels'
@@ -770,8 +771,19 @@ def test_device_resident_loop_equals_host_polled_driver(eng, shape, monkeypatch)
         sp = synth_pangenome_blocked(12000, 50000, seed=3)      # 75 MB of bits: the streaming (ring) kernels
         K, beta, fd, itermax, flags = (3 if shape == "large_ring" else 12), sp.beta_eff(2.5), False, 6, eng.EPI_LOGSPACE
     else:
-        sp = synth_pangenome(4000, 300, seed=77)
+        # deep_*: family order that follows the genomes (dozens of thin levels); chain_*: one row per level -- the device loop
+        # sweeps those speculatively from the start sweep on, the host-polled driver level by level
+        sp = synth_pangenome(4000, 300, seed=77, chain_order=shape.startswith(("deep", "chain")))
+        if shape.startswith("chain"):
+            n = sp.N
+            deg = np.full(n, 2); deg[0] = deg[-1] = 1
+            sp.rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+            sp.col = np.concatenate([[1]] + [[i - 1, i + 1] for i in range(1, n - 1)] + [[n - 2]]).astype(np.int32)
+            sp.w = np.full(len(sp.col), 0.5, np.float32)
         K, beta, fd, itermax, flags = {"graph_K3": (3, sp.beta_eff(2.5), False, 100, eng.EPI_REF),
+                                       "deep_K3": (3, sp.beta_eff(2.5), False, 100, eng.EPI_REF),
+                                       "chain_K3": (3, 2.5, False, 100, eng.EPI_REF),
+                                       "chain_skd": (3, 2.5, True, 100, eng.EPI_REF),
                                        "graph_skd": (4, sp.beta_eff(2.5), True, 100, eng.EPI_REF),
                                        "sweep_K7": (7, 0.0, False, 10, eng.EPI_REF),
                                        "sweep_K20": (20, 0.0, False, 10, eng.EPI_REF)}[shape]
