@@ -358,7 +358,12 @@ def run_ours(a):
     if sampler:
         sampler.start()
     dens["ms"], dens["n"] = 0.0, 0
+    profile_region = os.environ.get("NEMB200_BENCH_PROFILE") is not None   # ncu --profile-from-start off: only the timed region
+    if profile_region:
+        torch.cuda.profiler.start()
     ms_total, per_run, em_ms, run_ms, launches = timed_runs(run_default, a.steps, barrier, torch, st)
+    if profile_region:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if sampler else None
     dens_ms, dens_n = dens["ms"], dens["n"]
     ms_full, per_run_full, em_ms_full, _, _ = timed_runs(run_full, a.steps, barrier, torch, st)
