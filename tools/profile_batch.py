@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """One profiled call of a batched workload, bracketed by cudaProfilerStart/Stop (run under
 `ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv`).
-usage: tools/profile_batch.py chunk16|chunk16fd|cfg3|cfg2|cfg5"""
+usage: tools/profile_batch.py chunk16|chunk16fd|cfg3|cfg2|cfg5|shard25k"""
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -25,8 +25,8 @@ elif mode == "cfg3":
     inp = engine.DeviceInput.from_numpy(sp.bits, sp.D, sp.rowptr, sp.col, sp.w)
     inst = [(inp, k, 0.0, False, 10) for k in range(2, 21)]
     call = lambda: engine.nem_run_batch(inst, want_params=False)
-elif mode == "cfg5":
-    sp = synth_pangenome_large(200000, 50000, seed=42, device=dev)
+elif mode in ("cfg5", "shard25k"):       # shard25k: the rows one of 8 ranks holds of the benchmark instance
+    sp = synth_pangenome_large(200000 if mode == "cfg5" else 25000, 50000, seed=42, device=dev)
     g = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), sp.D, sp.rowptr, sp.col, sp.w, device=dev)
     inp = engine.DeviceInput(sp.bits, sp.D, g.rowptr, g.col, g.w, g.sched_ptr, g.sched_rows, g.n_levels)
     be = sp.beta_eff(2.5)
