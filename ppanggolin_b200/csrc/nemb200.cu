@@ -905,10 +905,15 @@ extern "C" int nemb200_sweep(nemb200_plan* pl, int64_t N, const double* logf, co
     long long blocks = (N + rows_per_block - 1) / rows_per_block;
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    if (GS == 4) k_sweep<false, 4><<<(unsigned)blocks, 256, 0, st>>>(a);
-    else if (GS == 8) k_sweep<false, 8><<<(unsigned)blocks, 256, 0, st>>>(a);
-    else if (GS == 16) k_sweep<false, 16><<<(unsigned)blocks, 256, 0, st>>>(a);
-    else k_sweep<false, 32><<<(unsigned)blocks, 256, 0, st>>>(a);
+    const size_t smem = (size_t)a.K * 256 * sizeof(double);   // sweep_independent_body (no neighbour term): a row's per-class terms
+    if (smem > 48 * 1024) {
+      const void* fn = GS == 16 ? (const void*)k_sweep<false, 16> : (const void*)k_sweep<false, 32>;
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (GS == 4) k_sweep<false, 4><<<(unsigned)blocks, 256, smem, st>>>(a);
+    else if (GS == 8) k_sweep<false, 8><<<(unsigned)blocks, 256, smem, st>>>(a);
+    else if (GS == 16) k_sweep<false, 16><<<(unsigned)blocks, 256, smem, st>>>(a);
+    else k_sweep<false, 32><<<(unsigned)blocks, 256, smem, st>>>(a);
     CK(cudaGetLastError());
   }
   return NEMB200_OK;

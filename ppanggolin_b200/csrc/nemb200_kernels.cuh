@@ -952,6 +952,73 @@ struct InstBar {
   }
 };
 
+// Sweep without a neighbour term (beta = 0: the K-selection sweep of partition.py:482-514 and the blind start sweep of every
+// run, nem_alg.c:2043-2046): rows are independent, so a THREAD owns a row and walks its classes -- every lane busy and no
+// shuffles, where the lane-per-class layout spends K dependent double shuffles per row on the reference's sequential sum
+// (at K = 20: 12 of 32 lanes idle).  The per-class terms wait in shared memory ([class][thread]: conflict-free) for the
+// row's sum, which keeps the kernel at ~50 registers (held in registers they cost 154 and the occupancy with them: 122 us
+// per sweep of 4 x 50 000 rows at K = 17..20, ncu: 2 warps per scheduler, issue slots 20 % busy).  Same expressions in the
+// same order as sweep_finish with ctx = 0 (x * exp(0) = x and x + 0.0 = x exactly): identical bits.
+// Dynamic shared memory: K * blockDim.x doubles.
+template <int KB>
+__device__ __forceinline__ void sweep_independent_body(const SweepArgs& a) {
+  extern __shared__ double s_terms[];
+  const int K = a.K;
+  double* mine = s_terms + threadIdx.x;
+  const int pitch = blockDim.x;
+  float wmax = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
+    const double* lfp = a.logf + (size_t)i * K;
+    double cum = 0.0, m = -INFINITY;
+    if (!a.logspace) {
+#pragma unroll 4
+      for (int k = 0; k < K; k++) {
+        const double lf = lfp[k];
+        const float lf32 = (float)lf;
+        const double f = (lf == -INFINITY) ? 0.0 : exp((double)lf32);
+        const double v = (double)a.pk[k] * f;
+        mine[k * pitch] = v;
+        cum = cum + v;
+      }
+    } else {
+#pragma unroll 4
+      for (int k = 0; k < K; k++) {
+        const double av = a.logpk64[k] + lfp[k];
+        mine[k * pitch] = av;
+        m = fmax(m, av);
+      }
+#pragma unroll 4
+      for (int k = 0; k < K; k++) {
+        const double e = (m > -INFINITY) ? exp(mine[k * pitch] - m) : 0.0;
+        mine[k * pitch] = e;
+        cum = cum + e;
+      }
+    }
+#pragma unroll 4
+    for (int k = 0; k < K; k++) {
+      const double v = mine[k * pitch];
+      float cnew;
+      if (!a.logspace) {
+        if (cum > 0) {
+          if (cum > kEps) { const double invZ = 1 / cum; cnew = (float)(invZ * v); }
+          else { const double invZ = 1 / (cum / kEps); cnew = (float)(invZ * (v / kEps)); }
+        } else {
+          cnew = (float)(1.0 / K);
+        }
+      } else {
+        cnew = (m == -INFINITY) ? (float)(1.0 / K) : (float)(v / cum);
+      }
+      const float told = a.T_old[(size_t)i * K + k];
+      __stcg(a.T_new + (size_t)i * K + k, cnew);
+      float dif = cnew - told;
+      if (dif < 0) dif = -dif;
+      wmax = fmaxf(wmax, dif);
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+  if ((threadIdx.x & 31) == 0 && wmax > 0.0f) atomicMax(a.maxdiff_bits, __float_as_uint(wmax));
+}
+
 constexpr int kSpecVeryDeep = 64;
 
 template <bool COOP, int GS, class Bar>
@@ -967,6 +1034,10 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const Bar& bar) {
   if (a.wait_sig != nullptr) {     // every CTA checks the flags itself (phase 1 = densities): no wait kernel in front
     peer_wait_lane(a.wait_sig, a.wait_n, 1, a.wait_epoch, a.wait_err);
     __syncthreads();
+  }
+  if (!COOP && (a.beta == 0.0f || a.rowptr == nullptr) && a.chg == nullptr) {   // no neighbour term: a thread per row
+    sweep_independent_body<GS>(a);
+    return;
   }
   bool spec = false;
   // speculation pays where the level-scheduled sweep is latency (few passes of the grid per level); a batch whose instances
