@@ -62,13 +62,16 @@ struct Params {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// Row-sharded multi-GPU exchange over NVLink peer memory (no collective library on the data path):
+// Row-sharded multi-GPU exchange over NVLink peer memory (no collective library on the data path).
+// Stepwise interface (host-polled driver, nem/sharded.py):
 //  * k_peer_broadcast pushes the shard of log-densities a rank has just computed into the logf buffer of EVERY rank
 //    (16-byte peer stores), which is the all-gather the replicated Gauss-Seidel sweep needs;
 //  * k_mstep_finalize reads the column statistics of every rank (peer loads) and adds them in rank order, which is the
 //    all-reduce of the M-step, fused into the consuming kernel (same order on every rank -> identical parameters);
 //  * two flag barriers per iteration order those accesses: k_peer_signal_wait in front of k_mstep_finalize; the last
 //    CTA of k_peer_broadcast signals the densities, and the sweep kernel's CTAs wait for them (peer_wait_lane).
+// Device-resident loop (nemb200_nem_sharded): the M-step exchange is k_b_finalize_ll ({payload, epoch} words, no fence, no
+// flag: see LLayout), the all-gather of the log-densities is the epilogue of k_b_density_ring.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 struct PeerOut {            // k_peer_broadcast: ptr[1..n-1] = the peers' buffers; row_off = first double of the shard
@@ -1823,9 +1826,6 @@ constexpr int kFinCols = 256;     // one column per thread: the kernel is a chai
 __device__ __forceinline__ void finalize_class_scalars(const Params& P, int k, double nk, int nchunk, const double* __restrict__ partial,
                                                        long long N_total, int lane);
 
-// With `pp` (row-sharded run, device-resident loop) the column chunks are dealt out to the ranks: a rank reduces only its
-// chunks (1 / n of the peer loads) and writes their centres, planes, dispersions and partial sums into EVERY rank's
-// parameter block (peer stores); the class scalars follow in finalize_scalars_body after a flag barrier.
 // size of class k over all ranks (rank order: the same value on every rank); every peer load in flight at once
 __device__ __forceinline__ double class_size_all_ranks(const PeerStats& ps, size_t KD, int k) {
   int ni[kMaxPeers];
@@ -1842,6 +1842,10 @@ __device__ __forceinline__ double class_size_all_ranks(const PeerStats& ps, size
   return (double)nk_i + nk_f;
 }
 
+// With `pp` and `fs` (row-sharded run with NEMB200_LL=0: the flag-barrier variant kept for comparison with k_b_finalize_ll)
+// the column chunks are dealt out to the ranks: after the first flag barrier a rank reduces only its chunks (1 / n of the
+// peer loads) and writes their centres, planes, dispersions and partial sums into EVERY rank's parameter block (peer
+// stores); after the second barrier the last CTA derives the class scalars.
 __device__ __forceinline__ void
 mstep_finalize_body(const Params& P, const PeerStats& ps, long long N_total, double* __restrict__ partial /*[K][nchunk][2]*/,
                     int* __restrict__ tickets /*[K]*/, const PeerParams* pp = nullptr, const FinSync* fs = nullptr) {
