@@ -589,11 +589,34 @@ k_density_sk_ring(const uint4* __restrict__ bits, long long N, int W4, int K, in
 // each M-step: K x D/4 x 16 doubles, 48 KB for a 500-genome chunk instance).  Rows that match their class or mismatch
 // almost everywhere (the common cases) cost 0-2 lookups per word, mixed rows at most 8.  +inf entries (e_kd <= 1e-20)
 // propagate to the reference's null density; a word whose total is infinite is summed directly.
-template <int KB>
+// SMEM: the CTA first copies the instance's tables (K x Ws x 128 doubles: 48 KB at K = 3, 500 genomes), plane words and word
+// totals into dynamic shared memory and looks them up there.  ncu on the global-memory version at 16 x (100 000 x 500): the
+// kernel is bound by L1 sector throughput -- every lookup instruction touches 32 different sectors -- not by latency; shared
+// memory serves the same scattered 8-byte reads at a few bank conflicts each.  Same tables, same order of additions:
+// identical sums.
+template <int KB, bool SMEM = false>
 __device__ __forceinline__ void
 density_skd_body(const uint32_t* __restrict__ bits, long long N, int Ws, int K, int G,
                  const uint32_t* __restrict__ m1, const uint32_t* __restrict__ valid, const double* __restrict__ Ltab /*[K][Ws*8][16]*/,
                  const double* __restrict__ Lword /*[K][Ws]*/, const double* __restrict__ B, double* __restrict__ logf) {
+  extern __shared__ double s_skd[];
+  const double* tabs = Ltab;
+  const double* lwords = Lword;
+  const uint32_t* pm1 = m1;
+  const uint32_t* pvalid = valid;
+  if (SMEM) {
+    const int kw = K * Ws;
+    double* s_tab = s_skd;                                       // [K][Ws][128]
+    double* s_lw = s_tab + (size_t)kw * 128;                     // [K][Ws]
+    uint32_t* s_m1 = reinterpret_cast<uint32_t*>(s_lw + kw);     // [K][Ws]
+    uint32_t* s_va = s_m1 + kw;
+    const double2* src2 = reinterpret_cast<const double2*>(Ltab);
+    double2* dst2 = reinterpret_cast<double2*>(s_tab);
+    for (int t = threadIdx.x; t < kw * 64; t += blockDim.x) dst2[t] = __ldg(src2 + t);
+    for (int t = threadIdx.x; t < kw; t += blockDim.x) { s_lw[t] = Lword[t]; s_m1[t] = m1[t]; s_va[t] = valid[t]; }
+    __syncthreads();
+    tabs = s_tab; lwords = s_lw; pm1 = s_m1; pvalid = s_va;
+  }
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
   const int grp = lane / G;
@@ -611,20 +634,20 @@ density_skd_body(const uint32_t* __restrict__ bits, long long N, int Ws, int K, 
 #pragma unroll
         for (int k = 0; k < KB; k++) {
           if (k < K) {
-            const uint32_t mm = (x ^ m1[k * Ws + c]) & valid[k * Ws + c];   // mismatching columns
-            if (mm != 0u) {
-              const double* tab = Ltab + ((size_t)k * Ws + c) * 128;
-              const double lw = Lword[(size_t)k * Ws + c];     // all 32 columns of the word (padding and mu = 0.5 included)
-              const bool direct = __popc(mm) <= 16 || isinf(lw);
-              uint32_t it = direct ? mm : ~mm;                  // the complement holds matches, mu = 0.5 and padding columns
-              double acc = 0.0;
-              while (it) {
-                const int q = (__ffs(it) - 1) >> 2;
-                acc += __ldg(tab + q * 16 + ((it >> (4 * q)) & 15u));
-                it &= ~(15u << (4 * q));
-              }
-              s[k] += direct ? acc : lw - acc;
+            const uint32_t mm = (x ^ pm1[k * Ws + c]) & pvalid[k * Ws + c];   // mismatching columns
+            const double* tab = tabs + ((size_t)k * Ws + c) * 128;
+            const double lw = lwords[(size_t)k * Ws + c];      // all 32 columns of the word (padding and mu = 0.5 included)
+            const bool direct = __popc(mm) <= 16 || isinf(lw);
+            const uint32_t it = direct ? mm : ~mm;              // the complement holds matches, mu = 0.5 and padding columns
+            // the non-zero nibbles in ascending order, as predicated lookups: eight independent loads and one chain of adds
+            // per class instead of a data-dependent loop (lanes of a warp hold different words; a zero nibble adds nothing)
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const uint32_t nib = (it >> (4 * q)) & 15u;
+              if (nib != 0u) acc += SMEM ? tab[q * 16 + nib] : __ldg(tab + q * 16 + nib);
             }
+            if (mm != 0u) s[k] += direct ? acc : lw - acc;
           }
         }
       }
@@ -3096,11 +3119,11 @@ __global__ void __launch_bounds__(kOhTpb, 1) k_b_onehot_ring(const BatchInst* __
   mstep_onehot_ring_body(reinterpret_cast<const uint4*>(I.bits), I.Ws / 4, tile_w, I.K, I.offsets, I.perm, I.cnt, I.Dpad, slice_rows);
 }
 
-template <int KB>
+template <int KB, bool SMEM>
 __global__ void __launch_bounds__(256) k_b_density_skd(const BatchInst* __restrict__ B, int G, int gate) {
   const BatchInst& I = B[blockIdx.z];
   if (gate && !b_active(I)) return;
-  density_skd_body<KB>(I.bits, I.N_loc, I.Ws, I.K, G, I.P.m1, I.P.valid, I.Ltab, I.Lword, I.P.B, I.logf_loc);
+  density_skd_body<KB, SMEM>(I.bits, I.N_loc, I.Ws, I.K, G, I.P.m1, I.P.valid, I.Ltab, I.Lword, I.P.B, I.logf_loc);
 }
 
 // row-sharded runs, start of a run: no rank may overwrite the others' log-densities (push) while they still read them for
