@@ -25,12 +25,12 @@ elif mode == "cfg3":
     inp = engine.DeviceInput.from_numpy(sp.bits, sp.D, sp.rowptr, sp.col, sp.w)
     inst = [(inp, k, 0.0, False, 10) for k in range(2, 21)]
     call = lambda: engine.nem_run_batch(inst, want_params=False)
-elif mode in ("cfg5", "shard25k"):       # shard25k: the rows one of 8 ranks holds of the benchmark instance
-    sp = synth_pangenome_large(200000 if mode == "cfg5" else 25000, 50000, seed=42, device=dev)
+elif mode in ("cfg5", "shard25k", "cfg5fd"):   # shard25k: the rows one of 8 ranks holds of the benchmark instance; cfg5fd: free dispersion
+    sp = synth_pangenome_large(25000 if mode == "shard25k" else 200000, 50000, seed=42, device=dev)
     g = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), sp.D, sp.rowptr, sp.col, sp.w, device=dev)
     inp = engine.DeviceInput(sp.bits, sp.D, g.rowptr, g.col, g.w, g.sched_ptr, g.sched_rows, g.n_levels)
     be = sp.beta_eff(2.5)
-    call = lambda: [engine.nem_run_device(inp, 3, be, flags=engine.EPI_LOGSPACE, want_params=False)]
+    call = lambda: [engine.nem_run_device(inp, 3, be, mode == "cfg5fd", 100, flags=engine.EPI_LOGSPACE, want_params=False)]
 else:
     sp = synth_pangenome(20000, 1000, seed=42)
     inp = engine.DeviceInput.from_numpy(sp.bits, sp.D, sp.rowptr, sp.col, sp.w)
