@@ -13,12 +13,13 @@ from ppanggolin_b200.synthetic import synth_pangenome, synth_pangenome_large
 mode = sys.argv[1]
 dev = torch.device("cuda", 0)
 if mode.startswith("chunk16"):
-    fd = mode.endswith("fd")
+    fd = "fd" in mode
+    kk = 5 if mode.endswith("5") else 3        # chunk16fd5: the K the K-selection picks on the synthetic configs[3] pangenome
     inst = []
     for b in range(16):
         sp = synth_pangenome_large(100000, 500, seed=100 + b, device=dev)
         g = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), sp.D, sp.rowptr, sp.col, sp.w, device=dev)
-        inst.append((engine.DeviceInput(sp.bits, sp.D, g.rowptr, g.col, g.w, g.sched_ptr, g.sched_rows, g.n_levels), 3, sp.beta_eff(2.5), fd, 100))
+        inst.append((engine.DeviceInput(sp.bits, sp.D, g.rowptr, g.col, g.w, g.sched_ptr, g.sched_rows, g.n_levels), kk, sp.beta_eff(2.5), fd, 100))
     call = lambda: engine.nem_run_batch(inst, want_params=False)
 elif mode == "cfg3":
     sp = synth_pangenome(50000, 500, seed=43)
