@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """One profiled call of a batched workload, bracketed by cudaProfilerStart/Stop (run under
 `ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv`).
-usage: tools/profile_batch.py chunk16|chunk16fd|cfg3|cfg2|cfg5|shard25k"""
+usage: tools/profile_batch.py chunk<n>[fd][5]|cfg3|cfg2|cfg5|cfg5fd|shard25k     (chunk16: 16 chunk instances, fd: free dispersion, 5: K = 5)"""
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -12,11 +12,12 @@ from ppanggolin_b200.synthetic import synth_pangenome, synth_pangenome_large
 
 mode = sys.argv[1]
 dev = torch.device("cuda", 0)
-if mode.startswith("chunk16"):
+if mode.startswith("chunk"):
     fd = "fd" in mode
     kk = 5 if mode.endswith("5") else 3        # chunk16fd5: the K the K-selection picks on the synthetic configs[3] pangenome
     inst = []
-    for b in range(16):
+    import re
+    for b in range(int(re.match(r"chunk(\d+)", mode).group(1))):
         sp = synth_pangenome_large(100000, 500, seed=100 + b, device=dev)
         g = engine.DeviceInput.from_numpy(np.zeros((1, 4), np.uint32), sp.D, sp.rowptr, sp.col, sp.w, device=dev)
         inst.append((engine.DeviceInput(sp.bits, sp.D, g.rowptr, g.col, g.w, g.sched_ptr, g.sched_rows, g.n_levels), kk, sp.beta_eff(2.5), fd, 100))
