@@ -1518,10 +1518,13 @@ mstep_onehot_ring_body(const uint4* __restrict__ bits4, int W4, int tile_w /*<= 
   constexpr uint32_t kGroupBytes = kOhRows * kOhTpb * 16;
 
   const int total = offsets[2 * K];
-  // few listed rows (steady state of the incremental update): fewer, fuller slices.  A CTA's counter flush (one RED per
-  // non-zero column of its tile and bucket, ~53 000 of them) costs as much as streaming ~200 rows, and with 64-row slices
-  // it was the whole M-step of a converging run (measured: ~70 us per iteration at 2 000 changed rows)
-  const long long S = min((long long)gridDim.y, max(1LL, ((long long)total + slice_rows - 1) / slice_rows));
+  // A CTA's counter flush (one RED per non-zero column of its tile and bucket, ~53 000 of them) costs as much as streaming
+  // ~200 rows; measured on the benchmark instance, 32 to 256 rows per slice give 41-44 us per incremental launch (the
+  // listed rows are scattered over the matrix, one 6 KB row per page), 64 being the best.
+  // slices of at most `slice_rows` rows, but no fewer slices than CTAs while a slice keeps 64 rows (a shard's full count of
+  // 25 000 rows: 148 slices of 169 rows instead of 98 of 256; a few thousand changed rows: 64-row slices)
+  const int eff_rows = min(slice_rows, max(64, (total + (int)gridDim.y - 1) / (int)gridDim.y));
+  const long long S = min((long long)gridDim.y, max(1LL, ((long long)total + eff_rows - 1) / eff_rows));
   if (blockIdx.y >= S) return;
   const int lo = (int)((long long)total * blockIdx.y / S), hi = (int)((long long)total * (blockIdx.y + 1) / S);
   if (lo >= hi) return;
